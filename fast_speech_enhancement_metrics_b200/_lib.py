@@ -1,0 +1,93 @@
+"""ctypes binding of libfsem_b200.so (C ABI declared in include/fsem.h).
+
+There is no fallback: if the shared library is missing or does not load, importing
+a metric raises.  Build it with `python -m fast_speech_enhancement_metrics_b200.build`
+(or `__graft_entry__.build()`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .design import PesqDesign, StoiDesign
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("FSEM_B200_LIB", os.path.join(HERE, "libfsem_b200.so"))
+
+FSEM_OK = 0
+FSEM_E_INVALID = -1
+FSEM_E_CUDA = -2
+FSEM_E_WORKSPACE = -3
+FSEM_E_TOO_SHORT = -4
+ITEM_OK, ITEM_TOO_SHORT, ITEM_NAN = 0, 1, 2
+
+# every symbol include/fsem.h declares
+EXPORTS = [
+    "fsem_version", "fsem_last_error", "fsem_launch_count",
+    "fsem_pesq_create", "fsem_pesq_destroy", "fsem_pesq_workspace_bytes", "fsem_pesq_score_f32",
+    "fsem_pesq_score_host_f32", "fsem_pesq_debug_taps",
+    "fsem_stoi_create", "fsem_stoi_destroy", "fsem_stoi_workspace_bytes", "fsem_stoi_score_f32",
+    "fsem_stoi_score_host_f32", "fsem_stoi_debug_taps",
+]
+
+
+class Batch(C.Structure):
+    """Mirror of fsem_batch_t."""
+    _fields_ = [
+        ("clean", C.c_void_p), ("deg", C.c_void_p), ("lengths", C.c_void_p),
+        ("batch", C.c_int64), ("n", C.c_int64), ("stride", C.c_int64),
+    ]
+
+
+class FsemError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__("libfsem_b200: %s (code %d)" % (message, code))
+        self.code = code
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "%s not found: the CUDA extension has not been built (python -m "
+            "fast_speech_enhancement_metrics_b200.build). There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, i64, i32p, fp = C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p
+    lib.fsem_version.restype = C.c_int
+    lib.fsem_last_error.restype = C.c_char_p
+    lib.fsem_launch_count.restype = C.c_int64
+    lib.fsem_pesq_create.argtypes = [C.POINTER(vp), C.POINTER(PesqDesign)]
+    lib.fsem_pesq_destroy.argtypes = [vp]
+    lib.fsem_pesq_workspace_bytes.argtypes = [vp, i64, i64]
+    lib.fsem_pesq_workspace_bytes.restype = C.c_size_t
+    lib.fsem_pesq_score_f32.argtypes = [vp, C.POINTER(Batch), fp, i32p, vp, C.c_size_t, vp]
+    lib.fsem_pesq_score_host_f32.argtypes = [vp, C.POINTER(Batch), fp, i32p]
+    lib.fsem_pesq_debug_taps.argtypes = [vp, i64, i64, vp, fp, vp, C.POINTER(i64), vp]
+    lib.fsem_stoi_create.argtypes = [C.POINTER(vp), C.POINTER(StoiDesign)]
+    lib.fsem_stoi_destroy.argtypes = [vp]
+    lib.fsem_stoi_workspace_bytes.argtypes = [vp, i64, i64]
+    lib.fsem_stoi_workspace_bytes.restype = C.c_size_t
+    lib.fsem_stoi_score_f32.argtypes = [vp, C.POINTER(Batch), fp, fp, i32p, i32p, vp, C.c_size_t, vp]
+    lib.fsem_stoi_score_host_f32.argtypes = [vp, C.POINTER(Batch), fp, fp, i32p, i32p]
+    lib.fsem_stoi_debug_taps.argtypes = [vp, i64, i64, vp, vp, fp, fp, C.POINTER(i64), vp]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if fn.restype is C.c_int and name not in ("fsem_version",):
+            fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(code: int) -> None:
+    if code != FSEM_OK:
+        msg = load().fsem_last_error()
+        raise FsemError(code, msg.decode("utf-8", "replace") if msg else "unknown error")
+
+
+def launch_count() -> int:
+    return int(load().fsem_launch_count())

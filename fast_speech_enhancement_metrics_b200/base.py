@@ -1,0 +1,89 @@
+"""Common base of the metric classes: argument checking, batching and dispatch.
+
+Mirrors fast_se_metrics/base.py:6-43 (`BaseMetric(sample_rate, use_gpu)`,
+`prepare_audio`, `prepare_inputs`, `compute_metric`, `__call__`).  Differences,
+all deliberate:
+
+* the arithmetic always runs on the current CUDA device through libfsem_b200.so;
+  `use_gpu` is kept for signature compatibility and only records where the caller
+  expects to hand tensors over (CPU tensors go through the library's host entry
+  point, which overlaps the host->device copy with compute; CUDA tensors are
+  consumed in place on the current stream).  Without a CUDA device or without the
+  built library the constructor raises -- there is no CPU fallback;
+* resample-on-ingest (base.py:19-20) is not a separate torchaudio op: STOI fuses
+  it into its first kernel;
+* optional `lengths=` (per-item valid samples of a padded batch); `None` gives
+  exactly the reference behaviour.
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+
+import torch
+
+from . import _lib
+
+
+class BaseMetric(ABC):
+    higher_is_better: bool
+    EXPECTED_SAMPLING_RATE: int
+
+    def __init__(self, sample_rate: int = 16000, use_gpu: bool = False):
+        self.sample_rate = int(sample_rate)
+        self.use_gpu = bool(use_gpu)
+        self._lib = _lib.load()                       # raises ImportError if the .so is missing
+        if not torch.cuda.is_available():
+            raise RuntimeError("fast_speech_enhancement_metrics_b200 needs a CUDA device (sm_100a); "
+                               "there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self._workspace = None
+
+    # ------------------------------------------------------------------ reference API
+    def prepare_audio(self, audio: torch.Tensor) -> torch.Tensor:
+        """base.py:16-21: at least 2-D, float32, unit stride along time.  The tensor stays
+        where it is (no implicit device move); inputs are never modified."""
+        audio = torch.atleast_2d(audio)
+        if audio.dim() != 2:
+            raise Exception("expected a [batch, samples] tensor")
+        if audio.dtype != torch.float32:
+            # the reference fails inside lfilter / stft with "expected scalar type Float"
+            raise RuntimeError("expected scalar type Float but found %s" % str(audio.dtype).replace("torch.", ""))
+        if audio.stride(1) != 1 or (audio.shape[0] > 1 and audio.stride(0) < audio.shape[1]):
+            audio = audio.contiguous()
+        return audio
+
+    def prepare_inputs(self, clean_speech, denoised_speech):
+        if clean_speech is not None and clean_speech.shape != denoised_speech.shape:
+            raise Exception("`clean_speech` and `denoised_speech` should have the same shape.")   # base.py:26-27
+        if clean_speech is not None:
+            clean_speech = self.prepare_audio(clean_speech)
+        denoised_speech = self.prepare_audio(denoised_speech)
+        if clean_speech is not None and clean_speech.device != denoised_speech.device:
+            raise Exception("`clean_speech` and `denoised_speech` should be on the same device.")
+        return clean_speech, denoised_speech
+
+    @abstractmethod
+    def compute_metric(self, clean_speech, denoised_speech, lengths=None) -> list[dict[str, float]]:
+        raise NotImplementedError
+
+    def __call__(self, clean_speech, denoised_speech, lengths=None) -> list[dict[str, float]]:
+        clean_speech, denoised_speech = self.prepare_inputs(clean_speech, denoised_speech)
+        return self.compute_metric(clean_speech, denoised_speech, lengths)
+
+    # ------------------------------------------------------------------ helpers
+    def _get_workspace(self, nbytes: int) -> torch.Tensor:
+        if self._workspace is None or self._workspace.numel() < nbytes or self._workspace.device != self.device:
+            self._workspace = None
+            self._workspace = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    @staticmethod
+    def _lengths_tensor(lengths, batch: int, n: int, device) -> torch.Tensor | None:
+        if lengths is None:
+            return None
+        t = torch.as_tensor(lengths).to(torch.int32).reshape(-1)
+        if t.numel() != batch:
+            raise Exception("`lengths` must have one entry per batch item")
+        if t.numel() and (int(t.min()) < 0 or int(t.max()) > n):
+            raise Exception("`lengths` entries must lie in [0, samples]")
+        return t.to(device).contiguous()

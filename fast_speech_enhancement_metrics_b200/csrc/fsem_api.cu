@@ -1,0 +1,624 @@
+// C ABI of libfsem_b200.so (see include/fsem.h): contexts, workspace planning, kernel launches,
+// and the host-buffer entry points with copy/compute overlap.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "fsem_common.cuh"
+#include "fsem_pesq.cuh"
+#include "fsem_stoi.cuh"
+
+using namespace fsem;
+
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define FSEM_CUDA(expr)                                                                          \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess)                                                                  \
+            return fail(FSEM_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),   \
+                        __FILE__, __LINE__);                                                     \
+    } while (0)
+
+#define FSEM_LAUNCHED()                                                                          \
+    do {                                                                                         \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                      \
+        FSEM_CUDA(cudaGetLastError());                                                           \
+    } while (0)
+
+inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct DeviceInfo {
+    int device = -1;
+    int sms = 0;
+};
+
+int query_device(DeviceInfo& d) {
+    FSEM_CUDA(cudaGetDevice(&d.device));
+    FSEM_CUDA(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, d.device));
+    return FSEM_OK;
+}
+
+// Double-buffered device staging for the host entry points.
+struct HostPipe {
+    cudaStream_t copy = nullptr, compute = nullptr;
+    cudaEvent_t copied[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
+    void* in[2] = {nullptr, nullptr};     // clean | deg | lengths of one chunk
+    size_t in_bytes = 0;
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    void* out[2] = {nullptr, nullptr};    // scores of one chunk
+    size_t out_bytes = 0;
+
+    int init() {
+        if (copy) return FSEM_OK;
+        FSEM_CUDA(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+        FSEM_CUDA(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            FSEM_CUDA(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+            FSEM_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+        }
+        return FSEM_OK;
+    }
+    int reserve(size_t in_b, size_t ws_b, size_t out_b) {
+        if (in_b > in_bytes) {
+            for (int i = 0; i < 2; ++i) {
+                if (in[i]) cudaFree(in[i]);
+                in[i] = nullptr;
+                FSEM_CUDA(cudaMalloc(&in[i], in_b));
+            }
+            in_bytes = in_b;
+        }
+        if (ws_b > ws_bytes) {
+            if (ws) cudaFree(ws);
+            ws = nullptr;
+            FSEM_CUDA(cudaMalloc(&ws, ws_b));
+            ws_bytes = ws_b;
+        }
+        if (out_b > out_bytes) {
+            for (int i = 0; i < 2; ++i) {
+                if (out[i]) cudaFree(out[i]);
+                out[i] = nullptr;
+                FSEM_CUDA(cudaMalloc(&out[i], out_b));
+            }
+            out_bytes = out_b;
+        }
+        return FSEM_OK;
+    }
+    void destroy() {
+        for (int i = 0; i < 2; ++i) {
+            if (in[i]) cudaFree(in[i]);
+            if (out[i]) cudaFree(out[i]);
+            if (copied[i]) cudaEventDestroy(copied[i]);
+            if (done[i]) cudaEventDestroy(done[i]);
+        }
+        if (ws) cudaFree(ws);
+        if (copy) cudaStreamDestroy(copy);
+        if (compute) cudaStreamDestroy(compute);
+    }
+};
+
+// items per chunk of the host pipeline: ~128 MB of input per chunk, at least 1 item
+int64_t host_chunk_items(int64_t batch, int64_t n) {
+    const int64_t bytes_per_item = 2 * n * (int64_t)sizeof(float);
+    int64_t items = (int64_t(128) << 20) / (bytes_per_item > 0 ? bytes_per_item : 1);
+    if (items < 1) items = 1;
+    if (items > batch) items = batch;
+    return items;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int fsem_version(void) { return FSEM_VERSION; }
+extern "C" const char* fsem_last_error(void) { return g_err; }
+extern "C" int64_t fsem_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+// ================================================================================================
+// PESQ
+// ================================================================================================
+struct fsem_pesq_ctx {
+    DeviceInfo dev;
+    PesqFilterCoef coef;
+    int warm = 640;
+    PesqTables* d_tab = nullptr;
+    int spec_ctas_per_sm = 2;
+    HostPipe pipe;
+};
+
+namespace {
+
+struct PesqPlan {
+    int64_t batch, n, zstride;
+    int tmax, chunk, nchunks;
+    size_t off_z, off_partial, off_bark, off_dist, off_power, total;
+};
+
+PesqPlan pesq_plan(const fsem_pesq_ctx* ctx, int64_t batch, int64_t n) {
+    PesqPlan p{};
+    p.batch = batch;
+    p.n = n;
+    p.zstride = round_up(n > 0 ? n : 1, 4);
+    p.tmax = pesq_num_frames(n);
+    if (p.tmax < 1) p.tmax = 1;
+    // chunking of the serial IIR pass: enough (signal, chunk) threads to fill the chip, chunks as
+    // long as possible (the warm-up prefix is redundant work), multiples of 64 samples
+    const int64_t target_threads = (int64_t)ctx->dev.sms * 768;
+    int64_t nch = ceil_div(target_threads, 2 * (batch > 0 ? batch : 1));
+    const int64_t max_ch = ceil_div(n > 0 ? n : 1, 1024);
+    if (nch > max_ch) nch = max_ch;
+    if (nch < 1) nch = 1;
+    int64_t chunk = round_up(ceil_div(n > 0 ? n : 1, nch), 64);
+    nch = ceil_div(n > 0 ? n : 1, chunk);
+    p.chunk = (int)chunk;
+    p.nchunks = (int)nch;
+    size_t off = 0;
+    p.off_z = off;       off = align256(off + sizeof(float) * 2 * batch * p.zstride);
+    p.off_partial = off; off = align256(off + sizeof(double) * 2 * batch * p.nchunks);
+    p.off_bark = off;    off = align256(off + sizeof(float) * 2 * batch * p.tmax * FSEM_PESQ_NBANDS);
+    p.off_dist = off;    off = align256(off + sizeof(float) * 2 * batch * p.tmax);
+    p.off_power = off;   off = align256(off + sizeof(double) * 2 * batch);
+    p.total = off;
+    return p;
+}
+
+}  // namespace
+
+extern "C" int fsem_pesq_create(fsem_pesq_ctx_t** out, const fsem_pesq_design_t* d) {
+    if (!out || !d) return fail(FSEM_E_INVALID, "fsem_pesq_create: null argument");
+    *out = nullptr;
+    fsem_pesq_ctx* ctx = new (std::nothrow) fsem_pesq_ctx();
+    if (!ctx) return fail(FSEM_E_INVALID, "out of host memory");
+    int rc = query_device(ctx->dev);
+    if (rc != FSEM_OK) { delete ctx; return rc; }
+    ctx->coef.k = d->bp_direct;
+    for (int s = 0; s < FSEM_BP_SECTIONS; ++s) {
+        ctx->coef.c0[s] = d->bp_c0[s]; ctx->coef.c1[s] = d->bp_c1[s];
+        ctx->coef.a1[s] = d->bp_a1[s]; ctx->coef.a2[s] = d->bp_a2[s];
+    }
+    ctx->coef.pb0 = d->pre_b[0]; ctx->coef.pb1 = d->pre_b[1]; ctx->coef.pb2 = d->pre_b[2];
+    ctx->coef.pa1 = d->pre_a[0]; ctx->coef.pa2 = d->pre_a[1];
+    ctx->warm = (int)round_up(d->warmup > 0 ? d->warmup : 640, 4);
+    for (int k = 0; k < 15; ++k) {
+        if (fabsf(d->taper[k] - (float)(k + 1) * 0.0625f) > 1e-7f) {
+            delete ctx;
+            return fail(FSEM_E_INVALID, "fsem_pesq_create: taper must be k/16 (PESQ.py:90)");
+        }
+    }
+    PesqTables h{};
+    memcpy(h.hann, d->hann, sizeof(h.hann));
+    double wtot = 0.0;
+    for (int b = 0; b < FSEM_PESQ_NBANDS; ++b) {
+        h.band_first[b] = d->band_first_bin[b];
+        h.band_count[b] = d->band_num_bins[b];
+        if (h.band_first[b] < 0 || h.band_count[b] < 0 || h.band_first[b] + h.band_count[b] > 256) {
+            delete ctx;
+            return fail(FSEM_E_INVALID, "fsem_pesq_create: band %d outside bins 0..255", b);
+        }
+        h.pow_dens[b] = d->pow_dens[b];
+        h.thresh[b] = d->thresh[b];
+        h.zw_exp[b] = d->zwicker_exp[b];
+        h.width[b] = d->width_bark[b];
+        h.loud_scale[b] = (float)((double)d->sl * pow(2.0 * (double)d->thresh[b], (double)d->zwicker_exp[b]));
+        if (b >= 1) wtot += (double)d->width_bark[b];
+    }
+    h.width_total = (float)wtot;
+    cudaError_t e = cudaMalloc(&ctx->d_tab, sizeof(PesqTables));
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->d_tab, &h, sizeof(h), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (ctx->d_tab) cudaFree(ctx->d_tab);
+        delete ctx;
+        return fail(FSEM_E_CUDA, "fsem_pesq_create: %s", cudaGetErrorString(e));
+    }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pesq_spectrum_kernel, kSpecWarps * 32, 0) == cudaSuccess && occ > 0)
+        ctx->spec_ctas_per_sm = occ;
+    *out = ctx;
+    return FSEM_OK;
+}
+
+extern "C" int fsem_pesq_destroy(fsem_pesq_ctx_t* ctx) {
+    if (!ctx) return FSEM_OK;
+    ctx->pipe.destroy();
+    if (ctx->d_tab) cudaFree(ctx->d_tab);
+    delete ctx;
+    return FSEM_OK;
+}
+
+extern "C" size_t fsem_pesq_workspace_bytes(const fsem_pesq_ctx_t* ctx, int64_t batch, int64_t n) {
+    if (!ctx || batch <= 0 || n <= 0) return 0;
+    return pesq_plan(ctx, batch, n).total;
+}
+
+extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in, float* mos_out,
+                                   int32_t* status_out, void* workspace, size_t workspace_bytes,
+                                   void* stream_v) {
+    if (!ctx || !in || !mos_out) return fail(FSEM_E_INVALID, "fsem_pesq_score_f32: null argument");
+    if (in->batch < 0 || in->n < 0 || in->stride < in->n)
+        return fail(FSEM_E_INVALID, "fsem_pesq_score_f32: bad shape batch=%lld n=%lld stride=%lld",
+                    (long long)in->batch, (long long)in->n, (long long)in->stride);
+    if (in->batch == 0) return FSEM_OK;
+    if (!in->clean || !in->deg) return fail(FSEM_E_INVALID, "fsem_pesq_score_f32: null input");
+    if (in->n >= (int64_t(1) << 30)) return fail(FSEM_E_INVALID, "fsem_pesq_score_f32: n too large");
+    // without per-item lengths every item has n samples: fewer than 20 frames is the reference's
+    // RuntimeError from unfold (PESQ.py:169)
+    if (!in->lengths && pesq_num_frames(in->n) < 20)
+        return fail(FSEM_E_TOO_SHORT, "PESQ needs at least 20 frames of 512/256 samples; n=%lld gives %d",
+                    (long long)in->n, pesq_num_frames(in->n));
+    const PesqPlan p = pesq_plan(ctx, in->batch, in->n);
+    if (!workspace || workspace_bytes < p.total)
+        return fail(FSEM_E_WORKSPACE, "fsem_pesq_score_f32: workspace %zu < %zu bytes", workspace_bytes, p.total);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    char* ws = static_cast<char*>(workspace);
+    float* z = reinterpret_cast<float*>(ws + p.off_z);
+    double* partial = reinterpret_cast<double*>(ws + p.off_partial);
+    float* bark = reinterpret_cast<float*>(ws + p.off_bark);
+    float* dist = reinterpret_cast<float*>(ws + p.off_dist);
+    double* power = reinterpret_cast<double*>(ws + p.off_power);
+
+    {   // kernel A
+        const int64_t threads = 2 * in->batch * p.nchunks;
+        const unsigned grid = (unsigned)ceil_div(threads, 128);
+        const bool vec4 = aligned16(in->clean) && aligned16(in->deg) && (in->stride % 4 == 0);
+        if (vec4)
+            pesq_filter_kernel<true><<<grid, 128, 0, stream>>>(in->clean, in->deg, in->lengths, in->batch, in->n,
+                                                              in->stride, p.chunk, p.nchunks, ctx->warm, ctx->coef,
+                                                              z, p.zstride, partial);
+        else
+            pesq_filter_kernel<false><<<grid, 128, 0, stream>>>(in->clean, in->deg, in->lengths, in->batch, in->n,
+                                                               in->stride, p.chunk, p.nchunks, ctx->warm, ctx->coef,
+                                                               z, p.zstride, partial);
+        FSEM_LAUNCHED();
+    }
+    {   // kernel B
+        const int64_t units = in->batch * (int64_t)p.tmax;
+        int64_t grid = ceil_div(units, kSpecWarps);
+        const int64_t cap = (int64_t)ctx->dev.sms * ctx->spec_ctas_per_sm;
+        if (grid > cap) grid = cap;
+        pesq_spectrum_kernel<<<(unsigned)grid, kSpecWarps * 32, 0, stream>>>(z, p.zstride, in->lengths, in->batch,
+                                                                            in->n, p.tmax, ctx->d_tab, bark);
+        FSEM_LAUNCHED();
+    }
+    {   // kernel C
+        pesq_bark_kernel<<<(unsigned)in->batch, kBarkThreads, 0, stream>>>(bark, partial, p.nchunks, in->lengths,
+                                                                          in->batch, in->n, p.tmax, ctx->d_tab, dist,
+                                                                          mos_out, status_out, power);
+        FSEM_LAUNCHED();
+    }
+    return FSEM_OK;
+}
+
+extern "C" int fsem_pesq_debug_taps(fsem_pesq_ctx_t* ctx, int64_t batch, int64_t n, const void* workspace,
+                                    float* bark_out, double* power_out, int64_t* frames_out, void* stream_v) {
+    if (!ctx || !workspace) return fail(FSEM_E_INVALID, "fsem_pesq_debug_taps: null argument");
+    const PesqPlan p = pesq_plan(ctx, batch, n);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    const char* ws = static_cast<const char*>(workspace);
+    if (frames_out) *frames_out = p.tmax;
+    if (bark_out)
+        FSEM_CUDA(cudaMemcpyAsync(bark_out, ws + p.off_bark, sizeof(float) * 2 * batch * p.tmax * FSEM_PESQ_NBANDS,
+                                  cudaMemcpyDeviceToDevice, stream));
+    if (power_out)
+        FSEM_CUDA(cudaMemcpyAsync(power_out, ws + p.off_power, sizeof(double) * 2 * batch, cudaMemcpyDeviceToDevice,
+                                  stream));
+    return FSEM_OK;
+}
+
+extern "C" int fsem_pesq_score_host_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in, float* mos_out,
+                                        int32_t* status_out) {
+    if (!ctx || !in || !mos_out) return fail(FSEM_E_INVALID, "fsem_pesq_score_host_f32: null argument");
+    if (in->batch < 0 || in->n < 0 || in->stride < in->n)
+        return fail(FSEM_E_INVALID, "fsem_pesq_score_host_f32: bad shape");
+    if (in->batch == 0) return FSEM_OK;
+    if (!in->lengths && pesq_num_frames(in->n) < 20)
+        return fail(FSEM_E_TOO_SHORT, "PESQ needs at least 20 frames of 512/256 samples; n=%lld gives %d",
+                    (long long)in->n, pesq_num_frames(in->n));
+    int rc = ctx->pipe.init();
+    if (rc != FSEM_OK) return rc;
+    const int64_t n = in->n, dstride = round_up(n, 4);
+    const int64_t per = host_chunk_items(in->batch, n);
+    const size_t sig_bytes = align256(sizeof(float) * per * dstride);
+    const size_t in_bytes = 2 * sig_bytes + align256(sizeof(int32_t) * per);
+    const size_t ws_bytes = fsem_pesq_workspace_bytes(ctx, per, n);
+    const size_t out_bytes = align256(sizeof(float) * per) + align256(sizeof(int32_t) * per);
+    rc = ctx->pipe.reserve(in_bytes, ws_bytes, out_bytes);
+    if (rc != FSEM_OK) return rc;
+    HostPipe& P = ctx->pipe;
+    int64_t done_chunks = 0;
+    for (int64_t i0 = 0; i0 < in->batch; i0 += per, ++done_chunks) {
+        const int slot = (int)(done_chunks & 1);
+        const int64_t cnt = (in->batch - i0 < per) ? (in->batch - i0) : per;
+        char* base = static_cast<char*>(P.in[slot]);
+        float* d_clean = reinterpret_cast<float*>(base);
+        float* d_deg = reinterpret_cast<float*>(base + sig_bytes);
+        int32_t* d_len = reinterpret_cast<int32_t*>(base + 2 * sig_bytes);
+        float* d_mos = reinterpret_cast<float*>(P.out[slot]);
+        int32_t* d_status = reinterpret_cast<int32_t*>(static_cast<char*>(P.out[slot]) + align256(sizeof(float) * per));
+        if (done_chunks >= 2) FSEM_CUDA(cudaStreamWaitEvent(P.copy, P.done[slot], 0));   // staging slot free again
+        FSEM_CUDA(cudaMemcpy2DAsync(d_clean, dstride * sizeof(float), in->clean + i0 * in->stride,
+                                    in->stride * sizeof(float), n * sizeof(float), cnt, cudaMemcpyHostToDevice, P.copy));
+        FSEM_CUDA(cudaMemcpy2DAsync(d_deg, dstride * sizeof(float), in->deg + i0 * in->stride,
+                                    in->stride * sizeof(float), n * sizeof(float), cnt, cudaMemcpyHostToDevice, P.copy));
+        if (in->lengths)
+            FSEM_CUDA(cudaMemcpyAsync(d_len, in->lengths + i0, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, P.copy));
+        FSEM_CUDA(cudaEventRecord(P.copied[slot], P.copy));
+        FSEM_CUDA(cudaStreamWaitEvent(P.compute, P.copied[slot], 0));
+        fsem_batch_t dev{d_clean, d_deg, in->lengths ? d_len : nullptr, cnt, n, dstride};
+        rc = fsem_pesq_score_f32(ctx, &dev, d_mos, d_status, P.ws, P.ws_bytes, P.compute);
+        if (rc != FSEM_OK) { cudaStreamSynchronize(P.copy); cudaStreamSynchronize(P.compute); return rc; }
+        FSEM_CUDA(cudaMemcpyAsync(mos_out + i0, d_mos, sizeof(float) * cnt, cudaMemcpyDeviceToHost, P.compute));
+        if (status_out)
+            FSEM_CUDA(cudaMemcpyAsync(status_out + i0, d_status, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, P.compute));
+        FSEM_CUDA(cudaEventRecord(P.done[slot], P.compute));
+    }
+    FSEM_CUDA(cudaStreamSynchronize(P.copy));
+    FSEM_CUDA(cudaStreamSynchronize(P.compute));
+    return FSEM_OK;
+}
+
+// ================================================================================================
+// STOI
+// ================================================================================================
+struct fsem_stoi_ctx {
+    DeviceInfo dev;
+    int orig = 1, neu = 1, width = 0, ntaps = 0;
+    float* d_taps = nullptr;
+    StoiTables* d_tab = nullptr;
+    float clip = 0.f, dyn_range = 40.f;
+    int tob_ctas_per_sm = 2;
+    HostPipe pipe;
+};
+
+namespace {
+
+struct StoiPlan {
+    int64_t batch, n, lmax, ystride;
+    int t0max, mask_words, umax, ustride, mmax, ntiles;
+    bool resample;
+    size_t off_y, off_energy, off_idx, off_count, off_mask, off_tob, off_partial, total;
+};
+
+StoiPlan stoi_plan(const fsem_stoi_ctx* ctx, int64_t batch, int64_t n) {
+    StoiPlan p{};
+    p.batch = batch;
+    p.n = n;
+    p.resample = ctx->orig != ctx->neu;
+    p.lmax = stoi_resampled_len(n, ctx->orig, ctx->neu);
+    p.ystride = round_up(p.lmax > 0 ? p.lmax : 1, 4);
+    p.t0max = stoi_num_frames(p.lmax);
+    if (p.t0max < 1) p.t0max = 1;
+    p.mask_words = (int)ceil_div(p.t0max, 32);
+    p.umax = p.t0max - 2 > 0 ? p.t0max - 2 : 0;
+    p.ustride = (int)round_up(p.umax > 0 ? p.umax : 1, 4);
+    p.mmax = p.t0max - 31 > 0 ? p.t0max - 31 : 0;
+    p.ntiles = (int)ceil_div(p.mmax > 0 ? p.mmax : 1, kSegTile);
+    size_t off = 0;
+    p.off_y = off;       off = align256(off + (p.resample ? sizeof(float) * 2 * batch * p.ystride : 0));
+    p.off_energy = off;  off = align256(off + sizeof(float) * batch * p.t0max);
+    p.off_idx = off;     off = align256(off + sizeof(int32_t) * batch * p.t0max);
+    p.off_count = off;   off = align256(off + sizeof(int32_t) * batch);
+    p.off_mask = off;    off = align256(off + sizeof(uint32_t) * batch * p.mask_words);
+    p.off_tob = off;     off = align256(off + sizeof(float) * 2 * batch * FSEM_STOI_NBANDS * p.ustride);
+    p.off_partial = off; off = align256(off + sizeof(float2) * batch * p.ntiles);
+    p.total = off;
+    return p;
+}
+
+}  // namespace
+
+extern "C" int fsem_stoi_create(fsem_stoi_ctx_t** out, const fsem_stoi_design_t* d) {
+    if (!out || !d) return fail(FSEM_E_INVALID, "fsem_stoi_create: null argument");
+    *out = nullptr;
+    if (d->orig <= 0 || d->neu <= 0) return fail(FSEM_E_INVALID, "fsem_stoi_create: bad rates");
+    if (d->orig != d->neu && (!d->taps || d->ntaps != 2 * d->width + d->orig || d->width < 0))
+        return fail(FSEM_E_INVALID, "fsem_stoi_create: bad resampling kernel (ntaps must be 2*width+orig)");
+    for (int b = 0; b < FSEM_STOI_NBANDS; ++b)
+        if (d->band_lo[b] < 0 || d->band_hi[b] < d->band_lo[b] || d->band_hi[b] > 256)
+            return fail(FSEM_E_INVALID, "fsem_stoi_create: band %d outside bins 0..255", b);
+    fsem_stoi_ctx* ctx = new (std::nothrow) fsem_stoi_ctx();
+    if (!ctx) return fail(FSEM_E_INVALID, "out of host memory");
+    int rc = query_device(ctx->dev);
+    if (rc != FSEM_OK) { delete ctx; return rc; }
+    ctx->orig = d->orig; ctx->neu = d->neu; ctx->width = d->width; ctx->ntaps = d->ntaps;
+    ctx->clip = d->clip; ctx->dyn_range = d->dyn_range;
+    StoiTables h{};
+    memcpy(h.window, d->window, sizeof(h.window));
+    for (int b = 0; b < FSEM_STOI_NBANDS; ++b) { h.band_lo[b] = d->band_lo[b]; h.band_hi[b] = d->band_hi[b]; }
+    h.clip = d->clip; h.dyn_range = d->dyn_range;
+    cudaError_t e = cudaMalloc(&ctx->d_tab, sizeof(StoiTables));
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->d_tab, &h, sizeof(h), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && d->orig != d->neu) {
+        e = cudaMalloc(&ctx->d_taps, sizeof(float) * d->neu * d->ntaps);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(ctx->d_taps, d->taps, sizeof(float) * d->neu * d->ntaps, cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        if (ctx->d_tab) cudaFree(ctx->d_tab);
+        if (ctx->d_taps) cudaFree(ctx->d_taps);
+        delete ctx;
+        return fail(FSEM_E_CUDA, "fsem_stoi_create: %s", cudaGetErrorString(e));
+    }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stoi_tob_kernel, kTobWarps * 32, 0) == cudaSuccess && occ > 0)
+        ctx->tob_ctas_per_sm = occ;
+    *out = ctx;
+    return FSEM_OK;
+}
+
+extern "C" int fsem_stoi_destroy(fsem_stoi_ctx_t* ctx) {
+    if (!ctx) return FSEM_OK;
+    ctx->pipe.destroy();
+    if (ctx->d_tab) cudaFree(ctx->d_tab);
+    if (ctx->d_taps) cudaFree(ctx->d_taps);
+    delete ctx;
+    return FSEM_OK;
+}
+
+extern "C" size_t fsem_stoi_workspace_bytes(const fsem_stoi_ctx_t* ctx, int64_t batch, int64_t n) {
+    if (!ctx || batch <= 0 || n <= 0) return 0;
+    return stoi_plan(ctx, batch, n).total;
+}
+
+extern "C" int fsem_stoi_score_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t* in, float* stoi_out,
+                                   float* estoi_out, int32_t* kept_frames_out, int32_t* status_out,
+                                   void* workspace, size_t workspace_bytes, void* stream_v) {
+    if (!ctx || !in || !stoi_out || !estoi_out) return fail(FSEM_E_INVALID, "fsem_stoi_score_f32: null argument");
+    if (in->batch < 0 || in->n < 0 || in->stride < in->n)
+        return fail(FSEM_E_INVALID, "fsem_stoi_score_f32: bad shape batch=%lld n=%lld stride=%lld",
+                    (long long)in->batch, (long long)in->n, (long long)in->stride);
+    if (in->batch == 0) return FSEM_OK;
+    if (!in->clean || !in->deg) return fail(FSEM_E_INVALID, "fsem_stoi_score_f32: null input");
+    if (in->n >= (int64_t(1) << 30)) return fail(FSEM_E_INVALID, "fsem_stoi_score_f32: n too large");
+    const StoiPlan p = stoi_plan(ctx, in->batch, in->n);
+    if (!workspace || workspace_bytes < p.total)
+        return fail(FSEM_E_WORKSPACE, "fsem_stoi_score_f32: workspace %zu < %zu bytes", workspace_bytes, p.total);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    char* ws = static_cast<char*>(workspace);
+    float* y = reinterpret_cast<float*>(ws + p.off_y);
+    float* energy = reinterpret_cast<float*>(ws + p.off_energy);
+    int32_t* kept_idx = reinterpret_cast<int32_t*>(ws + p.off_idx);
+    int32_t* kept_count = reinterpret_cast<int32_t*>(ws + p.off_count);
+    uint32_t* mask = reinterpret_cast<uint32_t*>(ws + p.off_mask);
+    float* tob = reinterpret_cast<float*>(ws + p.off_tob);
+    float2* partial = reinterpret_cast<float2*>(ws + p.off_partial);
+
+    const float* c10 = in->clean;
+    const float* d10 = in->deg;
+    int64_t sstride = in->stride;
+    if (p.resample) {
+        dim3 grid((unsigned)ceil_div(p.lmax, 256), (unsigned)(2 * in->batch));
+        stoi_resample_kernel<<<grid, 256, 0, stream>>>(in->clean, in->deg, in->lengths, in->batch, in->n, in->stride,
+                                                      ctx->d_taps, ctx->orig, ctx->neu, ctx->width, ctx->ntaps, y,
+                                                      p.ystride);
+        FSEM_LAUNCHED();
+        c10 = y;
+        d10 = y + in->batch * p.ystride;
+        sstride = p.ystride;
+    }
+    {
+        const int64_t warps = in->batch * (int64_t)p.t0max;
+        stoi_energy_kernel<<<(unsigned)ceil_div(warps * 32, 256), 256, 0, stream>>>(
+            c10, sstride, in->lengths, in->batch, in->n, ctx->orig, ctx->neu, p.t0max, ctx->d_tab, energy);
+        FSEM_LAUNCHED();
+    }
+    {
+        stoi_compact_kernel<<<(unsigned)ceil_div(in->batch * 32, 128), 128, 0, stream>>>(
+            energy, in->lengths, in->batch, in->n, ctx->orig, ctx->neu, p.t0max, p.mask_words, ctx->dyn_range,
+            kept_idx, kept_count, mask);
+        FSEM_LAUNCHED();
+    }
+    if (p.umax > 0) {
+        const int64_t units = in->batch * (int64_t)p.umax;
+        int64_t grid = ceil_div(units, kTobWarps);
+        const int64_t cap = (int64_t)ctx->dev.sms * ctx->tob_ctas_per_sm;
+        if (grid > cap) grid = cap;
+        stoi_tob_kernel<<<(unsigned)grid, kTobWarps * 32, 0, stream>>>(c10, d10, sstride, in->batch, p.t0max, p.umax,
+                                                                      p.ustride, kept_idx, kept_count, ctx->d_tab, tob);
+        FSEM_LAUNCHED();
+    }
+    {
+        stoi_segment_kernel<<<(unsigned)(in->batch * p.ntiles), kSegThreads, 0, stream>>>(
+            tob, in->batch, p.ustride, p.ntiles, kept_count, ctx->clip, partial);
+        FSEM_LAUNCHED();
+        stoi_finalize_kernel<<<(unsigned)ceil_div(in->batch, 128), 128, 0, stream>>>(
+            partial, in->batch, p.ntiles, kept_count, stoi_out, estoi_out, kept_frames_out, status_out);
+        FSEM_LAUNCHED();
+    }
+    return FSEM_OK;
+}
+
+extern "C" int fsem_stoi_debug_taps(fsem_stoi_ctx_t* ctx, int64_t batch, int64_t n, const void* workspace,
+                                    uint32_t* mask_out, float* tob_out, float* resampled_out, int64_t* dims_out,
+                                    void* stream_v) {
+    if (!ctx || !workspace) return fail(FSEM_E_INVALID, "fsem_stoi_debug_taps: null argument");
+    const StoiPlan p = stoi_plan(ctx, batch, n);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    const char* ws = static_cast<const char*>(workspace);
+    if (dims_out) {
+        dims_out[0] = p.mask_words;
+        dims_out[1] = p.ustride;
+        dims_out[2] = p.resample ? p.ystride : 0;
+    }
+    if (mask_out)
+        FSEM_CUDA(cudaMemcpyAsync(mask_out, ws + p.off_mask, sizeof(uint32_t) * batch * p.mask_words,
+                                  cudaMemcpyDeviceToDevice, stream));
+    if (tob_out)
+        FSEM_CUDA(cudaMemcpyAsync(tob_out, ws + p.off_tob, sizeof(float) * 2 * batch * FSEM_STOI_NBANDS * p.ustride,
+                                  cudaMemcpyDeviceToDevice, stream));
+    if (resampled_out && p.resample)
+        FSEM_CUDA(cudaMemcpyAsync(resampled_out, ws + p.off_y, sizeof(float) * 2 * batch * p.ystride,
+                                  cudaMemcpyDeviceToDevice, stream));
+    return FSEM_OK;
+}
+
+extern "C" int fsem_stoi_score_host_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t* in, float* stoi_out,
+                                        float* estoi_out, int32_t* kept_frames_out, int32_t* status_out) {
+    if (!ctx || !in || !stoi_out || !estoi_out) return fail(FSEM_E_INVALID, "fsem_stoi_score_host_f32: null argument");
+    if (in->batch < 0 || in->n < 0 || in->stride < in->n)
+        return fail(FSEM_E_INVALID, "fsem_stoi_score_host_f32: bad shape");
+    if (in->batch == 0) return FSEM_OK;
+    int rc = ctx->pipe.init();
+    if (rc != FSEM_OK) return rc;
+    const int64_t n = in->n, dstride = round_up(n, 4);
+    const int64_t per = host_chunk_items(in->batch, n);
+    const size_t sig_bytes = align256(sizeof(float) * per * dstride);
+    const size_t in_bytes = 2 * sig_bytes + align256(sizeof(int32_t) * per);
+    const size_t ws_bytes = fsem_stoi_workspace_bytes(ctx, per, n);
+    const size_t col = align256(sizeof(float) * per);
+    const size_t out_bytes = 4 * col;
+    rc = ctx->pipe.reserve(in_bytes, ws_bytes, out_bytes);
+    if (rc != FSEM_OK) return rc;
+    HostPipe& P = ctx->pipe;
+    int64_t done_chunks = 0;
+    for (int64_t i0 = 0; i0 < in->batch; i0 += per, ++done_chunks) {
+        const int slot = (int)(done_chunks & 1);
+        const int64_t cnt = (in->batch - i0 < per) ? (in->batch - i0) : per;
+        char* base = static_cast<char*>(P.in[slot]);
+        float* d_clean = reinterpret_cast<float*>(base);
+        float* d_deg = reinterpret_cast<float*>(base + sig_bytes);
+        int32_t* d_len = reinterpret_cast<int32_t*>(base + 2 * sig_bytes);
+        char* ob = static_cast<char*>(P.out[slot]);
+        float* d_stoi = reinterpret_cast<float*>(ob);
+        float* d_estoi = reinterpret_cast<float*>(ob + col);
+        int32_t* d_kept = reinterpret_cast<int32_t*>(ob + 2 * col);
+        int32_t* d_status = reinterpret_cast<int32_t*>(ob + 3 * col);
+        if (done_chunks >= 2) FSEM_CUDA(cudaStreamWaitEvent(P.copy, P.done[slot], 0));
+        FSEM_CUDA(cudaMemcpy2DAsync(d_clean, dstride * sizeof(float), in->clean + i0 * in->stride,
+                                    in->stride * sizeof(float), n * sizeof(float), cnt, cudaMemcpyHostToDevice, P.copy));
+        FSEM_CUDA(cudaMemcpy2DAsync(d_deg, dstride * sizeof(float), in->deg + i0 * in->stride,
+                                    in->stride * sizeof(float), n * sizeof(float), cnt, cudaMemcpyHostToDevice, P.copy));
+        if (in->lengths)
+            FSEM_CUDA(cudaMemcpyAsync(d_len, in->lengths + i0, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, P.copy));
+        FSEM_CUDA(cudaEventRecord(P.copied[slot], P.copy));
+        FSEM_CUDA(cudaStreamWaitEvent(P.compute, P.copied[slot], 0));
+        fsem_batch_t dev{d_clean, d_deg, in->lengths ? d_len : nullptr, cnt, n, dstride};
+        rc = fsem_stoi_score_f32(ctx, &dev, d_stoi, d_estoi, d_kept, d_status, P.ws, P.ws_bytes, P.compute);
+        if (rc != FSEM_OK) { cudaStreamSynchronize(P.copy); cudaStreamSynchronize(P.compute); return rc; }
+        FSEM_CUDA(cudaMemcpyAsync(stoi_out + i0, d_stoi, sizeof(float) * cnt, cudaMemcpyDeviceToHost, P.compute));
+        FSEM_CUDA(cudaMemcpyAsync(estoi_out + i0, d_estoi, sizeof(float) * cnt, cudaMemcpyDeviceToHost, P.compute));
+        if (kept_frames_out)
+            FSEM_CUDA(cudaMemcpyAsync(kept_frames_out + i0, d_kept, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, P.compute));
+        if (status_out)
+            FSEM_CUDA(cudaMemcpyAsync(status_out + i0, d_status, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, P.compute));
+        FSEM_CUDA(cudaEventRecord(P.done[slot], P.compute));
+    }
+    FSEM_CUDA(cudaStreamSynchronize(P.copy));
+    FSEM_CUDA(cudaStreamSynchronize(P.compute));
+    return FSEM_OK;
+}

@@ -1,0 +1,450 @@
+// PESQ kernels (sm_100a).  Three stream-ordered launches per call:
+//
+//   pesq_filter_kernel   x -> sum(y^2) partials (10th-order band-pass, parallel form) and the
+//                        tapered + pre-emphasised signal z          (PESQ.py:92-113)
+//   pesq_spectrum_kernel z -> Hann-512/256 power spectra of (clean, degraded) packed in ONE
+//                        complex FFT per frame -> 49 Bark-band power densities (PESQ.py:123-140,
+//                        bark.py:203-204)
+//   pesq_bark_kernel     level alignment gain, band/frame equalisation, Zwicker loudness,
+//                        symmetric/asymmetric disturbance, L6/L2 aggregation, MOS mapping
+//                        (PESQ.py:142-245, loudness.py:48-67, bark.py:169-184)
+//
+// The level-alignment gain g = sqrt(1e7 / P) needs the whole-signal band power, but everything up
+// to the power spectrum is linear, so the filters/FFT run on the UNSCALED signal and the Bark
+// powers are multiplied by g^2 in the last kernel.  equalize_ranges (PESQ.py:115-121) cancels
+// algebraically against the same normalisation; its only observable effect (NaN for an all-zero
+// item) is reproduced through g^2 = inf.
+#pragma once
+#include "fsem_common.cuh"
+#include "fsem_fft.cuh"
+
+namespace fsem {
+
+// ------------------------------------------------------------------------------------------------
+// device-side constant tables (one copy per context, in global memory, read through L1/constant path)
+struct PesqTables {
+    float hann[FSEM_PESQ_NFFT];
+    int32_t band_first[FSEM_PESQ_NBANDS];
+    int32_t band_count[FSEM_PESQ_NBANDS];
+    float pow_dens[FSEM_PESQ_NBANDS];
+    float thresh[FSEM_PESQ_NBANDS];
+    float zw_exp[FSEM_PESQ_NBANDS];
+    float width[FSEM_PESQ_NBANDS];
+    float loud_scale[FSEM_PESQ_NBANDS];  // Sl * (2*thresh)^exp
+    float width_total;                   // sum_{b>=1} width
+};
+
+// filter coefficients travel as a kernel argument (constant bank)
+struct PesqFilterCoef {
+    float k;
+    float c0[FSEM_BP_SECTIONS], c1[FSEM_BP_SECTIONS], a1[FSEM_BP_SECTIONS], a2[FSEM_BP_SECTIONS];
+    float pb0, pb1, pb2, pa1, pa2;
+};
+
+struct IirState {
+    float w1[FSEM_BP_SECTIONS], w2[FSEM_BP_SECTIONS];
+    float s1, s2;
+};
+
+// one sample of the band-pass (parallel form, 22 flop-instructions): returns y
+__device__ __forceinline__ float bandpass_step(const PesqFilterCoef& P, IirState& st, float x) {
+    float acc_a = P.k * x;
+    float acc_b = 0.f;
+#pragma unroll
+    for (int s = 0; s < FSEM_BP_SECTIONS; ++s) {
+        float w = fmaf(-P.a1[s], st.w1[s], fmaf(-P.a2[s], st.w2[s], x));
+        if (s < 3) {
+            acc_a = fmaf(P.c0[s], w, acc_a);
+            acc_a = fmaf(P.c1[s], st.w1[s], acc_a);
+        } else {
+            acc_b = fmaf(P.c0[s], w, acc_b);
+            acc_b = fmaf(P.c1[s], st.w1[s], acc_b);
+        }
+        st.w2[s] = st.w1[s];
+        st.w1[s] = w;
+    }
+    return acc_a + acc_b;
+}
+
+// one sample of the pre-emphasis biquad (transposed direct form II): returns z
+__device__ __forceinline__ float preemph_step(const PesqFilterCoef& P, IirState& st, float x) {
+    float z = fmaf(P.pb0, x, st.s1);
+    st.s1 = fmaf(-P.pa1, z, fmaf(P.pb1, x, st.s2));
+    st.s2 = fmaf(-P.pa2, z, P.pb2 * x);
+    return z;
+}
+
+// taper weight of sample t in a signal of `len` samples (PESQ.py:108-109); 1 in the interior
+__device__ __forceinline__ float taper_weight(int t, int len) {
+    float w = 1.f;
+    if (t < 15) w *= (float)(t + 1) * 0.0625f;
+    if (t >= len - 15) w *= (float)(len - t) * 0.0625f;
+    return w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel A: one thread per (signal, time chunk).  The thread starts `warm` samples before its
+// chunk with zero state (both IIRs have decayed below fp32 resolution by then), walks the chunk
+// serially, accumulates y^2 and writes z.  Signals: s < B -> clean[s], else deg[s - B].
+template <bool kVec4>
+__global__ void __launch_bounds__(128)
+pesq_filter_kernel(const float* __restrict__ clean, const float* __restrict__ deg,
+                   const int32_t* __restrict__ lengths, int64_t batch, int64_t n, int64_t stride,
+                   int chunk, int nchunks, int warm, const __grid_constant__ PesqFilterCoef P,
+                   float* __restrict__ z_out, int64_t zstride, double* __restrict__ partial) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= 2 * batch * nchunks) return;
+    const int64_t sig = gid / nchunks;
+    const int c = (int)(gid - sig * nchunks);
+    const int64_t item = sig < batch ? sig : sig - batch;
+    const float* __restrict__ x = (sig < batch ? clean : deg) + item * stride;
+    float* __restrict__ z = z_out + sig * zstride;
+    const int len = item_length(lengths, item, n);
+
+    const int t_acc = c * chunk;                       // first sample owned by this thread
+    if (t_acc >= len) { partial[gid] = 0.0; return; }
+    const int t_end = min(len, t_acc + chunk);
+    int t = max(0, t_acc - warm);                       // chunk and warm are multiples of 4
+
+    IirState st;
+#pragma unroll
+    for (int s = 0; s < FSEM_BP_SECTIONS; ++s) { st.w1[s] = 0.f; st.w2[s] = 0.f; }
+    st.s1 = 0.f; st.s2 = 0.f;
+
+    auto load4 = [&](int tt, float (&v)[4]) {
+        if (kVec4 && tt + 4 <= len) {
+            float4 q = __ldg(reinterpret_cast<const float4*>(x + tt));
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = (tt + j < len) ? __ldg(x + tt + j) : 0.f;
+        }
+    };
+
+    // ---- warm-up: advance both filter states, no output
+    for (; t < t_acc; t += 4) {
+        float v[4];
+        load4(t, v);
+        const bool edge = (t < 16) || (t + 4 > len - 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            (void)bandpass_step(P, st, v[j]);
+            float xv = edge ? v[j] * taper_weight(t + j, len) : v[j];
+            (void)preemph_step(P, st, xv);
+        }
+    }
+    // ---- owned samples
+    double acc_d = 0.0;
+    float acc = 0.f;
+    int groups = 0;
+    for (; t < t_end; t += 4) {
+        float v[4], zz[4], yy[4];
+        load4(t, v);
+        const bool edge = (t < 16) || (t + 4 > len - 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            yy[j] = bandpass_step(P, st, v[j]);          // v[j] = 0 beyond len -> contributes 0 only if state..
+            float xv = edge ? v[j] * taper_weight(t + j, len) : v[j];
+            zz[j] = preemph_step(P, st, xv);
+        }
+        if (t + 4 <= t_end) {
+            acc += (yy[0] * yy[0] + yy[1] * yy[1]) + (yy[2] * yy[2] + yy[3] * yy[3]);
+            if (kVec4) {
+                *reinterpret_cast<float4*>(z + t) = make_float4(zz[0], zz[1], zz[2], zz[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) z[t + j] = zz[j];
+            }
+        } else {  // ragged tail of the signal: only samples < len count
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (t + j < t_end) { acc = fmaf(yy[j], yy[j], acc); z[t + j] = zz[j]; }
+            }
+        }
+        if (++groups == 16) { acc_d += (double)acc; acc = 0.f; groups = 0; }
+    }
+    partial[gid] = acc_d + (double)acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel B: persistent warps; one warp = one (item, frame) unit at a time.
+constexpr int kSpecWarps = 8;
+
+__global__ void __launch_bounds__(kSpecWarps * 32)
+pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t* __restrict__ lengths,
+                     int64_t batch, int64_t n, int tmax, const PesqTables* __restrict__ tab,
+                     float* __restrict__ bark /* [2][batch][tmax][49], unscaled */) {
+    __shared__ float2 s_buf[kSpecWarps][kFftBufElems];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    float2* buf = s_buf[warp];
+    float* pbuf = reinterpret_cast<float*>(buf);          // reused for the 2 x 256 power values
+
+    FftTwiddles tw;
+    tw.init(lane);
+    float win[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) win[m] = tab->hann[lane + 32 * m];
+    // this lane sums Bark bands `lane` and `lane + 32`
+    int bfirst[2], bcount[2];
+    float bscale[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        int b = lane + 32 * h;
+        bool ok = b < FSEM_PESQ_NBANDS;
+        bfirst[h] = ok ? tab->band_first[b] : 0;
+        bcount[h] = ok ? tab->band_count[b] : 0;
+        bscale[h] = ok ? tab->pow_dens[b] : 0.f;
+    }
+
+    const int64_t units = batch * (int64_t)tmax;
+    const int64_t wstride = (int64_t)gridDim.x * kSpecWarps;
+    for (int64_t u = (int64_t)blockIdx.x * kSpecWarps + warp; u < units; u += wstride) {
+        const int64_t item = u / tmax;
+        const int f = (int)(u - item * tmax);
+        const int len = item_length(lengths, item, n);
+        if (f >= pesq_num_frames(len)) continue;
+        const float* __restrict__ zc = z + item * zstride;
+        const float* __restrict__ zd = z + (batch + item) * zstride;
+        const int base = f * FSEM_PESQ_HOP + lane;
+        float re[16], im[16];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            int idx = base + 32 * m;
+            bool ok = idx < len;                         // zero padding beyond the signal (PESQ.py:128-130)
+            re[m] = ok ? __ldg(zc + idx) * win[m] : 0.f;
+            im[m] = ok ? __ldg(zd + idx) * win[m] : 0.f;
+        }
+        warp_fft512<false>(re, im, buf, tw, lane);
+        float pc[8], pd[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) packed_power(buf, lane + 32 * j, pc[j], pd[j]);
+        if (lane == 0) { pc[0] = 0.f; pd[0] = 0.f; }     // "we won't use energy feature" (PESQ.py:136)
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { pbuf[lane + 32 * j] = pc[j]; pbuf[256 + lane + 32 * j] = pd[j]; }
+        __syncwarp();
+        float* out_c = bark + (item * tmax + f) * FSEM_PESQ_NBANDS;
+        float* out_d = bark + ((batch + item) * tmax + f) * FSEM_PESQ_NBANDS;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float sc = 0.f, sd = 0.f;
+            for (int q = 0; q < bcount[h]; ++q) {
+                sc += pbuf[bfirst[h] + q];
+                sd += pbuf[256 + bfirst[h] + q];
+            }
+            int b = lane + 32 * h;
+            if (b < FSEM_PESQ_NBANDS) { out_c[b] = sc * bscale[h]; out_d[b] = sd * bscale[h]; }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel C: one CTA per item; Bark-domain model.
+constexpr int kBarkThreads = 128;
+constexpr int kBarkTile = 64;  // frames per shared-memory tile
+
+__device__ __forceinline__ float zwicker_loudness(float p, float thr, float inv_thr, float e, float scale) {
+    // loudness.py:62-67: Sl*(2 thr)^e * ((0.5 + 0.5 p/thr)^e - 1), 0 where p <= thr
+    float l = scale * (powf(fmaf(0.5f * p, inv_thr, 0.5f), e) - 1.f);
+    return (p <= thr) ? 0.f : l;   // NaN p: comparison false -> l (NaN) propagates like the reference
+}
+
+__global__ void __launch_bounds__(kBarkThreads)
+pesq_bark_kernel(const float* __restrict__ bark, const double* __restrict__ partial, int nchunks,
+                 const int32_t* __restrict__ lengths, int64_t batch, int64_t n, int tmax,
+                 const PesqTables* __restrict__ tab, float* __restrict__ dist_ws /* [2][batch][tmax] */,
+                 float* __restrict__ mos_out, int32_t* __restrict__ status_out,
+                 double* __restrict__ power_out /* [2][batch] */) {
+    __shared__ float s_tile[2][kBarkTile][FSEM_PESQ_NBANDS];
+    __shared__ float s_thr[FSEM_PESQ_NBANDS], s_ithr[FSEM_PESQ_NBANDS], s_exp[FSEM_PESQ_NBANDS],
+        s_lsc[FSEM_PESQ_NBANDS], s_w[FSEM_PESQ_NBANDS], s_ratio[FSEM_PESQ_NBANDS];
+    __shared__ float s_silent[kBarkTile];
+    __shared__ float s_fr[kBarkTile];
+    __shared__ float s_g2[2];
+    __shared__ float s_carry;
+    __shared__ double s_mean[2][FSEM_PESQ_NBANDS];
+    __shared__ float s_red[2][kBarkThreads / 32];
+
+    const int tid = threadIdx.x;
+    const int64_t item = blockIdx.x;
+    const int len = item_length(lengths, item, n);
+    const int T = pesq_num_frames(len);
+
+    if (tid < FSEM_PESQ_NBANDS) {
+        float thr = tab->thresh[tid];
+        s_thr[tid] = thr;
+        s_ithr[tid] = 1.f / thr;
+        s_exp[tid] = tab->zw_exp[tid];
+        s_lsc[tid] = tab->loud_scale[tid];
+        s_w[tid] = tab->width[tid];
+    }
+    if (tid < 2) {
+        // level alignment (PESQ.py:97-100): g^2 = 1e7 / (sum(y^2) / (len + 5120) / 1.04684)
+        const double* p = partial + ((int64_t)tid * batch + item) * nchunks;
+        double acc = 0.0;
+        for (int c = 0; c < nchunks; ++c) acc += p[c];
+        power_out[(int64_t)tid * batch + item] = acc;
+        s_g2[tid] = (float)(1.0e7 * ((double)len + 5120.0) * 1.04684 / acc);
+    }
+    __syncthreads();
+    const float g2c = s_g2[0], g2d = s_g2[1];
+    if (T < 20 || !(isfinite(g2c) && isfinite(g2d))) {
+        if (tid == 0) {
+            mos_out[item] = nanf("");
+            if (status_out) status_out[item] = (T < 20) ? FSEM_ITEM_TOO_SHORT : FSEM_ITEM_NAN;
+        }
+        return;
+    }
+    const float* __restrict__ bc = bark + item * (int64_t)tmax * FSEM_PESQ_NBANDS;
+    const float* __restrict__ bd = bark + (batch + item) * (int64_t)tmax * FSEM_PESQ_NBANDS;
+
+    auto load_tile = [&](int f0, int nf) {
+        const int cnt = nf * FSEM_PESQ_NBANDS;
+        const float* srcc = bc + (int64_t)f0 * FSEM_PESQ_NBANDS;
+        const float* srcd = bd + (int64_t)f0 * FSEM_PESQ_NBANDS;
+        float* dc = &s_tile[0][0][0];
+        float* dd = &s_tile[1][0][0];
+        for (int i = tid; i < cnt; i += kBarkThreads) {
+            dc[i] = __ldg(srcc + i) * g2c;
+            dd[i] = __ldg(srcd + i) * g2d;
+        }
+    };
+
+    // ---- phase 1: silent-frame flags and mean audible band power (PESQ.py:144-147)
+    double band_acc = 0.0;   // thread t < 98: signal t / 49, band t % 49
+    const int my_sig = tid / FSEM_PESQ_NBANDS;
+    const int my_band = tid - my_sig * FSEM_PESQ_NBANDS;
+    for (int f0 = 0; f0 < T; f0 += kBarkTile) {
+        const int nf = min(kBarkTile, T - f0);
+        __syncthreads();
+        load_tile(f0, nf);
+        __syncthreads();
+        if (tid < nf) {
+            float a = 0.f;
+#pragma unroll 7
+            for (int b = 0; b < FSEM_PESQ_NBANDS; ++b) {
+                float p = s_tile[0][tid][b];
+                a += p * ((p > s_thr[b] * 100.f) ? 1.f : 0.f);
+            }
+            s_silent[tid] = (a < 1.0e7f) ? 1.f : 0.f;
+        }
+        __syncthreads();
+        if (tid < 2 * FSEM_PESQ_NBANDS) {
+            const float thr100 = s_thr[my_band] * 100.f;
+            for (int f = 0; f < nf; ++f) {
+                float p = s_tile[my_sig][f][my_band];
+                float m = ((p > thr100) ? 1.f : 0.f) * (1.f - s_silent[f]);
+                band_acc += (double)(p * m);
+            }
+        }
+    }
+    if (tid < 2 * FSEM_PESQ_NBANDS) s_mean[my_sig][my_band] = band_acc / (double)T;
+    __syncthreads();
+    if (tid < FSEM_PESQ_NBANDS) {
+        float r = (float)((s_mean[1][tid] + 1000.0) / (s_mean[0][tid] + 1000.0));
+        s_ratio[tid] = fminf(fmaxf(r, 0.01f), 100.f);
+    }
+    if (tid == 0) s_carry = 0.f;
+    __syncthreads();
+
+    const float wtot = tab->width_total;
+    float* __restrict__ dsym = dist_ws + item * (int64_t)tmax;
+    float* __restrict__ dasym = dist_ws + (batch + item) * (int64_t)tmax;
+
+    // ---- phase 2: frame equalisation, loudness, disturbances (PESQ.py:149-224)
+    for (int f0 = 0; f0 < T; f0 += kBarkTile) {
+        const int nf = min(kBarkTile, T - f0);
+        __syncthreads();
+        load_tile(f0, nf);
+        __syncthreads();
+        float afp_c = 0.f;
+        if (tid < nf) {
+            float afp_d = 0.f;
+#pragma unroll 7
+            for (int b = 0; b < FSEM_PESQ_NBANDS; ++b) {
+                float c = s_ratio[b] * s_tile[0][tid][b];
+                float d = s_tile[1][tid][b];
+                afp_c += c * ((c > s_thr[b]) ? 1.f : 0.f);
+                afp_d += d * ((d > s_thr[b]) ? 1.f : 0.f);
+            }
+            s_fr[tid] = (afp_c + 5.0e3f) / (afp_d + 5.0e3f);
+        }
+        __syncthreads();
+        if (tid < nf) {
+            const int f = f0 + tid;
+            float fr = s_fr[tid];
+            if (f > 0) {
+                float prev = (tid == 0) ? s_carry : s_fr[tid - 1];
+                fr = 0.8f * fr + 0.2f * prev;               // non-recursive smoothing (PESQ.py:159)
+            }
+            fr = fminf(fmaxf(fr, 3.0e-4f), 5.f);
+            float sym_acc = 0.f, asym_acc = 0.f;
+            for (int b = 0; b < FSEM_PESQ_NBANDS; ++b) {
+                const float c = s_ratio[b] * s_tile[0][tid][b];
+                const float d = fr * s_tile[1][tid][b];
+                const float thr = s_thr[b], ithr = s_ithr[b], e = s_exp[b], lsc = s_lsc[b];
+                const float lc = zwicker_loudness(c, thr, ithr, e, lsc);
+                const float ld = zwicker_loudness(d, thr, ithr, e, lsc);
+                const float dead = 0.25f * fminf(lc, ld);
+                float diff = ld - lc;
+                float mag = fmaxf(fabsf(diff) - dead, 0.f);
+                float dist = copysignf(mag, diff);
+                if (diff != diff) dist = diff;             // keep NaN
+                if (b >= 1) {                               // band 0 excluded (bark.py:184)
+                    const float wd = s_w[b] * dist;
+                    sym_acc = fmaf(wd, wd, sym_acc);
+                    const float ratio = (d + 50.f) / (c + 50.f);
+                    float scale = 0.f;
+                    if (!(ratio < 2.49f)) {                // 2.49^1.2 < 3: below that the scale is 0 anyway
+                        scale = powf(ratio, 1.2f);
+                        if (scale < 3.f) scale = 0.f;
+                        scale = fminf(scale, 12.f);
+                    }
+                    asym_acc += fabsf(wd * scale);
+                }
+            }
+            float sym = fmaxf(sqrtf(wtot * sym_acc), 1.0e-20f);
+            float asym = fmaxf(asym_acc, 1.0e-20f);
+            const float weight = powf((afp_c + 1.0e5f) * 1.0e-7f, 0.04f);
+            dsym[f] = fminf(sym / weight, 45.f);
+            dasym[f] = fminf(asym / weight, 45.f);
+        }
+        __syncthreads();
+        if (tid == 0) s_carry = s_fr[nf - 1];
+    }
+    __syncthreads();   // dsym/dasym written by this CTA are visible to it after the barrier
+
+    // ---- phase 3: L6 over 20-frame windows (hop 10), L2 across windows, MOS (PESQ.py:168-172, 240-243)
+    const int W = (T - 20) / 10 + 1;
+    float acc_s = 0.f, acc_a = 0.f;
+    for (int w = tid; w < W; w += kBarkThreads) {
+        float s6 = 0.f, a6 = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < 20; ++j) {
+            float s = dsym[10 * w + j], a = dasym[10 * w + j];
+            float s2 = s * s, a2 = a * a;
+            s6 = fmaf(s2 * s2, s2, s6);
+            a6 = fmaf(a2 * a2, a2, a6);
+        }
+        float ps = powf(s6 * 0.05f, 1.f / 6.f), pa = powf(a6 * 0.05f, 1.f / 6.f);
+        acc_s = fmaf(ps, ps, acc_s);
+        acc_a = fmaf(pa, pa, acc_a);
+    }
+    acc_s = warp_sum(acc_s);
+    acc_a = warp_sum(acc_a);
+    if ((tid & 31) == 0) { s_red[0][tid >> 5] = acc_s; s_red[1][tid >> 5] = acc_a; }
+    __syncthreads();
+    if (tid == 0) {
+        float ts = 0.f, ta = 0.f;
+        for (int i = 0; i < kBarkThreads / 32; ++i) { ts += s_red[0][i]; ta += s_red[1][i]; }
+        float d_sym = sqrtf(ts / (float)W), d_asym = sqrtf(ta / (float)W);
+        float mos = 4.5f - 0.1f * d_sym - 0.0309f * d_asym;
+        mos = 0.999f + 4.f / (1.f + expf(-1.3669f * mos + 3.8224f));
+        mos_out[item] = mos;
+        if (status_out) status_out[item] = (mos == mos) ? FSEM_ITEM_OK : FSEM_ITEM_NAN;
+    }
+}
+
+}  // namespace fsem

@@ -1,0 +1,333 @@
+// STOI / ESTOI kernels (sm_100a).  Stream-ordered launches per call:
+//
+//   stoi_resample_kernel   polyphase sinc-Hann FIR to 10 kHz (base.py:16-21 -> torchaudio Resample);
+//                          skipped when the input already is 10 kHz
+//   stoi_energy_kernel     Hann-windowed 256/128 frame energies of the CLEAN signal in dB (STOI.py:92-98)
+//   stoi_compact_kernel    max energy, -40 dB mask, warp-ballot prefix scan -> kept-frame list, K (STOI.py:102-107)
+//   stoi_tob_kernel        STFT frame u straight from kept frames u, u+1, u+2 (the overlap-add buffer of
+//                          STOI.py:71-86 is never materialised), clean+degraded packed in one complex
+//                          512-pt FFT, 15 third-octave band sums, sqrt (STOI.py:49-69, 121-125)
+//   stoi_segment_kernel    sliding 30-frame segments from a shared-memory tile: equalise + clip +
+//                          correlate (STOI), row/column normalise + correlate (ESTOI) (STOI.py:129-198)
+//   stoi_finalize_kernel   fixed-order sum of tile partials / number of segments
+#pragma once
+#include "fsem_common.cuh"
+#include "fsem_fft.cuh"
+
+namespace fsem {
+
+struct StoiTables {
+    float window[FSEM_STOI_WIN];
+    int32_t band_lo[FSEM_STOI_NBANDS];
+    int32_t band_hi[FSEM_STOI_NBANDS];
+    float clip;
+    float dyn_range;
+};
+
+// ------------------------------------------------------------------------------------------------
+// General polyphase resampler: y[neu*k + p] = sum_j taps[p][j] * xpad[orig*k + j],
+// xpad = `width` zeros | x | zeros.  One thread per output sample; grid.y = signal.
+__global__ void __launch_bounds__(256)
+stoi_resample_kernel(const float* __restrict__ clean, const float* __restrict__ deg,
+                     const int32_t* __restrict__ lengths, int64_t batch, int64_t n, int64_t stride,
+                     const float* __restrict__ taps, int orig, int neu, int width, int ntaps,
+                     float* __restrict__ y, int64_t ystride) {
+    const int64_t sig = blockIdx.y;
+    const int64_t item = sig < batch ? sig : sig - batch;
+    const int len = item_length(lengths, item, n);
+    const int64_t L = stoi_resampled_len(len, orig, neu);
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= L) return;
+    const float* __restrict__ x = (sig < batch ? clean : deg) + item * stride;
+    const int64_t k = m / neu;
+    const int p = (int)(m - k * neu);
+    const float* __restrict__ h = taps + (int64_t)p * ntaps;
+    const int64_t i0 = k * orig - width;
+    float acc = 0.f;
+    for (int j = 0; j < ntaps; ++j) {
+        int64_t i = i0 + j;
+        float xv = (i >= 0 && i < len) ? __ldg(x + i) : 0.f;
+        acc = fmaf(__ldg(h + j), xv, acc);
+    }
+    y[sig * ystride + m] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Frame energies of the clean 10 kHz signal: E_t = 20*log10(||w * x_t||_2 + 1e-9) (STOI.py:94-98).
+// The products w*x are rounded to fp32 as the reference does; the sum of squares is accumulated in
+// fp64 (exactly rounded norm), the remaining ops are fp32 in the reference's order.  One warp per frame.
+__global__ void __launch_bounds__(256)
+stoi_energy_kernel(const float* __restrict__ sig10k, int64_t sstride, const int32_t* __restrict__ lengths,
+                   int64_t batch, int64_t n, int orig, int neu, int t0max,
+                   const StoiTables* __restrict__ tab, float* __restrict__ energy /* [batch][t0max] */) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= batch * (int64_t)t0max) return;
+    const int64_t item = wid / t0max;
+    const int t = (int)(wid - item * t0max);
+    const int64_t L = stoi_resampled_len(item_length(lengths, item, n), orig, neu);
+    if (t >= stoi_num_frames(L)) return;
+    const float* __restrict__ x = sig10k + item * sstride + (int64_t)t * FSEM_STOI_HOP;
+    double acc = 0.0;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        int q = lane + 32 * m;
+        float f = __fmul_rn(__ldg(x + q), tab->window[q]);
+        acc = fma((double)f, (double)f, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        float nrm = (float)sqrt(acc);
+        float v = __fadd_rn(nrm, 1e-9f);
+        float lg = (float)log10((double)v);
+        energy[item * t0max + t] = __fmul_rn(20.f, lg);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One warp per item: mask_t = ((max E - 40) - E_t) < 0 in fp32 (STOI.py:102), compaction by
+// warp ballot + popcount prefix.  Writes the kept-frame list, K and the mask bits.
+__global__ void __launch_bounds__(128)
+stoi_compact_kernel(const float* __restrict__ energy, const int32_t* __restrict__ lengths, int64_t batch,
+                    int64_t n, int orig, int neu, int t0max, int mask_words, float dyn_range,
+                    int32_t* __restrict__ kept_idx /* [batch][t0max] */, int32_t* __restrict__ kept_count,
+                    uint32_t* __restrict__ mask_bits /* [batch][mask_words] */) {
+    const int lane = threadIdx.x & 31;
+    const int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (item >= batch) return;
+    const int64_t L = stoi_resampled_len(item_length(lengths, item, n), orig, neu);
+    const int T0 = stoi_num_frames(L);
+    const float* __restrict__ e = energy + item * t0max;
+    float mx = -INFINITY;
+    for (int t = lane; t < T0; t += 32) mx = fmaxf(mx, e[t]);
+    mx = warp_max(mx);
+    const float thr = __fsub_rn(mx, dyn_range);
+    int count = 0;
+    for (int t0 = 0; t0 < mask_words * 32; t0 += 32) {
+        const int t = t0 + lane;
+        bool keep = false;
+        if (t < T0) keep = __fsub_rn(thr, e[t]) < 0.f;
+        const unsigned bal = __ballot_sync(kFull, keep);
+        if (keep) kept_idx[item * t0max + count + __popc(bal & ((1u << lane) - 1u))] = t;
+        if (lane == 0) mask_bits[item * mask_words + (t0 >> 5)] = bal;
+        count += __popc(bal);
+    }
+    if (lane == 0) kept_count[item] = count;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Third-octave spectrogram of the silence-removed signals.  Persistent warps over (item, u).
+// STFT frame u of the reference = FFT512 of the 256-sample chunk
+//     c_u[q] = w[q] * ( f_{u+1}[q] + (q < 128 ? f_u[q + 128] : f_{u+2}[q - 128]) ),   f_j[q] = w[q] * x[128*t_j + q]
+// zero-padded to 512 (torch.stft centre-pads the 256 window; the circular shift does not change the
+// power spectrum), where t_j is the j-th kept frame.  Every product/sum is rounded to fp32 like the reference.
+constexpr int kTobWarps = 8;
+
+__global__ void __launch_bounds__(kTobWarps * 32)
+stoi_tob_kernel(const float* __restrict__ clean10k, const float* __restrict__ deg10k, int64_t sstride,
+                int64_t batch, int t0max, int umax,
+                int ustride, const int32_t* __restrict__ kept_idx, const int32_t* __restrict__ kept_count,
+                const StoiTables* __restrict__ tab, float* __restrict__ tob /* [2][batch][15][ustride] */) {
+    __shared__ float2 s_buf[kTobWarps][kFftBufElems];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    float2* buf = s_buf[warp];
+    float* pbuf = reinterpret_cast<float*>(buf);
+
+    FftTwiddles tw;
+    tw.init(lane);
+    float win[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) win[m] = tab->window[lane + 32 * m];
+    // lanes 0..14 sum the clean bands, lanes 16..30 the degraded bands
+    const int band = lane & 15;
+    const bool band_ok = band < FSEM_STOI_NBANDS;
+    const int lo = band_ok ? tab->band_lo[band] : 0;
+    const int hi = band_ok ? tab->band_hi[band] : 0;
+    const int psel = (lane >> 4) * 256;
+
+    const int64_t units = batch * (int64_t)umax;
+    const int64_t wstride = (int64_t)gridDim.x * kTobWarps;
+    for (int64_t unit = (int64_t)blockIdx.x * kTobWarps + warp; unit < units; unit += wstride) {
+        const int64_t item = unit / umax;
+        const int u = (int)(unit - item * umax);
+        const int K = kept_count[item];
+        if (u >= K - 2) continue;
+        const int32_t* idx = kept_idx + item * t0max + u;
+        const int64_t ta = (int64_t)idx[0] * FSEM_STOI_HOP, tb = (int64_t)idx[1] * FSEM_STOI_HOP,
+                      tc = (int64_t)idx[2] * FSEM_STOI_HOP;
+        const float* __restrict__ xc = clean10k + item * sstride;
+        const float* __restrict__ xd = deg10k + item * sstride;
+        float re[16], im[16];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const int q = lane + 32 * m;
+            // neighbour frame: first half of the chunk overlaps the tail of frame u, second half the head of frame u+2
+            const int64_t nb = (m < 4) ? (ta + q + 128) : (tc + q - 128);
+            const float wn = (m < 4) ? win[m + 4] : win[m - 4];
+            float c = __fadd_rn(__fmul_rn(win[m], __ldg(xc + tb + q)), __fmul_rn(wn, __ldg(xc + nb)));
+            float d = __fadd_rn(__fmul_rn(win[m], __ldg(xd + tb + q)), __fmul_rn(wn, __ldg(xd + nb)));
+            re[m] = __fmul_rn(win[m], c);
+            im[m] = __fmul_rn(win[m], d);
+        }
+#pragma unroll
+        for (int m = 8; m < 16; ++m) { re[m] = 0.f; im[m] = 0.f; }
+        warp_fft512<true>(re, im, buf, tw, lane);
+        float pc[8], pd[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) packed_power(buf, lane + 32 * j, pc[j], pd[j]);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { pbuf[lane + 32 * j] = pc[j]; pbuf[256 + lane + 32 * j] = pd[j]; }
+        __syncwarp();
+        float s = 0.f;
+        for (int k = lo; k < hi; ++k) s += pbuf[psel + k];
+        if (band_ok) {
+            const int64_t sig = (lane >> 4) ? (batch + item) : item;
+            tob[(sig * FSEM_STOI_NBANDS + band) * ustride + u] = sqrtf(s);
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Segment kernel: CTA = (item, tile of kSegTile consecutive segments).
+constexpr int kSegTile = 64;
+constexpr int kSegThreads = 256;
+constexpr int kSegCols = kSegTile + FSEM_STOI_SEG - 1;  // 93 frames feed 64 segments
+constexpr int kSegPitch = 97;                            // odd pitch: conflict-free rows
+
+__device__ __forceinline__ float rsqrt_or_zero(float v) { return v > 0.f ? rsqrtf(v) : 0.f; }
+
+__global__ void __launch_bounds__(kSegThreads)
+stoi_segment_kernel(const float* __restrict__ tob, int64_t batch, int ustride, int ntiles,
+                    const int32_t* __restrict__ kept_count, float clip,
+                    float2* __restrict__ partial /* [batch][ntiles] (stoi, estoi) */) {
+    __shared__ float s_x[FSEM_STOI_NBANDS][kSegPitch];
+    __shared__ float s_y[FSEM_STOI_NBANDS][kSegPitch];
+    __shared__ float4 s_row[kSegTile][FSEM_STOI_NBANDS];   // (mean_x, 1/||x-mean||, mean_y, 1/||y-mean||)
+    __shared__ float s_red[2][kSegThreads / 32];
+
+    const int tid = threadIdx.x;
+    const int64_t item = blockIdx.x / ntiles;
+    const int tile = (int)(blockIdx.x - item * ntiles);
+    const int K = kept_count[item];
+    const int M = max(K - 31, 0);                     // number of segments (STOI.py:183-186)
+    const int m0 = tile * kSegTile;
+    if (m0 >= M) {
+        if (tid == 0) partial[item * ntiles + tile] = make_float2(0.f, 0.f);
+        return;
+    }
+    const int nseg = min(kSegTile, M - m0);
+    const int ncol = nseg + FSEM_STOI_SEG - 1;
+    const float* __restrict__ tx = tob + (item * FSEM_STOI_NBANDS) * (int64_t)ustride + m0;
+    const float* __restrict__ ty = tob + ((batch + item) * FSEM_STOI_NBANDS) * (int64_t)ustride + m0;
+    for (int i = tid; i < FSEM_STOI_NBANDS * kSegCols; i += kSegThreads) {
+        int j = i / kSegCols, c = i - j * kSegCols;
+        bool ok = c < ncol;
+        s_x[j][c] = ok ? __ldg(tx + (int64_t)j * ustride + c) : 0.f;
+        s_y[j][c] = ok ? __ldg(ty + (int64_t)j * ustride + c) : 0.f;
+    }
+    __syncthreads();
+
+    // ---- part A: per (segment, band) rows: STOI term + row statistics for ESTOI
+    float stoi_acc = 0.f;
+    for (int id = tid; id < FSEM_STOI_NBANDS * kSegTile; id += kSegThreads) {
+        const int j = id / kSegTile, m = id - j * kSegTile;
+        if (m >= nseg) continue;
+        float x[FSEM_STOI_SEG], y[FSEM_STOI_SEG];
+        float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f;
+#pragma unroll
+        for (int q = 0; q < FSEM_STOI_SEG; ++q) {
+            x[q] = s_x[j][m + q];
+            y[q] = s_y[j][m + q];
+            sx += x[q]; sy += y[q];
+            sxx = fmaf(x[q], x[q], sxx);
+            syy = fmaf(y[q], y[q], syy);
+        }
+        // equalize_clip (STOI.py:129-139)
+        const float alpha = sqrtf(sxx) / (sqrtf(syy) + 1e-9f);
+        const float mx = sx * (1.f / FSEM_STOI_SEG), my = sy * (1.f / FSEM_STOI_SEG);
+        float syc = 0.f;
+#pragma unroll
+        for (int q = 0; q < FSEM_STOI_SEG; ++q) {
+            float yc = fminf(y[q] * alpha, x[q] * clip);
+            syc += yc;
+        }
+        const float myc = syc * (1.f / FSEM_STOI_SEG);
+        float vxx = 0.f, vyy = 0.f, vxy = 0.f, vyo = 0.f;
+#pragma unroll
+        for (int q = 0; q < FSEM_STOI_SEG; ++q) {
+            float yc = fminf(y[q] * alpha, x[q] * clip);
+            float dx = x[q] - mx, dy = yc - myc, dyo = y[q] - my;
+            vxx = fmaf(dx, dx, vxx);
+            vyy = fmaf(dy, dy, vyy);
+            vxy = fmaf(dx, dy, vxy);
+            vyo = fmaf(dyo, dyo, vyo);
+        }
+        const float rx = rsqrt_or_zero(vxx), ry = rsqrt_or_zero(vyy);
+        stoi_acc += vxy * rx * ry;                     // correlation of the normalised rows (STOI.py:174-175, 190)
+        s_row[m][j] = make_float4(mx, rx, my, rsqrt_or_zero(vyo));
+    }
+    __syncthreads();
+
+    // ---- part B: ESTOI: per (segment, time column): rows normalised, then columns (STOI.py:178-181, 193)
+    float estoi_acc = 0.f;
+    for (int id = tid; id < kSegTile * FSEM_STOI_SEG; id += kSegThreads) {
+        const int m = id / FSEM_STOI_SEG, q = id - m * FSEM_STOI_SEG;
+        if (m >= nseg) continue;
+        float xh[FSEM_STOI_NBANDS], yh[FSEM_STOI_NBANDS];
+        float sx = 0.f, sy = 0.f;
+#pragma unroll
+        for (int j = 0; j < FSEM_STOI_NBANDS; ++j) {
+            const float4 r = s_row[m][j];
+            xh[j] = (s_x[j][m + q] - r.x) * r.y;
+            yh[j] = (s_y[j][m + q] - r.z) * r.w;
+            sx += xh[j]; sy += yh[j];
+        }
+        const float mx = sx * (1.f / FSEM_STOI_NBANDS), my = sy * (1.f / FSEM_STOI_NBANDS);
+        float vxx = 0.f, vyy = 0.f, vxy = 0.f;
+#pragma unroll
+        for (int j = 0; j < FSEM_STOI_NBANDS; ++j) {
+            float dx = xh[j] - mx, dy = yh[j] - my;
+            vxx = fmaf(dx, dx, vxx);
+            vyy = fmaf(dy, dy, vyy);
+            vxy = fmaf(dx, dy, vxy);
+        }
+        estoi_acc += vxy * rsqrt_or_zero(vxx) * rsqrt_or_zero(vyy);
+    }
+    stoi_acc = warp_sum(stoi_acc);
+    estoi_acc = warp_sum(estoi_acc);
+    if ((tid & 31) == 0) { s_red[0][tid >> 5] = stoi_acc; s_red[1][tid >> 5] = estoi_acc; }
+    __syncthreads();
+    if (tid == 0) {
+        float a = 0.f, b = 0.f;
+        for (int i = 0; i < kSegThreads / 32; ++i) { a += s_red[0][i]; b += s_red[1][i]; }
+        partial[item * ntiles + tile] = make_float2(a, b);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+stoi_finalize_kernel(const float2* __restrict__ partial, int64_t batch, int ntiles,
+                     const int32_t* __restrict__ kept_count, float* __restrict__ stoi_out,
+                     float* __restrict__ estoi_out, int32_t* __restrict__ kept_out,
+                     int32_t* __restrict__ status_out) {
+    const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= batch) return;
+    const int K = kept_count[item];
+    const int M = max(K - 31, 0);
+    double a = 0.0, b = 0.0;
+    for (int t = 0; t < ntiles; ++t) {
+        float2 p = partial[item * ntiles + t];
+        a += (double)p.x;
+        b += (double)p.y;
+    }
+    // correlations / normalisation / num_segments (STOI.py:147-151, 198); M = 0 -> 0/0 = NaN like the reference
+    const float fm = (float)M;
+    stoi_out[item] = (float)(a / FSEM_STOI_NBANDS) / fm;
+    estoi_out[item] = (float)(b / FSEM_STOI_SEG) / fm;
+    if (kept_out) kept_out[item] = K;
+    if (status_out) status_out[item] = (M > 0) ? FSEM_ITEM_OK : FSEM_ITEM_TOO_SHORT;
+}
+
+}  // namespace fsem

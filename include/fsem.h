@@ -1,0 +1,169 @@
+/*
+ * fsem.h -- C ABI of libfsem_b200.so: batched PESQ and STOI/ESTOI scoring on sm_100a.
+ *
+ * The reference (kcoost/fast_speech_enhancement_metrics) is pure Python and has no
+ * FFI layer of its own; this header is the boundary its two metric classes would bind
+ * to replace their torch/torchaudio op chains:
+ *
+ *   fsem_pesq_*  replaces  PESQ.compute_metric / get_disturbances   (fast_se_metrics/PESQ.py:174-245)
+ *                          incl. align_level (:92-102), pre_emphasize (:104-113),
+ *                          get_bark_bands (:123-140), BarkFilterBank.forward (utils/bark.py:189-204),
+ *                          Loudness.* (utils/loudness.py:48-67)
+ *   fsem_stoi_*  replaces  BaseMetric.prepare_audio's resample (fast_se_metrics/base.py:16-21) and
+ *                          STOI.compute_stoi / compute_metric         (fast_se_metrics/STOI.py:153-205)
+ *                          incl. remove_silent_frames (:88-111), overlap_and_add (:71-86),
+ *                          stft (:49-69), compute_segments (:121-127), equalize_clip (:129-139),
+ *                          normalize (:113-119), compute_correlation (:141-151)
+ *
+ * Conventions
+ *   - plain C types only; `stream` is a cudaStream_t passed as void*.
+ *   - "device" pointers are CUDA device pointers owned by the caller; "host" pointers are
+ *     ordinary (ideally pinned) host memory owned by the caller.  Inputs are never modified.
+ *   - every call returns 0 on success and a negative FSEM_E_* code on failure;
+ *     fsem_last_error() returns a thread-local message for the last failure.
+ *   - device entry points are stream-ordered and do not synchronise; the *_host_* entry
+ *     points include the host<->device copies and return after the scores are in host memory.
+ *   - a context is bound to the CUDA device that was current when it was created and may
+ *     be used from one host thread at a time.
+ *   - there is no CPU fallback: without a CUDA device every entry point fails with FSEM_E_CUDA.
+ */
+#ifndef FSEM_H_
+#define FSEM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define FSEM_API __attribute__((visibility("default")))
+#else
+#define FSEM_API
+#endif
+
+#define FSEM_VERSION 100 /* 0.1.0 */
+
+#define FSEM_OK 0
+#define FSEM_E_INVALID (-1) /* bad argument (null pointer, negative size, ...) */
+#define FSEM_E_CUDA (-2)    /* CUDA runtime error (message in fsem_last_error) */
+#define FSEM_E_WORKSPACE (-3) /* workspace too small */
+#define FSEM_E_TOO_SHORT (-4) /* PESQ: fewer than 20 frames (reference: RuntimeError, PESQ.py:169) */
+
+/* per-item status written next to the scores */
+#define FSEM_ITEM_OK 0
+#define FSEM_ITEM_TOO_SHORT 1 /* PESQ: < 20 frames; STOI: no 30-frame segment (score = NaN) */
+#define FSEM_ITEM_NAN 2       /* score is NaN (e.g. all-zero PESQ input; reference gives NaN too) */
+
+#define FSEM_PESQ_NBANDS 49
+#define FSEM_PESQ_NFFT 512
+#define FSEM_PESQ_HOP 256
+#define FSEM_BP_SECTIONS 5
+#define FSEM_STOI_NBANDS 15
+#define FSEM_STOI_WIN 256
+#define FSEM_STOI_HOP 128
+#define FSEM_STOI_SEG 30
+
+/* A batch of utterance pairs.  Rows are fp32, `stride` floats apart; row i holds
+ * lengths[i] valid samples (all `n` when lengths == NULL).  Mirrors the
+ * (clean_speech, denoised_speech) [batch, samples] tensors of BaseMetric.__call__
+ * (base.py:41-43). */
+typedef struct fsem_batch {
+    const float* clean;     /* [batch, stride] */
+    const float* deg;       /* [batch, stride] */
+    const int32_t* lengths; /* [batch] or NULL; same memory space as clean/deg */
+    int64_t batch;
+    int64_t n;      /* samples per row (max length) */
+    int64_t stride; /* row pitch in floats, >= n */
+} fsem_batch_t;
+
+/* Host-designed constants of PESQ.__init__ (PESQ.py:55-90, bark.py:129-164, loudness.py:42-46).
+ * The 10th-order band-pass (scipy butter(5,[325,3250]) rounded to fp32, PESQ.py:80-81) is passed
+ * in PARALLEL form: y = direct*x + sum_s (c0_s + c1_s z^-1) / (1 + a1_s z^-1 + a2_s z^-2) x,
+ * obtained on the host from the poles/residues of the fp32-rounded polynomials. */
+typedef struct fsem_pesq_design {
+    float bp_direct;
+    float bp_c0[FSEM_BP_SECTIONS];
+    float bp_c1[FSEM_BP_SECTIONS];
+    float bp_a1[FSEM_BP_SECTIONS];
+    float bp_a2[FSEM_BP_SECTIONS];
+    float pre_b[3];  /* pre-emphasis biquad numerator   (PESQ.py:85) */
+    float pre_a[2];  /* a1, a2 of the denominator (a0 = 1) (PESQ.py:86) */
+    float taper[15]; /* k/16, k = 1..15                 (PESQ.py:90) */
+    int32_t warmup;  /* samples after which both IIR impulse responses are < fp32 eps */
+    float hann[FSEM_PESQ_NFFT];              /* periodic Hann window (PESQ.py:63-71) */
+    int32_t band_first_bin[FSEM_PESQ_NBANDS]; /* contiguous runs of FFT bins (bark.py:137-148) */
+    int32_t band_num_bins[FSEM_PESQ_NBANDS];
+    float pow_dens[FSEM_PESQ_NBANDS];  /* pow_dens_correction * Sp (bark.py:132) */
+    float thresh[FSEM_PESQ_NBANDS];    /* absolute hearing threshold (loudness.py:43) */
+    float zwicker_exp[FSEM_PESQ_NBANDS]; /* loudness exponents (loudness.py:45-46) */
+    float width_bark[FSEM_PESQ_NBANDS];  /* band widths in Bark (bark.py:131) */
+    float sl;                            /* Sl (loudness.py:25) */
+} fsem_pesq_design_t;
+
+/* Host-designed constants of STOI.__init__ (STOI.py:11-47) and of the ingest resampler
+ * (base.py:13; torchaudio sinc_interp_hann kernel). */
+typedef struct fsem_stoi_design {
+    int32_t orig;   /* reduced input rate  (8 for 16 kHz -> 10 kHz); orig == neu: no resampling */
+    int32_t neu;    /* reduced output rate (5) */
+    int32_t width;  /* kernel half-width in input samples (10) */
+    int32_t ntaps;  /* 2*width + orig (28) */
+    const float* taps; /* HOST pointer, [neu][ntaps] fp32; may be NULL when orig == neu */
+    float window[FSEM_STOI_WIN];       /* hann_window(257)[1:] exactly as torch builds it (STOI.py:24) */
+    int32_t band_lo[FSEM_STOI_NBANDS]; /* third-octave band b sums FFT bins [lo, hi) (STOI.py:26-47) */
+    int32_t band_hi[FSEM_STOI_NBANDS];
+    float clip;      /* 1 + 10^(-beta/20) (STOI.py:137-138) */
+    float dyn_range; /* 40 dB (STOI.py:22) */
+} fsem_stoi_design_t;
+
+typedef struct fsem_pesq_ctx fsem_pesq_ctx_t;
+typedef struct fsem_stoi_ctx fsem_stoi_ctx_t;
+
+FSEM_API int fsem_version(void);
+FSEM_API const char* fsem_last_error(void);
+/* number of kernel launches issued by this library on the calling thread since load */
+FSEM_API int64_t fsem_launch_count(void);
+
+/* ------------------------------------------------------------------ PESQ */
+FSEM_API int fsem_pesq_create(fsem_pesq_ctx_t** out, const fsem_pesq_design_t* design);
+FSEM_API int fsem_pesq_destroy(fsem_pesq_ctx_t* ctx);
+/* bytes of device workspace fsem_pesq_score_f32 needs for a [batch, n] call */
+FSEM_API size_t fsem_pesq_workspace_bytes(const fsem_pesq_ctx_t* ctx, int64_t batch, int64_t n);
+/* Device entry point.  mos_out[batch] fp32, status_out[batch] int32 (may be NULL): device. */
+FSEM_API int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in, float* mos_out,
+                        int32_t* status_out, void* workspace, size_t workspace_bytes, void* stream);
+/* Host entry point: `in` holds HOST pointers; copies in chunks overlapped with compute,
+ * scores land in host memory; synchronises before returning. */
+FSEM_API int fsem_pesq_score_host_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in, float* mos_out,
+                             int32_t* status_out);
+/* Stage taps for parity tests (device pointers, after a score call on the same workspace):
+ * copies the Bark-band power densities [2, batch, frames, 49] (clean then degraded, level-aligned)
+ * into `bark_out` and the band-pass energies sum(y^2) [2, batch] (double) into `power_out`. */
+FSEM_API int fsem_pesq_debug_taps(fsem_pesq_ctx_t* ctx, int64_t batch, int64_t n, const void* workspace,
+                         float* bark_out, double* power_out, int64_t* frames_out, void* stream);
+
+/* ------------------------------------------------------------------ STOI */
+FSEM_API int fsem_stoi_create(fsem_stoi_ctx_t** out, const fsem_stoi_design_t* design);
+FSEM_API int fsem_stoi_destroy(fsem_stoi_ctx_t* ctx);
+FSEM_API size_t fsem_stoi_workspace_bytes(const fsem_stoi_ctx_t* ctx, int64_t batch, int64_t n);
+/* Device entry point.  stoi_out/estoi_out[batch] fp32, kept_frames_out[batch] int32 (K, may be
+ * NULL), status_out[batch] (may be NULL): device pointers. */
+FSEM_API int fsem_stoi_score_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t* in, float* stoi_out,
+                        float* estoi_out, int32_t* kept_frames_out, int32_t* status_out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+FSEM_API int fsem_stoi_score_host_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t* in, float* stoi_out,
+                             float* estoi_out, int32_t* kept_frames_out, int32_t* status_out);
+/* Stage taps (device pointers, after a score call on the same workspace):
+ * mask_out  [batch, mask_words] uint32 bit t of item i = frame t kept   (may be NULL)
+ * tob_out   [2, batch, 15, tob_frames] third-octave magnitudes           (may be NULL)
+ * resampled_out [2, batch, resampled_len] the 10 kHz signals             (may be NULL)
+ * The three sizes are returned through dims_out[3] = {mask_words, tob_frames, resampled_len}. */
+FSEM_API int fsem_stoi_debug_taps(fsem_stoi_ctx_t* ctx, int64_t batch, int64_t n, const void* workspace,
+                         uint32_t* mask_out, float* tob_out, float* resampled_out,
+                         int64_t* dims_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSEM_H_ */

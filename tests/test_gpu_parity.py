@@ -1,0 +1,248 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the public classes and hence
+through the C ABI of libfsem_b200.so, against
+
+  * the golden fixtures (outputs of the real reference's CPU path, tests/golden/*.npz), and
+  * the numpy oracle (oracle/) on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): |dPESQ| <= 1e-3, |dSTOI|, |dESTOI| <= 1e-4, the
+silent-frame mask and the kept-frame count K bit-exact.  Against the float64 oracle (which
+does not carry the reference's own float32-IIR noise) PESQ is held to 2e-4.
+"""
+import json
+import os
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pesq_oracle as po
+from oracle import stoi_oracle as so
+from tests.conftest import ROOT, unpack_masks
+from tests.golden.cases import pesq_cases, stoi_cases
+
+pytestmark = pytest.mark.gpu
+
+PESQ_CASES = pesq_cases()
+STOI_CASES = stoi_cases()
+REPORT = {}
+
+
+def _report(key, value):
+    REPORT[key] = value
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "parity_report.json"), "w") as f:
+        json.dump(REPORT, f, indent=1, sort_keys=True)
+
+
+@pytest.fixture(scope="module")
+def pesq():
+    from fast_speech_enhancement_metrics_b200 import PESQ
+    return PESQ(16000, use_gpu=True)
+
+
+@pytest.fixture(scope="module")
+def stoi_metrics():
+    from fast_speech_enhancement_metrics_b200 import STOI
+    cache = {}
+
+    def get(fs):
+        if fs not in cache:
+            cache[fs] = STOI(fs, use_gpu=True)
+        return cache[fs]
+    return get
+
+
+def _maxdiff(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert np.array_equal(np.isnan(a), np.isnan(b)), (a, b)
+    ok = ~np.isnan(b)
+    return float(np.max(np.abs(a[ok] - b[ok]), initial=0.0))
+
+
+# ------------------------------------------------------------------------------------------ PESQ
+@pytest.mark.parametrize("name", sorted(PESQ_CASES))
+def test_pesq_matches_reference_and_oracle(name, pesq, golden_pesq):
+    clean, deg, lengths = PESQ_CASES[name]
+    c = torch.from_numpy(clean).cuda()
+    d = torch.from_numpy(deg).cuda()
+    got = np.array([r["PESQ"] for r in pesq(c, d, lengths=lengths)])
+    want = golden_pesq[name]
+    oracle = po.pesq_batch(clean, deg, lengths)
+    d_ref, d_orc = _maxdiff(got, want), _maxdiff(got, oracle)
+    _report("pesq/" + name, {"max_abs_vs_reference": d_ref, "max_abs_vs_oracle": d_orc, "got": got.tolist()})
+    assert d_ref <= 1e-3
+    assert d_orc <= 2e-4
+
+
+def test_pesq_stage_taps(pesq):
+    clean, deg, _ = PESQ_CASES["speech2s"]
+    c = torch.from_numpy(clean).cuda()
+    d = torch.from_numpy(deg).cuda()
+    pesq.score_tensors(c, d)
+    bark, power = pesq.debug_taps()
+    bark, power = bark.cpu().numpy().astype(np.float64), power.cpu().numpy()
+    n = clean.shape[1]
+    worst_p, worst_b = 0.0, 0.0
+    for i in range(clean.shape[0]):
+        for s, x in enumerate((clean[i], deg[i])):
+            p_or = po.band_power(x.astype(np.float64))
+            worst_p = max(worst_p, abs(power[s, i] - p_or) / p_or)
+            g2 = 1e7 * (n + 5120) * 1.04684 / power[s, i]
+            m = max(np.abs(clean[i]).max(), np.abs(deg[i]).max())
+            b_or = po.bark_bands(x.astype(np.float64) / m)
+            worst_b = max(worst_b, np.max(np.abs(bark[s, i, : b_or.shape[0]] * g2 - b_or)) / b_or.max())
+    _report("pesq/taps", {"band_power_rel": worst_p, "bark_rel_of_max": worst_b})
+    assert worst_p <= 3e-5
+    assert worst_b <= 1e-4
+
+
+def test_pesq_host_entry_equals_device_entry(pesq):
+    clean, deg, _ = PESQ_CASES["speech2s"]
+    dev = [r["PESQ"] for r in pesq(torch.from_numpy(clean).cuda(), torch.from_numpy(deg).cuda())]
+    host = [r["PESQ"] for r in pesq(torch.from_numpy(clean), torch.from_numpy(deg))]
+    assert dev == host
+    # unaligned rows (odd row pitch) take the scalar-load path and must agree to rounding
+    pad_c = torch.zeros(clean.shape[0], clean.shape[1] + 3, device="cuda")
+    pad_d = torch.zeros_like(pad_c)
+    pad_c[:, 1:-2] = torch.from_numpy(clean).cuda()
+    pad_d[:, 1:-2] = torch.from_numpy(deg).cuda()
+    odd = [r["PESQ"] for r in pesq(pad_c[:, 1:-2], pad_d[:, 1:-2])]
+    assert np.max(np.abs(np.array(odd) - np.array(dev))) <= 1e-5
+
+
+def test_pesq_errors(pesq):
+    x = torch.randn(2, 5120, device="cuda")
+    with pytest.raises(RuntimeError):                       # 19 frames (PESQ.py:169)
+        pesq(x, x)
+    with pytest.raises(Exception, match="same shape"):      # base.py:26-27
+        pesq(torch.randn(2, 8000, device="cuda"), torch.randn(2, 8001, device="cuda"))
+    with pytest.raises(AssertionError):                     # PESQ.py:235
+        pesq(None, torch.randn(2, 8000, device="cuda"))
+    with pytest.raises(RuntimeError):                       # float64 input
+        pesq(torch.randn(1, 8000, dtype=torch.float64), torch.randn(1, 8000, dtype=torch.float64))
+    out = pesq(torch.randn(16000), torch.randn(16000))      # 1-D input -> one item (atleast_2d)
+    assert len(out) == 1 and isinstance(out[0]["PESQ"], float)
+
+
+# ------------------------------------------------------------------------------------------ STOI
+@pytest.mark.parametrize("name", sorted(STOI_CASES))
+def test_stoi_matches_reference_and_oracle(name, stoi_metrics, golden_stoi):
+    clean, deg, lengths, fs = STOI_CASES[name]
+    metric = stoi_metrics(fs)
+    c = torch.from_numpy(clean).cuda()
+    d = torch.from_numpy(deg).cuda()
+    res = metric(c, d, lengths=lengths)
+    s = np.array([r["STOI"] for r in res])
+    e = np.array([r["ESTOI"] for r in res])
+    k = metric.last_kept_frames.numpy().astype(np.int64)
+    os_, oe, ok = so.stoi_batch(clean, deg, fs, lengths)
+    rep = {
+        "stoi_vs_reference": _maxdiff(s, golden_stoi[name + "/stoi"]),
+        "estoi_vs_reference": _maxdiff(e, golden_stoi[name + "/estoi"]),
+        "stoi_vs_oracle": _maxdiff(s, os_), "estoi_vs_oracle": _maxdiff(e, oe),
+        "K": k.tolist(), "K_reference": golden_stoi[name + "/K"].tolist(),
+    }
+    # silent-frame mask, bit for bit
+    taps = metric.debug_taps()
+    words = taps["mask"].cpu().numpy().view(np.uint32)
+    masks = unpack_masks(golden_stoi, name)
+    flips = 0
+    for i in range(clean.shape[0]):
+        nfr = len(masks[i]) if lengths is None else None
+        ref_mask = masks[i]
+        t0 = so.silent_frame_mask(so.resample(clean[i, : (clean.shape[1] if lengths is None else lengths[i])], fs, so.FS))[0].shape[0]
+        mine = np.array([(words[i, t >> 5] >> (t & 31)) & 1 for t in range(t0)], bool)
+        flips += int(np.sum(mine != ref_mask[:t0]))
+    rep["mask_bit_flips"] = flips
+    _report("stoi/" + name, rep)
+    assert np.array_equal(k, golden_stoi[name + "/K"])
+    assert flips == 0
+    assert rep["stoi_vs_reference"] <= 1e-4 and rep["estoi_vs_reference"] <= 1e-4
+    assert rep["stoi_vs_oracle"] <= 1e-4 and rep["estoi_vs_oracle"] <= 1e-4
+
+
+def test_stoi_stage_taps(stoi_metrics, golden_stoi):
+    clean, deg, _, fs = STOI_CASES["speech16k_3s"]
+    metric = stoi_metrics(fs)
+    metric.score_tensors(torch.from_numpy(clean).cuda(), torch.from_numpy(deg).cuda())
+    taps = metric.debug_taps()
+    res = taps["resampled"].cpu().numpy()
+    d_res = float(np.max(np.abs(res[0, 0, :4000] - golden_stoi["tap_resampled_clean"])))
+    ref_tob = golden_stoi["tap_tob"]
+    tob = taps["tob"].cpu().numpy()
+    u = ref_tob.shape[2]
+    d_tob = float(max(np.max(np.abs(tob[0, 0, :, :u] - ref_tob[0])), np.max(np.abs(tob[1, 0, :, :u] - ref_tob[1]))) / ref_tob.max())
+    _report("stoi/taps", {"resampled_abs": d_res, "tob_rel_of_max": d_tob})
+    assert d_res <= 5e-7
+    assert d_tob <= 2e-5
+
+
+def test_stoi_host_entry_equals_device_entry(stoi_metrics):
+    clean, deg, _, fs = STOI_CASES["speech16k_3s"]
+    metric = stoi_metrics(fs)
+    dev = metric(torch.from_numpy(clean).cuda(), torch.from_numpy(deg).cuda())
+    host = metric(torch.from_numpy(clean), torch.from_numpy(deg))
+    assert dev == host
+
+
+def test_stoi_errors(stoi_metrics, golden_stoi):
+    metric = stoi_metrics(10000)
+    assert int(golden_stoi["err_no_segments"]) == 1
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        with pytest.raises(TypeError):                     # STOI.py:163-165, 205
+            metric(torch.randn(2, 3000, device="cuda"), torch.randn(2, 3000, device="cuda"))
+        assert any(issubclass(x.category, RuntimeWarning) for x in w)
+    with pytest.raises(Exception, match="same shape"):
+        metric(torch.randn(2, 8000, device="cuda"), torch.randn(2, 8001, device="cuda"))
+    with pytest.raises(AssertionError):
+        metric(None, torch.randn(2, 8000, device="cuda"))
+
+
+# ------------------------------------------------------------------------------------------ properties at size
+def test_properties_at_full_size(pesq, stoi_metrics):
+    """BASELINE configs[1]/[2] shapes (256 x 10 s PESQ, 1024 x 4 s STOI): size-independent
+    properties -- batch invariance (bit-exact), padded+lengths == sliced, identical pair ->
+    the reference's fixed points (4.6438887 / 1.0), monotone in SNR."""
+    from fast_speech_enhancement_metrics_b200.synth import synth_batch
+    g = torch.Generator(device="cuda").manual_seed(7)
+    base_c, base_d, _ = synth_batch(300, 8, 160000)
+    c = torch.from_numpy(base_c).cuda().repeat(32, 1)                 # 256 x 10 s
+    noise = torch.randn(c.shape, device="cuda", generator=g)
+    snr = torch.linspace(-5, 25, 256, device="cuda")[:, None]
+    d = c + noise * (c.pow(2).mean(1, keepdim=True) / 10 ** (snr / 10)).sqrt()
+    full = np.array([r["PESQ"] for r in pesq(c, d)])
+    assert np.all(np.isfinite(full)) and full.min() > 1.0 and full.max() < 4.65
+    sub = np.array([r["PESQ"] for r in pesq(c[100:108].clone(), d[100:108].clone())])
+    assert np.array_equal(sub, full[100:108])                        # batch invariance, bit for bit
+    same = np.array([r["PESQ"] for r in pesq(c[:16], c[:16].clone())])
+    assert np.max(np.abs(same - 4.6438887)) <= 1e-4
+    # higher SNR -> better score for the same clean item (items i and i+8k share the clean signal)
+    per_clean = full.reshape(32, 8)
+    assert np.all(per_clean[-1] > per_clean[0])
+    # padded batch + lengths == per-item slices
+    lens = [160000, 48000, 16000 + 37, 5376, 99999, 160000, 8192, 30000]
+    padded = np.array([r["PESQ"] for r in pesq(c[:8], d[:8], lengths=lens)])
+    sliced = np.array([pesq(c[i:i + 1, :n].contiguous(), d[i:i + 1, :n].contiguous())[0]["PESQ"] for i, n in enumerate(lens)])
+    assert np.max(np.abs(padded - sliced)) <= 2e-6
+
+    st = stoi_metrics(16000)
+    c4 = c[:, :64000].repeat(4, 1).contiguous()                      # 1024 x 4 s
+    d4 = d[:, :64000].repeat(4, 1).contiguous()
+    res = st(c4, d4)
+    s = np.array([r["STOI"] for r in res]); e = np.array([r["ESTOI"] for r in res])
+    assert np.all(np.isfinite(s)) and np.all(np.isfinite(e)) and s.max() <= 1.0 + 1e-6
+    assert np.array_equal(s[:256], s[256:512]) and np.array_equal(e[:256], e[768:])
+    sub = st(c4[300:304].clone(), d4[300:304].clone())
+    assert [r["STOI"] for r in sub] == s[300:304].tolist()
+    one = st(c4[:8], c4[:8].clone())
+    assert max(abs(r["STOI"] - 1.0) for r in one) <= 1e-5 and max(abs(r["ESTOI"] - 1.0) for r in one) <= 1e-5
+    lens = [64000, 30000, 20001, 64000, 12345, 50000, 64000, 40000]
+    padded = st(c4[:8], d4[:8], lengths=lens)
+    kp = st.last_kept_frames.clone()
+    for i, n in enumerate(lens):
+        r = st(c4[i:i + 1, :n].contiguous(), d4[i:i + 1, :n].contiguous())[0]
+        assert int(st.last_kept_frames[0]) == int(kp[i])
+        assert abs(r["STOI"] - padded[i]["STOI"]) <= 2e-6 and abs(r["ESTOI"] - padded[i]["ESTOI"]) <= 2e-6

@@ -1,0 +1,96 @@
+"""CPU tests (-m "not gpu"): host-side design code, the C-ABI library's exports, and the
+shape arithmetic shared by host and device.  No compute calls (there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+from scipy.signal import lfilter
+
+from fast_speech_enhancement_metrics_b200 import _lib, design, p862_tables
+from oracle import pesq_oracle as po
+from oracle import stoi_oracle as so
+from oracle import tables as otab
+from tests.conftest import ROOT
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    assert lib.fsem_version() == 100
+    header = open(os.path.join(ROOT, "include", "fsem.h")).read()
+    declared = set(re.findall(r"FSEM_API [^;(]*?\b(fsem_[a-z0-9_]+)\(", header))
+    assert declared == set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.fsem_last_error() is not None
+
+
+def test_struct_layouts_match_header_sizes():
+    # sizes implied by include/fsem.h (all members are 4-byte scalars except the taps pointer)
+    assert ctypes.sizeof(design.PesqDesign) == 4 * (1 + 4 * 5 + 3 + 2 + 15 + 1 + 512 + 6 * 49 + 1)
+    assert ctypes.sizeof(design.StoiDesign) == 16 + 8 + 4 * 256 + 4 * 30 + 8
+    assert ctypes.sizeof(_lib.Batch) == 48
+
+
+def test_tables_agree_with_oracle_copy():
+    assert np.array_equal(p862_tables.BINS_PER_BAND, otab.BINS_PER_BAND)
+    assert np.array_equal(p862_tables.CENTRE_BARK, otab.BAND_CENTRE_BARK)
+    assert np.array_equal(p862_tables.WIDTH_BARK, otab.BAND_WIDTH_BARK)
+    assert np.array_equal(p862_tables.POW_DENS_CORRECTION, otab.POWER_DENSITY_CORRECTION)
+    assert np.array_equal(p862_tables.ABS_THRESH_POWER, otab.ABS_THRESHOLD_POWER)
+
+
+def test_pesq_design_reproduces_the_reference_filter(golden_pesq):
+    b32, a32 = design.power_filter_f32()
+    assert np.array_equal(b32, golden_pesq["tap_power_filter"][0])
+    assert np.array_equal(a32, golden_pesq["tap_power_filter"][1])
+    d = design.pesq_design()
+    assert np.array_equal(np.array(d.hann[:], np.float32), golden_pesq["tap_hann512"])
+    # the float32 parallel form run in float64 reproduces the direct form's band power
+    rng = np.random.default_rng(0)
+    x = lfilter([1.0], [1.0, -0.97], rng.standard_normal(20000))
+    y = d.bp_direct * x
+    for s in range(5):
+        y = y + lfilter([d.bp_c0[s], d.bp_c1[s]], [1.0, d.bp_a1[s], d.bp_a2[s]], x)
+    p_ref = po.band_power(x)
+    assert abs(np.dot(y, y) - p_ref) <= 2e-5 * p_ref
+    assert d.warmup % 64 == 0 and 512 <= d.warmup <= 1024
+    assert list(d.band_first_bin[:3]) == [0, 1, 2] and d.band_first_bin[48] + d.band_num_bins[48] == 256
+
+
+def test_stoi_design_matches_reference_constants(golden_stoi):
+    d, taps = design.stoi_design(16000)
+    assert (d.orig, d.neu, d.width, d.ntaps) == (8, 5, 10, 28)
+    assert np.array_equal(taps, golden_stoi["tap_resample_kernel"])
+    assert np.array_equal(np.array(d.window[:], np.float32), golden_stoi["tap_window"])
+    obm = np.zeros((15, 257), np.float32)
+    for i in range(15):
+        obm[i, d.band_lo[i]:d.band_hi[i]] = 1
+    assert np.array_equal(obm, golden_stoi["tap_obm"])
+    d10, taps10 = design.stoi_design(10000)
+    assert d10.orig == d10.neu and taps10 is None
+    t, w, o, n = design.sinc_hann_kernel(8000, 10000)
+    ot, ow, oo, on = so.resample_kernel(8000, 10000)
+    assert (w, o, n) == (ow, oo, on) and np.array_equal(t, ot)
+
+
+def test_metric_constructor_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from fast_speech_enhancement_metrics_b200 import PESQ, STOI
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        PESQ(16000, use_gpu=True)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        STOI(16000, use_gpu=False)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "fast_speech_enhancement_metrics_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
+                assert "/root/reference" not in text, f
