@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- PESQ + STOI/ESTOI audio-seconds scored per second on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--seconds S]
+
+Workload (BASELINE.json configs[4]): PESQ + STOI/ESTOI of a batch of 8192 x 10 s synthetic
+speech-like pairs at 16 kHz, batch-sharded over the N ranks (strong scaling: 8192 / N items per
+GPU), only the per-item scores gathered with one NCCL all-gather.  One "step" = one PESQ call plus
+one STOI call over the whole (sharded) batch = 81 920 audio-seconds.
+
+  value  : device-resident inputs -> scores on device (+ all-gather), CUDA events on the launching
+           stream, barrier + synchronize on both sides, max over ranks.
+  e2e    : the same through the public API `PESQ(...)(clean, denoised)` / `STOI(...)(clean, denoised)`
+           with pinned HOST tensors: the library's host entry point copies H->D in chunks overlapped
+           with compute and copies the scores back, every step.
+  roofline: dominant kernel (largest device time in the step, measured live with CUDA events around
+           every launch): algorithmic bytes of its metric call (8 B per sample pair = 128 000 B per
+           audio-second) / its average duration, against MEASURED_PEAKS.json's hbm_gbs.
+  cpu_baseline / --impl reference: the numpy oracle port (oracle/) of the reference's CPU path on the
+           host cores (one process per core), on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "PESQ+STOI audio-seconds scored/sec"
+UNIT = "audio-s/s"
+FS = 16000
+BYTES_PER_AUDIO_SECOND_PER_METRIC = 2 * 4 * FS   # two fp32 signals read once
+
+
+# ------------------------------------------------------------------------------------------ data
+def make_shard(batch: int, n: int, seed: int, device):
+    """Synthetic speech-like pairs (recipe of fast_speech_enhancement_metrics_b200.synth): a pool of
+    seeded numpy items (low-passed noise x syllabic envelope + -60 dB floor), expanded on the GPU
+    with a per-item circular shift and gain; degraded = clean + white noise at SNR ~ U[-5, 25] dB."""
+    import numpy as np
+    import torch
+
+    from fast_speech_enhancement_metrics_b200.synth import synth_batch
+    pool = min(batch, 256)
+    base, _, _ = synth_batch(seed, pool, n)
+    base = torch.from_numpy(base).to(device)
+    g = torch.Generator(device=device).manual_seed(seed)
+    clean = torch.empty(batch, n, dtype=torch.float32, device=device)
+    for i0 in range(0, batch, pool):
+        cnt = min(pool, batch - i0)
+        shift = int(torch.randint(0, n, (1,), generator=g, device=device).item())
+        gain = 0.5 + torch.rand(cnt, 1, generator=g, device=device)
+        clean[i0:i0 + cnt] = torch.roll(base[:cnt], shifts=shift, dims=1) * gain
+    deg = torch.empty_like(clean)
+    snr = torch.rand(batch, 1, generator=g, device=device) * 30.0 - 5.0
+    step = 512
+    for i0 in range(0, batch, step):
+        c = clean[i0:i0 + step]
+        noise = torch.randn(c.shape, generator=g, device=device)
+        scale = (c.pow(2).mean(1, keepdim=True) / 10.0 ** (snr[i0:i0 + step] / 10.0)).sqrt()
+        deg[i0:i0 + step] = c + noise * scale
+    return clean, deg
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ CPU baseline
+def _cpu_worker(args):
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    seed, n = args
+    import numpy as np
+
+    from fast_speech_enhancement_metrics_b200.synth import synth_batch
+    from oracle import pesq_oracle, stoi_oracle
+    clean, deg, _ = synth_batch(seed, 1, n)
+    t = time.perf_counter()
+    p = pesq_oracle.pesq_batch(clean, deg)
+    s, e, _ = stoi_oracle.stoi_batch(clean, deg, FS)
+    return time.perf_counter() - t, float(p[0]), float(s[0]), float(e[0])
+
+
+def cpu_baseline(n: int, items: int, cores: int, repeats: int = 1) -> dict:
+    """Oracle port of the reference's CPU path (PESQ + STOI per item), one process per core."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    best = None
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(9000 + i, 16000) for i in range(cores)])      # warm the workers
+        for r in range(repeats):
+            t0 = time.perf_counter()
+            pool.map(_cpu_worker, [(1000 + i, n) for i in range(items)], chunksize=1)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    audio_s = items * n / FS
+    return {"value": audio_s / best, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d items x %.0f s (PESQ+STOI per item, numpy oracle port of the reference CPU path, "
+                      "%d worker processes, best of %d)" % (items, n / FS, cores, repeats),
+            "seconds": best}
+
+
+def host_cores() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = host_cores()
+    n = int(args.seconds * FS)
+    items = max(cores, 16)
+    times = []
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(9000 + i, 16000) for i in range(cores)])
+        for step in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            pool.map(_cpu_worker, [(1000 + step * items + i, n) for i in range(items)], chunksize=1)
+            dt = time.perf_counter() - t0
+            if step >= args.warmup:
+                times.append(dt)
+    audio_s = items * n / FS
+    total = sum(times)
+    value = audio_s * len(times) / total
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+        "config": {"workload": "PESQ+STOI/ESTOI, %d x %.0f s @16 kHz (BASELINE configs[4]); each step a bounded "
+                               "sample of %d items" % (args.batch, args.seconds, items),
+                   "sample_items_per_step": items},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d items x %.0f s per step, numpy oracle port of the reference CPU path "
+                                   "(use_gpu=False), %d worker processes" % (items, args.seconds, cores)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ main arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8192, help="total items over all ranks")
+    ap.add_argument("--seconds", type=float, default=10.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from fast_speech_enhancement_metrics_b200 import PESQ, STOI, _lib
+    from fast_speech_enhancement_metrics_b200.dist import gather_scores, shard_range
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    elif args.gpus > 1:
+        print("bench.py: --gpus %d needs torchrun (WORLD_SIZE is 1); running 1 rank" % args.gpus, file=sys.stderr)
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    n = int(args.seconds * FS)
+    lo, hi = shard_range(args.batch, world, rank)
+    local_b = hi - lo
+    audio_s_total = args.batch * n / FS
+
+    pesq = PESQ(FS, use_gpu=True)
+    stoi = STOI(FS, use_gpu=True)
+    clean, deg = make_shard(local_b, n, 1000 + rank, device)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    gathered = torch.empty(args.batch, 3, dtype=torch.float32, device=device)
+
+    def step_device():
+        mos, _ = pesq.score_tensors(clean, deg)
+        sc, _, _ = stoi.score_tensors(clean, deg)
+        local = torch.stack([mos, sc[0], sc[1]], dim=1)
+        return gather_scores(local, args.batch, world, out=gathered)
+
+    # ---- value: device-resident inputs
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _lib.profile_reset()
+    _lib.profile_enable(True)
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step_device()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = _lib.launch_count() - launches0
+    _lib.profile_enable(False)
+    prof = _lib.profile_read()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = audio_s_total / (ms_per_step * 1e-3)
+    scores = out.cpu().numpy()
+    finite = float(np.isfinite(scores).mean())
+
+    # ---- e2e: public API with pinned host tensors (H2D + compute + D2H every step)
+    e2e = None
+    if not args.no_e2e:
+        hc = torch.empty(clean.shape, dtype=torch.float32, pin_memory=True).copy_(clean)
+        hd = torch.empty(deg.shape, dtype=torch.float32, pin_memory=True).copy_(deg)
+        torch.cuda.synchronize()
+
+        def step_e2e():
+            p = pesq(hc, hd)
+            s = stoi(hc, hd)
+            local = torch.tensor([[a["PESQ"], b["STOI"], b["ESTOI"]] for a, b in zip(p, s)], dtype=torch.float32)
+            if world > 1:
+                return gather_scores(local.to(device), args.batch, world, out=gathered).cpu()
+            return local
+
+        e_steps = max(1, min(args.steps, 3))
+        step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            step_e2e()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": audio_s_total * e_steps / float(dt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(2 * 2 * args.batch * n * 4),      # 2 metric calls x 2 signals
+               "d2h_bytes_per_step": int(args.batch * (8 + 16)),           # mos+status, stoi+estoi+K+status
+               "steps": e_steps, "api": "PESQ(16000)(clean_cpu, deg_cpu) + STOI(16000)(clean_cpu, deg_cpu), pinned"}
+        del hc, hd
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in prof.items()}
+    top = max(prof.items(), key=lambda kv: kv[1][0])
+    top_name, (top_ms, top_cnt) = top
+    local_audio_s = local_b * n / FS
+    alg_bytes = BYTES_PER_AUDIO_SECOND_PER_METRIC * local_audio_s          # per launch (one launch per metric call)
+    top_avg_ms = top_ms / max(top_cnt, 1)
+    achieved = alg_bytes / (top_avg_ms * 1e-3) / 1e9
+    traffic_path = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    traffic = None
+    if os.path.exists(traffic_path):
+        traffic = json.load(open(traffic_path)).get(top_name)
+    roofline = {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": top_avg_ms,
+                "note": "FP32-issue-bound path (SURVEY 7.2): the HBM fraction is reported as the metric asks"}
+    step_bytes = 2 * BYTES_PER_AUDIO_SECOND_PER_METRIC * local_audio_s
+    roofline_step = {"achieved": step_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                     "algorithmic_bytes_per_step_per_gpu": step_bytes}
+
+    cpu = None
+    if not args.no_cpu and world == 1:
+        cores = host_cores()
+        cpu = cpu_baseline(n, max(64, 4 * cores), cores)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "PESQ + STOI/ESTOI, %d x %.0f s @16 kHz, batch-sharded over %d GPU(s) "
+                               "(BASELINE configs[4])" % (args.batch, args.seconds, world),
+                   "batch_total": args.batch, "batch_per_gpu": local_b, "samples": n, "sample_rate": FS,
+                   "l2": "inputs (%.1f GB per GPU) exceed L2; no flush" % (2 * local_b * n * 4 / 1e9),
+                   "collective": "all_gather of [batch/N, 3] fp32 scores (NCCL)" if world > 1 else "none"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "roofline_step": roofline_step, "kernels": kernels, "cpu_baseline": cpu,
+        "finite_score_fraction": finite,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

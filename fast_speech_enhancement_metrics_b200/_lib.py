@@ -24,6 +24,7 @@ ITEM_OK, ITEM_TOO_SHORT, ITEM_NAN = 0, 1, 2
 # every symbol include/fsem.h declares
 EXPORTS = [
     "fsem_version", "fsem_last_error", "fsem_launch_count",
+    "fsem_profile_enable", "fsem_profile_reset", "fsem_profile_read",
     "fsem_pesq_create", "fsem_pesq_destroy", "fsem_pesq_workspace_bytes", "fsem_pesq_score_f32",
     "fsem_pesq_score_host_f32", "fsem_pesq_debug_taps",
     "fsem_stoi_create", "fsem_stoi_destroy", "fsem_stoi_workspace_bytes", "fsem_stoi_score_f32",
@@ -61,6 +62,8 @@ def load() -> C.CDLL:
     lib.fsem_version.restype = C.c_int
     lib.fsem_last_error.restype = C.c_char_p
     lib.fsem_launch_count.restype = C.c_int64
+    lib.fsem_profile_enable.argtypes = [C.c_int]
+    lib.fsem_profile_read.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.fsem_pesq_create.argtypes = [C.POINTER(vp), C.POINTER(PesqDesign)]
     lib.fsem_pesq_destroy.argtypes = [vp]
     lib.fsem_pesq_workspace_bytes.argtypes = [vp, i64, i64]
@@ -91,3 +94,22 @@ def check(code: int) -> None:
 
 def launch_count() -> int:
     return int(load().fsem_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    load().fsem_profile_enable(1 if on else 0)
+
+
+def profile_reset() -> None:
+    load().fsem_profile_reset()
+
+
+def profile_read() -> dict:
+    """{kernel name: (total device ms, launches)} accumulated since the last reset."""
+    lib, out = load(), {}
+    for i in range(9):
+        name, ms, cnt = C.c_char_p(), C.c_double(), C.c_int64()
+        if lib.fsem_profile_read(i, C.byref(name), C.byref(ms), C.byref(cnt)) != FSEM_OK:
+            break
+        out[name.value.decode()] = (ms.value, cnt.value)
+    return out

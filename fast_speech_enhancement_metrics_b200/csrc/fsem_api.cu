@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "fsem_common.cuh"
 #include "fsem_pesq.cuh"
@@ -41,6 +42,49 @@ int fail(int code, const char* fmt, ...) {
     } while (0)
 
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+// ---- optional per-kernel timing with CUDA events on the launching stream (bench.py only; not thread-safe)
+enum KernelId {
+    K_PESQ_FILTER = 0, K_PESQ_SPECTRUM, K_PESQ_BARK, K_STOI_RESAMPLE, K_STOI_ENERGY, K_STOI_COMPACT,
+    K_STOI_TOB, K_STOI_SEGMENT, K_STOI_FINALIZE, K_COUNT
+};
+const char* const kKernelNames[K_COUNT] = {
+    "pesq_filter_kernel", "pesq_spectrum_kernel", "pesq_bark_kernel", "stoi_resample_kernel", "stoi_energy_kernel",
+    "stoi_compact_kernel", "stoi_tob_kernel", "stoi_segment_kernel", "stoi_finalize_kernel"};
+bool g_profile = false;
+struct ProfRecord { int id; cudaEvent_t start, stop; };
+std::vector<ProfRecord> g_prof_pending;
+std::vector<cudaEvent_t> g_prof_pool;
+double g_prof_ms[K_COUNT] = {0};
+int64_t g_prof_launches[K_COUNT] = {0};
+
+cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+struct ProfScope {
+    int id; cudaStream_t stream; cudaEvent_t start = nullptr;
+    ProfScope(int id_, cudaStream_t s) : id(id_), stream(s) {
+        if (g_profile) { start = prof_event(); cudaEventRecord(start, stream); }
+    }
+    ~ProfScope() {
+        if (start) { cudaEvent_t stop = prof_event(); cudaEventRecord(stop, stream); g_prof_pending.push_back({id, start, stop}); }
+    }
+};
+void prof_collect() {
+    for (auto& r : g_prof_pending) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.stop) == cudaSuccess && cudaEventElapsedTime(&ms, r.start, r.stop) == cudaSuccess) {
+            g_prof_ms[r.id] += ms;
+            g_prof_launches[r.id] += 1;
+        }
+        g_prof_pool.push_back(r.start);
+        g_prof_pool.push_back(r.stop);
+    }
+    g_prof_pending.clear();
+}
 
 struct DeviceInfo {
     int device = -1;
@@ -129,6 +173,20 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 extern "C" int fsem_version(void) { return FSEM_VERSION; }
 extern "C" const char* fsem_last_error(void) { return g_err; }
 extern "C" int64_t fsem_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+extern "C" int fsem_profile_enable(int on) { g_profile = on != 0; return FSEM_OK; }
+extern "C" int fsem_profile_reset(void) {
+    prof_collect();
+    for (int i = 0; i < K_COUNT; ++i) { g_prof_ms[i] = 0; g_prof_launches[i] = 0; }
+    return FSEM_OK;
+}
+extern "C" int fsem_profile_read(int index, const char** name, double* total_ms, int64_t* launches) {
+    if (index < 0 || index >= K_COUNT) return FSEM_E_INVALID;
+    prof_collect();
+    if (name) *name = kKernelNames[index];
+    if (total_ms) *total_ms = g_prof_ms[index];
+    if (launches) *launches = g_prof_launches[index];
+    return FSEM_OK;
+}
 
 // ================================================================================================
 // PESQ
@@ -277,13 +335,15 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
         const unsigned grid = (unsigned)ceil_div(threads, 128);
         const bool vec4 = aligned16(in->clean) && aligned16(in->deg) && (in->stride % 4 == 0);
         if (vec4)
-            pesq_filter_kernel<true><<<grid, 128, 0, stream>>>(in->clean, in->deg, in->lengths, in->batch, in->n,
-                                                              in->stride, p.chunk, p.nchunks, ctx->warm, ctx->coef,
-                                                              z, p.zstride, partial);
+            { ProfScope prof_(K_PESQ_FILTER, stream);
+              pesq_filter_kernel<true><<<grid, 128, 0, stream>>>(in->clean, in->deg, in->lengths, in->batch, in->n,
+                                                                in->stride, p.chunk, p.nchunks, ctx->warm, ctx->coef,
+                                                                z, p.zstride, partial); }
         else
-            pesq_filter_kernel<false><<<grid, 128, 0, stream>>>(in->clean, in->deg, in->lengths, in->batch, in->n,
-                                                               in->stride, p.chunk, p.nchunks, ctx->warm, ctx->coef,
-                                                               z, p.zstride, partial);
+            { ProfScope prof_(K_PESQ_FILTER, stream);
+              pesq_filter_kernel<false><<<grid, 128, 0, stream>>>(in->clean, in->deg, in->lengths, in->batch, in->n,
+                                                                 in->stride, p.chunk, p.nchunks, ctx->warm, ctx->coef,
+                                                                 z, p.zstride, partial); }
         FSEM_LAUNCHED();
     }
     {   // kernel B
@@ -291,14 +351,16 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
         int64_t grid = ceil_div(units, kSpecWarps);
         const int64_t cap = (int64_t)ctx->dev.sms * ctx->spec_ctas_per_sm;
         if (grid > cap) grid = cap;
-        pesq_spectrum_kernel<<<(unsigned)grid, kSpecWarps * 32, 0, stream>>>(z, p.zstride, in->lengths, in->batch,
-                                                                            in->n, p.tmax, ctx->d_tab, bark);
+        { ProfScope prof_(K_PESQ_SPECTRUM, stream);
+          pesq_spectrum_kernel<<<(unsigned)grid, kSpecWarps * 32, 0, stream>>>(z, p.zstride, in->lengths, in->batch,
+                                                                              in->n, p.tmax, ctx->d_tab, bark); }
         FSEM_LAUNCHED();
     }
     {   // kernel C
-        pesq_bark_kernel<<<(unsigned)in->batch, kBarkThreads, 0, stream>>>(bark, partial, p.nchunks, in->lengths,
-                                                                          in->batch, in->n, p.tmax, ctx->d_tab, dist,
-                                                                          mos_out, status_out, power);
+        { ProfScope prof_(K_PESQ_BARK, stream);
+          pesq_bark_kernel<<<(unsigned)in->batch, kBarkThreads, 0, stream>>>(bark, partial, p.nchunks, in->lengths,
+                                                                            in->batch, in->n, p.tmax, ctx->d_tab, dist,
+                                                                            mos_out, status_out, power); }
         FSEM_LAUNCHED();
     }
     return FSEM_OK;
@@ -503,9 +565,10 @@ extern "C" int fsem_stoi_score_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t* in,
     int64_t sstride = in->stride;
     if (p.resample) {
         dim3 grid((unsigned)ceil_div(p.lmax, 256), (unsigned)(2 * in->batch));
-        stoi_resample_kernel<<<grid, 256, 0, stream>>>(in->clean, in->deg, in->lengths, in->batch, in->n, in->stride,
-                                                      ctx->d_taps, ctx->orig, ctx->neu, ctx->width, ctx->ntaps, y,
-                                                      p.ystride);
+        { ProfScope prof_(K_STOI_RESAMPLE, stream);
+          stoi_resample_kernel<<<grid, 256, 0, stream>>>(in->clean, in->deg, in->lengths, in->batch, in->n, in->stride,
+                                                        ctx->d_taps, ctx->orig, ctx->neu, ctx->width, ctx->ntaps, y,
+                                                        p.ystride); }
         FSEM_LAUNCHED();
         c10 = y;
         d10 = y + in->batch * p.ystride;
@@ -513,14 +576,16 @@ extern "C" int fsem_stoi_score_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t* in,
     }
     {
         const int64_t warps = in->batch * (int64_t)p.t0max;
-        stoi_energy_kernel<<<(unsigned)ceil_div(warps * 32, 256), 256, 0, stream>>>(
-            c10, sstride, in->lengths, in->batch, in->n, ctx->orig, ctx->neu, p.t0max, ctx->d_tab, energy);
+        { ProfScope prof_(K_STOI_ENERGY, stream);
+          stoi_energy_kernel<<<(unsigned)ceil_div(warps * 32, 256), 256, 0, stream>>>(
+              c10, sstride, in->lengths, in->batch, in->n, ctx->orig, ctx->neu, p.t0max, ctx->d_tab, energy); }
         FSEM_LAUNCHED();
     }
     {
-        stoi_compact_kernel<<<(unsigned)ceil_div(in->batch * 32, 128), 128, 0, stream>>>(
-            energy, in->lengths, in->batch, in->n, ctx->orig, ctx->neu, p.t0max, p.mask_words, ctx->dyn_range,
-            kept_idx, kept_count, mask);
+        { ProfScope prof_(K_STOI_COMPACT, stream);
+          stoi_compact_kernel<<<(unsigned)ceil_div(in->batch * 32, 128), 128, 0, stream>>>(
+              energy, in->lengths, in->batch, in->n, ctx->orig, ctx->neu, p.t0max, p.mask_words, ctx->dyn_range,
+              kept_idx, kept_count, mask); }
         FSEM_LAUNCHED();
     }
     if (p.umax > 0) {
@@ -528,16 +593,19 @@ extern "C" int fsem_stoi_score_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t* in,
         int64_t grid = ceil_div(units, kTobWarps);
         const int64_t cap = (int64_t)ctx->dev.sms * ctx->tob_ctas_per_sm;
         if (grid > cap) grid = cap;
-        stoi_tob_kernel<<<(unsigned)grid, kTobWarps * 32, 0, stream>>>(c10, d10, sstride, in->batch, p.t0max, p.umax,
-                                                                      p.ustride, kept_idx, kept_count, ctx->d_tab, tob);
+        { ProfScope prof_(K_STOI_TOB, stream);
+          stoi_tob_kernel<<<(unsigned)grid, kTobWarps * 32, 0, stream>>>(c10, d10, sstride, in->batch, p.t0max, p.umax,
+                                                                        p.ustride, kept_idx, kept_count, ctx->d_tab, tob); }
         FSEM_LAUNCHED();
     }
     {
-        stoi_segment_kernel<<<(unsigned)(in->batch * p.ntiles), kSegThreads, 0, stream>>>(
-            tob, in->batch, p.ustride, p.ntiles, kept_count, ctx->clip, partial);
+        { ProfScope prof_(K_STOI_SEGMENT, stream);
+          stoi_segment_kernel<<<(unsigned)(in->batch * p.ntiles), kSegThreads, 0, stream>>>(
+              tob, in->batch, p.ustride, p.ntiles, kept_count, ctx->clip, partial); }
         FSEM_LAUNCHED();
-        stoi_finalize_kernel<<<(unsigned)ceil_div(in->batch, 128), 128, 0, stream>>>(
-            partial, in->batch, p.ntiles, kept_count, stoi_out, estoi_out, kept_frames_out, status_out);
+        { ProfScope prof_(K_STOI_FINALIZE, stream);
+          stoi_finalize_kernel<<<(unsigned)ceil_div(in->batch, 128), 128, 0, stream>>>(
+              partial, in->batch, p.ntiles, kept_count, stoi_out, estoi_out, kept_frames_out, status_out); }
         FSEM_LAUNCHED();
     }
     return FSEM_OK;

@@ -125,6 +125,13 @@ FSEM_API const char* fsem_last_error(void);
 /* number of kernel launches issued by this library on the calling thread since load */
 FSEM_API int64_t fsem_launch_count(void);
 
+/* Optional per-kernel timing (CUDA events on the launching stream).  Bench/diagnostics only,
+ * process-global and not thread-safe.  fsem_profile_read synchronises on the recorded events and
+ * returns the accumulated device time and launch count of kernel `index` (0 <= index < 9). */
+FSEM_API int fsem_profile_enable(int on);
+FSEM_API int fsem_profile_reset(void);
+FSEM_API int fsem_profile_read(int index, const char** name, double* total_ms, int64_t* launches);
+
 /* ------------------------------------------------------------------ PESQ */
 FSEM_API int fsem_pesq_create(fsem_pesq_ctx_t** out, const fsem_pesq_design_t* design);
 FSEM_API int fsem_pesq_destroy(fsem_pesq_ctx_t* ctx);
@@ -138,8 +145,9 @@ FSEM_API int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in, f
 FSEM_API int fsem_pesq_score_host_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in, float* mos_out,
                              int32_t* status_out);
 /* Stage taps for parity tests (device pointers, after a score call on the same workspace):
- * copies the Bark-band power densities [2, batch, frames, 49] (clean then degraded, level-aligned)
- * into `bark_out` and the band-pass energies sum(y^2) [2, batch] (double) into `power_out`. */
+ * copies the Bark-band power densities [2, batch, frames, 49] (clean then degraded, BEFORE level
+ * alignment: multiply by g^2 = 1e7 * (n + 5120) * 1.04684 / power) into `bark_out` and the
+ * band-pass energies sum(y^2) [2, batch] (double) into `power_out`. */
 FSEM_API int fsem_pesq_debug_taps(fsem_pesq_ctx_t* ctx, int64_t batch, int64_t n, const void* workspace,
                          float* bark_out, double* power_out, int64_t* frames_out, void* stream);
 
