@@ -252,7 +252,7 @@ extern "C" int fsem_pesq_create(fsem_pesq_ctx_t** out, const fsem_pesq_design_t*
     }
     ctx->coef.pb0 = d->pre_b[0]; ctx->coef.pb1 = d->pre_b[1]; ctx->coef.pb2 = d->pre_b[2];
     ctx->coef.pa1 = d->pre_a[0]; ctx->coef.pa2 = d->pre_a[1];
-    ctx->warm = (int)round_up(d->warmup > 0 ? d->warmup : 640, 4);
+    ctx->warm = (int)round_up(d->warmup > 0 ? d->warmup : 640, 32);
     for (int k = 0; k < 15; ++k) {
         if (fabsf(d->taper[k] - (float)(k + 1) * 0.0625f) > 1e-7f) {
             delete ctx;
@@ -265,9 +265,11 @@ extern "C" int fsem_pesq_create(fsem_pesq_ctx_t** out, const fsem_pesq_design_t*
     for (int b = 0; b < FSEM_PESQ_NBANDS; ++b) {
         h.band_first[b] = d->band_first_bin[b];
         h.band_count[b] = d->band_num_bins[b];
-        if (h.band_first[b] < 0 || h.band_count[b] < 0 || h.band_first[b] + h.band_count[b] > 256) {
+        const int expect_first = b == 0 ? 0 : h.band_first[b - 1] + h.band_count[b - 1];
+        if (h.band_first[b] != expect_first || h.band_count[b] < 1 || h.band_count[b] > 32 ||
+            h.band_first[b] + h.band_count[b] > 256) {
             delete ctx;
-            return fail(FSEM_E_INVALID, "fsem_pesq_create: band %d outside bins 0..255", b);
+            return fail(FSEM_E_INVALID, "fsem_pesq_create: Bark bands must tile bins 0..255 contiguously, at most 32 bins each (band %d)", b);
         }
         h.pow_dens[b] = d->pow_dens[b];
         h.thresh[b] = d->thresh[b];
@@ -331,19 +333,20 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
     double* power = reinterpret_cast<double*>(ws + p.off_power);
 
     {   // kernel A
-        const int64_t threads = 2 * in->batch * p.nchunks;
-        const unsigned grid = (unsigned)ceil_div(threads, 128);
         const bool vec4 = aligned16(in->clean) && aligned16(in->deg) && (in->stride % 4 == 0);
-        if (vec4)
+        if (vec4) {
+            const int64_t units = ceil_div(2 * in->batch, 32) * p.nchunks;
             { ProfScope prof_(K_PESQ_FILTER, stream);
-              pesq_filter_kernel<true><<<grid, 128, 0, stream>>>(in->clean, in->deg, in->lengths, in->batch, in->n,
-                                                                in->stride, p.chunk, p.nchunks, ctx->warm, ctx->coef,
-                                                                z, p.zstride, partial); }
-        else
+              pesq_filter_tiled_kernel<<<(unsigned)ceil_div(units, kFiltWarps), kFiltWarps * 32, 0, stream>>>(
+                  in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, p.chunk, p.nchunks, ctx->warm,
+                  ctx->coef, z, p.zstride, partial); }
+        } else {
+            const int64_t threads = 2 * in->batch * p.nchunks;
             { ProfScope prof_(K_PESQ_FILTER, stream);
-              pesq_filter_kernel<false><<<grid, 128, 0, stream>>>(in->clean, in->deg, in->lengths, in->batch, in->n,
-                                                                 in->stride, p.chunk, p.nchunks, ctx->warm, ctx->coef,
-                                                                 z, p.zstride, partial); }
+              pesq_filter_kernel<false><<<(unsigned)ceil_div(threads, 128), 128, 0, stream>>>(
+                  in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, p.chunk, p.nchunks, ctx->warm,
+                  ctx->coef, z, p.zstride, partial); }
+        }
         FSEM_LAUNCHED();
     }
     {   // kernel B
@@ -441,6 +444,8 @@ struct fsem_stoi_ctx {
     DeviceInfo dev;
     int orig = 1, neu = 1, width = 0, ntaps = 0;
     float* d_taps = nullptr;
+    bool fast85 = false;        // taps fit the specialised 8:5 kernel
+    Resample85Taps taps85;
     StoiTables* d_tab = nullptr;
     float clip = 0.f, dyn_range = 40.f;
     int tob_ctas_per_sm = 2;
@@ -493,6 +498,9 @@ extern "C" int fsem_stoi_create(fsem_stoi_ctx_t** out, const fsem_stoi_design_t*
     for (int b = 0; b < FSEM_STOI_NBANDS; ++b)
         if (d->band_lo[b] < 0 || d->band_hi[b] < d->band_lo[b] || d->band_hi[b] > 256)
             return fail(FSEM_E_INVALID, "fsem_stoi_create: band %d outside bins 0..255", b);
+    for (int b = 0; b + 1 < FSEM_STOI_NBANDS; ++b)
+        if (d->band_hi[b] != d->band_lo[b + 1] || d->band_hi[b] - d->band_lo[b] > 48)
+            return fail(FSEM_E_INVALID, "fsem_stoi_create: third-octave bands must be contiguous and at most 48 bins wide");
     fsem_stoi_ctx* ctx = new (std::nothrow) fsem_stoi_ctx();
     if (!ctx) return fail(FSEM_E_INVALID, "out of host memory");
     int rc = query_device(ctx->dev);
@@ -515,6 +523,14 @@ extern "C" int fsem_stoi_create(fsem_stoi_ctx_t** out, const fsem_stoi_design_t*
         if (ctx->d_taps) cudaFree(ctx->d_taps);
         delete ctx;
         return fail(FSEM_E_CUDA, "fsem_stoi_create: %s", cudaGetErrorString(e));
+    }
+    if (d->orig == 8 && d->neu == 5 && d->width == 10 && d->ntaps == 28) {
+        ctx->fast85 = true;
+        for (int p = 0; p < 5; ++p)
+            for (int j = 0; j < 28; ++j) {
+                ctx->taps85.h[p][j] = d->taps[p * 28 + j];
+                if ((j < rs85_lo(p) || j > rs85_hi(p)) && d->taps[p * 28 + j] != 0.f) ctx->fast85 = false;
+            }
     }
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stoi_tob_kernel, kTobWarps * 32, 0) == cudaSuccess && occ > 0)
@@ -564,11 +580,23 @@ extern "C" int fsem_stoi_score_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t* in,
     const float* d10 = in->deg;
     int64_t sstride = in->stride;
     if (p.resample) {
-        dim3 grid((unsigned)ceil_div(p.lmax, 256), (unsigned)(2 * in->batch));
-        { ProfScope prof_(K_STOI_RESAMPLE, stream);
-          stoi_resample_kernel<<<grid, 256, 0, stream>>>(in->clean, in->deg, in->lengths, in->batch, in->n, in->stride,
-                                                        ctx->d_taps, ctx->orig, ctx->neu, ctx->width, ctx->ntaps, y,
-                                                        p.ystride); }
+        if (ctx->fast85) {
+            dim3 grid((unsigned)ceil_div(p.lmax, kRs85TileOut), (unsigned)(2 * in->batch));
+            const bool vec4 = aligned16(in->clean) && aligned16(in->deg) && (in->stride % 4 == 0);
+            { ProfScope prof_(K_STOI_RESAMPLE, stream);
+              if (vec4)
+                  stoi_resample85_kernel<true><<<grid, kRs85Threads, 0, stream>>>(
+                      in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, ctx->taps85, y, p.ystride);
+              else
+                  stoi_resample85_kernel<false><<<grid, kRs85Threads, 0, stream>>>(
+                      in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, ctx->taps85, y, p.ystride); }
+        } else {
+            dim3 grid((unsigned)ceil_div(p.lmax, 256), (unsigned)(2 * in->batch));
+            { ProfScope prof_(K_STOI_RESAMPLE, stream);
+              stoi_resample_kernel<<<grid, 256, 0, stream>>>(in->clean, in->deg, in->lengths, in->batch, in->n,
+                                                            in->stride, ctx->d_taps, ctx->orig, ctx->neu, ctx->width,
+                                                            ctx->ntaps, y, p.ystride); }
+        }
         FSEM_LAUNCHED();
         c10 = y;
         d10 = y + in->batch * p.ystride;

@@ -170,16 +170,85 @@ __device__ __forceinline__ void warp_fft512(float (&re)[16], float (&im)[16], fl
     __syncwarp();
 }
 
-// Power spectra of the two packed real frames at bin k (0 <= k < 256):
+// Power spectra of the two packed real frames from Z[k] (a) and Z[N-k] (b):
 //   |C[k]|^2 = ((Zr[k] + Zr[N-k])^2 + (Zi[k] - Zi[N-k])^2) / 4
 //   |D[k]|^2 = ((Zi[k] + Zi[N-k])^2 + (Zr[k] - Zr[N-k])^2) / 4
-__device__ __forceinline__ void packed_power(const float2* buf, int k, float& pc, float& pd) {
-    float2 a = buf[fft_out_index(k)];
-    float2 b = buf[fft_out_index((kFftN - k) & (kFftN - 1))];
+__device__ __forceinline__ void packed_power_pair(float2 a, float2 b, float& pc, float& pd) {
     float sr = a.x + b.x, dr = a.x - b.x;
     float si = a.y + b.y, di = a.y - b.y;
-    pc = 0.25f * (sr * sr + di * di);
-    pd = 0.25f * (si * si + dr * dr);
+    pc = 0.25f * fmaf(sr, sr, di * di);
+    pd = 0.25f * fmaf(si, si, dr * dr);
+}
+
+// Lane L gets the power of the 8 CONSECUTIVE bins k = 8L .. 8L+7 of both packed frames.
+// With fft_out_index(k) = 10*(k >> 3) + (k & 7) the eight Z[k] are four conflict-free LDS.128 at
+// buf + 10L, the mirrored Z[512-k], j = 1..7, are four LDS.128 at group 63-L, and Z[512-8L] is one LDS.64.
+__device__ __forceinline__ void packed_power8(const float2* buf, int lane, float (&pc)[8], float (&pd)[8]) {
+    float2 a[8], m[8];
+    const float4* pa = reinterpret_cast<const float4*>(buf + 10 * lane);
+    const float4* pm = reinterpret_cast<const float4*>(buf + 10 * (63 - lane));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float4 v = pa[i];
+        a[2 * i] = make_float2(v.x, v.y); a[2 * i + 1] = make_float2(v.z, v.w);
+        float4 w = pm[i];
+        m[2 * i] = make_float2(w.x, w.y); m[2 * i + 1] = make_float2(w.z, w.w);
+    }
+    const float2 b0 = buf[lane == 0 ? 0 : 10 * (64 - lane)];
+    packed_power_pair(a[0], b0, pc[0], pd[0]);
+#pragma unroll
+    for (int j = 1; j < 8; ++j) packed_power_pair(a[j], m[8 - j], pc[j], pd[j]);
+}
+
+// Static description of how one lane's 8 consecutive bins map onto contiguous frequency bands.
+struct BandPlan {
+    unsigned start_mask;   // bit j set: bin 8L + j is the first bin of a band
+    int first_band;        // index of the band that starts at the lowest set bit (bands are consecutive)
+    // Build from band start bins (ascending, starts[0] == 0 expected so that every bin belongs to a band).
+    __device__ __forceinline__ void init(const int32_t* starts, int nbands, int lane) {
+        start_mask = 0u;
+        first_band = 0x7fffffff;
+        for (int b = 0; b < nbands; ++b) {
+            int f = starts[b];
+            if ((f >> 3) == lane) {
+                start_mask |= 1u << (f & 7);
+                first_band = min(first_band, b);
+            }
+        }
+    }
+};
+
+// Segmented band sums of the two power rows.  Bands that live inside the lane are emitted directly, the band
+// that is open at the lane's right edge collects the head partials of the following lanes (at most kSpan of
+// them) through shuffles.  emit(band, sum_clean, sum_deg) is called by the lane in which the band STARTS.
+template <int kSpan, typename Emit>
+__device__ __forceinline__ void band_sums8(const float (&pc)[8], const float (&pd)[8], const BandPlan& plan, int lane,
+                                           Emit emit) {
+    float run_c = 0.f, run_d = 0.f, head_c = 0.f, head_d = 0.f;
+    int nb = -1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if ((plan.start_mask >> j) & 1u) {
+            if (nb < 0) { head_c = run_c; head_d = run_d; }
+            else emit(plan.first_band + nb, run_c, run_d);
+            ++nb;
+            run_c = 0.f; run_d = 0.f;
+        }
+        run_c += pc[j];
+        run_d += pd[j];
+    }
+    const bool transparent = nb < 0;           // no band starts here: all 8 bins continue an earlier band
+    if (transparent) { head_c = run_c; head_d = run_d; run_c = 0.f; run_d = 0.f; }
+    bool open = true;
+#pragma unroll
+    for (int d = 1; d <= kSpan; ++d) {
+        float hc = __shfl_down_sync(0xffffffffu, head_c, d);
+        float hd = __shfl_down_sync(0xffffffffu, head_d, d);
+        bool tr = __shfl_down_sync(0xffffffffu, transparent ? 1 : 0, d) != 0;
+        if (open && lane + d < 32) { run_c += hc; run_d += hd; }
+        open = open && tr && (lane + d < 32);
+    }
+    if (!transparent) emit(plan.first_band + nb, run_c, run_d);
 }
 
 }  // namespace fsem

@@ -167,6 +167,132 @@ pesq_filter_kernel(const float* __restrict__ clean, const float* __restrict__ de
 }
 
 // ------------------------------------------------------------------------------------------------
+// Kernel A, tiled variant (16-byte aligned rows): one warp = 32 SIGNALS x one time chunk, every lane
+// walking its own signal serially.  Global traffic is staged through a warp-private shared-memory tile of
+// 32 rows x 32 samples so that every LDG/STG is a coalesced 128-byte row segment (the direct variant above
+// issues 32 scattered 16-byte accesses per instruction and is bound by L1 wavefronts):
+//   fill   : 8 x (LDG.128 coalesced -> registers), then 8 x STS.128          (rows = signals)
+//   compute: lane l reads row l (8 x LDS.128, pitch 36 floats = conflict-free), runs both IIRs on 32
+//            samples, overwrites the row with z in place
+//   drain  : 8 x (LDS.128 -> STG.128 coalesced)
+// The next tile's loads are issued before the current tile is computed (register prefetch).
+constexpr int kFiltWarps = 4;
+constexpr int kFiltPitch = 36;   // floats per tile row (32 + 4 pad)
+
+__global__ void __launch_bounds__(kFiltWarps * 32)
+pesq_filter_tiled_kernel(const float* __restrict__ clean, const float* __restrict__ deg,
+                         const int32_t* __restrict__ lengths, int64_t batch, int64_t n, int64_t stride,
+                         int chunk, int nchunks, int warm, const __grid_constant__ PesqFilterCoef P,
+                         float* __restrict__ z_out, int64_t zstride, double* __restrict__ partial) {
+    __shared__ __align__(16) float s_tile[kFiltWarps][32 * kFiltPitch];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    float* tile = s_tile[warp];
+    const int64_t groups = ceil_div(2 * batch, 32);
+    const int64_t unit = (int64_t)blockIdx.x * kFiltWarps + warp;     // (signal group, chunk)
+    if (unit >= groups * nchunks) return;
+    const int64_t grp = unit / nchunks;
+    const int c = (int)(unit - grp * nchunks);
+    const int64_t sig0 = grp * 32;
+
+    // own signal (compute role)
+    const int64_t sig = sig0 + lane;
+    const bool sig_ok = sig < 2 * batch;
+    const int64_t item = sig_ok ? (sig < batch ? sig : sig - batch) : 0;
+    const int len = sig_ok ? item_length(lengths, item, n) : 0;
+    // rows this lane helps to move (transfer role): rows (lane >> 3) + 4*i, float4 column lane & 7
+    const int col = (lane & 7) * 4;
+    const float* src_row[8];
+    float* dst_row[8];
+    int row_len[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t rs = sig0 + (lane >> 3) + 4 * i;
+        const bool ok = rs < 2 * batch;
+        const int64_t ri = ok ? (rs < batch ? rs : rs - batch) : 0;
+        src_row[i] = (rs < batch ? clean : deg) + ri * stride + col;
+        dst_row[i] = z_out + (ok ? rs : 0) * zstride + col;
+        row_len[i] = ok ? item_length(lengths, ri, n) : 0;
+    }
+    const int t_acc = c * chunk;
+    const int t_stop = min((int)n, t_acc + chunk);           // common upper bound of the chunk
+    const int t_end = min(len, t_stop);                      // this lane's own bound
+    int t = max(0, t_acc - warm);                            // multiple of 32
+
+    IirState st;
+#pragma unroll
+    for (int s = 0; s < FSEM_BP_SECTIONS; ++s) { st.w1[s] = 0.f; st.w2[s] = 0.f; }
+    st.s1 = 0.f; st.s2 = 0.f;
+    double acc_d = 0.0;
+
+    auto fetch = [&](int tt, float4 (&v)[8]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int a = tt + col;
+            if (a + 4 <= row_len[i]) {
+                v[i] = __ldg(reinterpret_cast<const float4*>(src_row[i] + tt));
+            } else {
+                const float* q = src_row[i] + tt;
+                v[i].x = (a < row_len[i]) ? __ldg(q) : 0.f;
+                v[i].y = (a + 1 < row_len[i]) ? __ldg(q + 1) : 0.f;
+                v[i].z = (a + 2 < row_len[i]) ? __ldg(q + 2) : 0.f;
+                v[i].w = (a + 3 < row_len[i]) ? __ldg(q + 3) : 0.f;
+            }
+        }
+    };
+    float4 pre[8];
+    if (t < t_stop) fetch(t, pre);
+    for (; t < t_stop; t += 32) {
+        // fill the tile with the prefetched segment, then prefetch the next one
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(tile + ((lane >> 3) + 4 * i) * kFiltPitch + col) = pre[i];
+        __syncwarp();
+        if (t + 32 < t_stop) fetch(t + 32, pre);
+        // compute: lane owns row `lane`
+        float* row = tile + lane * kFiltPitch;
+        const bool owned = t >= t_acc;
+        float acc = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            float4 q = *reinterpret_cast<const float4*>(row + 4 * g);
+            float v[4] = {q.x, q.y, q.z, q.w};
+            float zz[4];
+            const int tg = t + 4 * g;
+            const bool edge = (tg < 16) || (tg + 4 > len - 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float yv = bandpass_step(P, st, v[j]);
+                float xv = edge ? v[j] * taper_weight(tg + j, len) : v[j];
+                zz[j] = preemph_step(P, st, xv);
+                if (tg + j < t_end) acc = fmaf(yv, yv, acc);
+            }
+            *reinterpret_cast<float4*>(row + 4 * g) = make_float4(zz[0], zz[1], zz[2], zz[3]);
+        }
+        if (owned) acc_d += (double)acc;
+        __syncwarp();
+        // drain z (only owned samples; rows beyond their length keep whatever is there -- never read)
+        if (owned) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int a = t + col;
+                float4 q = *reinterpret_cast<const float4*>(tile + ((lane >> 3) + 4 * i) * kFiltPitch + col);
+                if (a + 4 <= row_len[i]) {
+                    *reinterpret_cast<float4*>(dst_row[i] + t) = q;
+                } else {
+                    float* d = dst_row[i] + t;
+                    if (a < row_len[i]) d[0] = q.x;
+                    if (a + 1 < row_len[i]) d[1] = q.y;
+                    if (a + 2 < row_len[i]) d[2] = q.z;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (sig_ok) partial[sig * nchunks + c] = acc_d;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Kernel B: persistent warps; one warp = one (item, frame) unit at a time.
 constexpr int kSpecWarps = 8;
 
@@ -174,28 +300,19 @@ __global__ void __launch_bounds__(kSpecWarps * 32)
 pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t* __restrict__ lengths,
                      int64_t batch, int64_t n, int tmax, const PesqTables* __restrict__ tab,
                      float* __restrict__ bark /* [2][batch][tmax][49], unscaled */) {
-    __shared__ float2 s_buf[kSpecWarps][kFftBufElems];
+    __shared__ __align__(16) float2 s_buf[kSpecWarps][kFftBufElems];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     float2* buf = s_buf[warp];
-    float* pbuf = reinterpret_cast<float*>(buf);          // reused for the 2 x 256 power values
 
     FftTwiddles tw;
     tw.init(lane);
     float win[16];
 #pragma unroll
     for (int m = 0; m < 16; ++m) win[m] = tab->hann[lane + 32 * m];
-    // this lane sums Bark bands `lane` and `lane + 32`
-    int bfirst[2], bcount[2];
-    float bscale[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        int b = lane + 32 * h;
-        bool ok = b < FSEM_PESQ_NBANDS;
-        bfirst[h] = ok ? tab->band_first[b] : 0;
-        bcount[h] = ok ? tab->band_count[b] : 0;
-        bscale[h] = ok ? tab->pow_dens[b] : 0.f;
-    }
+    BandPlan plan;
+    plan.init(tab->band_first, FSEM_PESQ_NBANDS, lane);
+    const float* __restrict__ pow_dens = tab->pow_dens;
 
     const int64_t units = batch * (int64_t)tmax;
     const int64_t wstride = (int64_t)gridDim.x * kSpecWarps;
@@ -204,38 +321,35 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
         const int f = (int)(u - item * tmax);
         const int len = item_length(lengths, item, n);
         if (f >= pesq_num_frames(len)) continue;
-        const float* __restrict__ zc = z + item * zstride;
-        const float* __restrict__ zd = z + (batch + item) * zstride;
-        const int base = f * FSEM_PESQ_HOP + lane;
+        const float* __restrict__ zc = z + item * zstride + f * FSEM_PESQ_HOP + lane;
+        const float* __restrict__ zd = z + (batch + item) * zstride + f * FSEM_PESQ_HOP + lane;
+        const int room = len - (f * FSEM_PESQ_HOP + lane);     // samples available from this lane's first index
         float re[16], im[16];
+        if (room > 32 * 15) {                                   // whole frame inside the signal (the common case)
 #pragma unroll
-        for (int m = 0; m < 16; ++m) {
-            int idx = base + 32 * m;
-            bool ok = idx < len;                         // zero padding beyond the signal (PESQ.py:128-130)
-            re[m] = ok ? __ldg(zc + idx) * win[m] : 0.f;
-            im[m] = ok ? __ldg(zd + idx) * win[m] : 0.f;
+            for (int m = 0; m < 16; ++m) {
+                re[m] = __ldg(zc + 32 * m) * win[m];
+                im[m] = __ldg(zd + 32 * m) * win[m];
+            }
+        } else {                                                // zero padding beyond the signal (PESQ.py:128-130)
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                bool ok = 32 * m < room;
+                re[m] = ok ? __ldg(zc + 32 * m) * win[m] : 0.f;
+                im[m] = ok ? __ldg(zd + 32 * m) * win[m] : 0.f;
+            }
         }
         warp_fft512<false>(re, im, buf, tw, lane);
         float pc[8], pd[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) packed_power(buf, lane + 32 * j, pc[j], pd[j]);
+        packed_power8(buf, lane, pc, pd);
         if (lane == 0) { pc[0] = 0.f; pd[0] = 0.f; }     // "we won't use energy feature" (PESQ.py:136)
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { pbuf[lane + 32 * j] = pc[j]; pbuf[256 + lane + 32 * j] = pd[j]; }
-        __syncwarp();
-        float* out_c = bark + (item * tmax + f) * FSEM_PESQ_NBANDS;
-        float* out_d = bark + ((batch + item) * tmax + f) * FSEM_PESQ_NBANDS;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            float sc = 0.f, sd = 0.f;
-            for (int q = 0; q < bcount[h]; ++q) {
-                sc += pbuf[bfirst[h] + q];
-                sd += pbuf[256 + bfirst[h] + q];
-            }
-            int b = lane + 32 * h;
-            if (b < FSEM_PESQ_NBANDS) { out_c[b] = sc * bscale[h]; out_d[b] = sd * bscale[h]; }
-        }
+        float* __restrict__ out_c = bark + (item * tmax + f) * FSEM_PESQ_NBANDS;
+        float* __restrict__ out_d = bark + ((batch + item) * tmax + f) * FSEM_PESQ_NBANDS;
+        band_sums8<4>(pc, pd, plan, lane, [&](int band, float sc, float sd) {
+            const float w = __ldg(pow_dens + band);          // power-density correction * Sp (bark.py:132, 204)
+            out_c[band] = sc * w;
+            out_d[band] = sd * w;
+        });
         __syncwarp();
     }
 }
