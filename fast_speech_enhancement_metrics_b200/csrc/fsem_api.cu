@@ -335,11 +335,17 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
     {   // kernel A
         const bool vec4 = aligned16(in->clean) && aligned16(in->deg) && (in->stride % 4 == 0);
         if (vec4) {
-            const int64_t units = ceil_div(2 * in->batch, 32) * p.nchunks;
+            const int64_t units = 2 * ceil_div(in->batch, 32) * p.nchunks;
+            const unsigned grid = (unsigned)ceil_div(units, kFiltWarps);
             { ProfScope prof_(K_PESQ_FILTER, stream);
-              pesq_filter_tiled_kernel<<<(unsigned)ceil_div(units, kFiltWarps), kFiltWarps * 32, 0, stream>>>(
-                  in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, p.chunk, p.nchunks, ctx->warm,
-                  ctx->coef, z, p.zstride, partial); }
+              if (in->lengths)
+                  pesq_filter_tiled_kernel<true><<<grid, kFiltWarps * 32, 0, stream>>>(
+                      in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, p.chunk, p.nchunks, ctx->warm,
+                      ctx->coef, z, p.zstride, partial);
+              else
+                  pesq_filter_tiled_kernel<false><<<grid, kFiltWarps * 32, 0, stream>>>(
+                      in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, p.chunk, p.nchunks, ctx->warm,
+                      ctx->coef, z, p.zstride, partial); }
         } else {
             const int64_t threads = 2 * in->batch * p.nchunks;
             { ProfScope prof_(K_PESQ_FILTER, stream);
