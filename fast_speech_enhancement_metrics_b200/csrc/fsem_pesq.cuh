@@ -306,9 +306,12 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
                      int64_t batch, int64_t n, int tmax, const PesqTables* __restrict__ tab,
                      float* __restrict__ bark /* [2][batch][tmax][49], unscaled */) {
     __shared__ __align__(16) float2 s_buf[kSpecWarps][kFftBufElems];
+    __shared__ float s_band[kSpecWarps][2][64];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     float2* buf = s_buf[warp];
+    float* bands_c = s_band[warp][0];
+    float* bands_d = s_band[warp][1];
 
     FftTwiddles tw;
     tw.init(lane);
@@ -317,45 +320,64 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
     for (int m = 0; m < 16; ++m) win[m] = tab->hann[lane + 32 * m];
     BandPlan plan;
     plan.init(tab->band_first, FSEM_PESQ_NBANDS, lane);
-    const float* __restrict__ pow_dens = tab->pow_dens;
+    // power-density correction * Sp of the two bands this lane stores (bark.py:132, 204)
+    const float scale0 = tab->pow_dens[lane];
+    const float scale1 = (lane + 32 < FSEM_PESQ_NBANDS) ? tab->pow_dens[lane + 32] : 0.f;
 
+    // every warp owns a contiguous range of the flattened (item, frame) space: one division per warp
     const int64_t units = batch * (int64_t)tmax;
-    const int64_t wstride = (int64_t)gridDim.x * kSpecWarps;
-    for (int64_t u = (int64_t)blockIdx.x * kSpecWarps + warp; u < units; u += wstride) {
-        const int64_t item = u / tmax;
-        const int f = (int)(u - item * tmax);
-        const int len = item_length(lengths, item, n);
-        if (f >= pesq_num_frames(len)) continue;
-        const float* __restrict__ zc = z + item * zstride + f * FSEM_PESQ_HOP + lane;
-        const float* __restrict__ zd = z + (batch + item) * zstride + f * FSEM_PESQ_HOP + lane;
-        const int room = len - (f * FSEM_PESQ_HOP + lane);     // samples available from this lane's first index
-        float re[16], im[16];
-        if (room > 32 * 15) {                                   // whole frame inside the signal (the common case)
+    const int64_t nwarps = (int64_t)gridDim.x * kSpecWarps;
+    const int64_t per = (units + nwarps - 1) / nwarps;
+    const int64_t u0 = ((int64_t)blockIdx.x * kSpecWarps + warp) * per;
+    const int64_t u1 = min(units, u0 + per);
+    if (u0 >= u1) return;
+    int64_t item = u0 / tmax;
+    int f = (int)(u0 - item * tmax);
+    int len = item_length(lengths, item, n);
+    int T = pesq_num_frames(len);
+    for (int64_t u = u0; u < u1; ++u) {
+        if (f < T) {
+            const int first = f * FSEM_PESQ_HOP + lane;
+            const float* __restrict__ zc = z + item * zstride + first;
+            const float* __restrict__ zd = z + (batch + item) * zstride + first;
+            // Loads are unconditional: a frame that sticks out of the signal reads on into the workspace (always
+            // mapped), and those samples are then replaced by the zero padding of PESQ.py:128-130.
+            float re[16], im[16];
 #pragma unroll
             for (int m = 0; m < 16; ++m) {
                 re[m] = __ldg(zc + 32 * m) * win[m];
                 im[m] = __ldg(zd + 32 * m) * win[m];
             }
-        } else {                                                // zero padding beyond the signal (PESQ.py:128-130)
+            if (f * FSEM_PESQ_HOP + FSEM_PESQ_NFFT > len) {      // warp-uniform, last frame(s) only
+                const int room = len - first;
 #pragma unroll
-            for (int m = 0; m < 16; ++m) {
-                bool ok = 32 * m < room;
-                re[m] = ok ? __ldg(zc + 32 * m) * win[m] : 0.f;
-                im[m] = ok ? __ldg(zd + 32 * m) * win[m] : 0.f;
+                for (int m = 0; m < 16; ++m)
+                    if (32 * m >= room) { re[m] = 0.f; im[m] = 0.f; }
             }
+            warp_fft512<false>(re, im, buf, tw, lane);
+            float pc[8], pd[8];
+            packed_power8(buf, lane, pc, pd);
+            if (lane == 0) { pc[0] = 0.f; pd[0] = 0.f; }     // "we won't use energy feature" (PESQ.py:136)
+            band_sums8<4>(pc, pd, plan, lane, [&](int band, float sc, float sd) {
+                bands_c[band] = sc;
+                bands_d[band] = sd;
+            });
+            __syncwarp();
+            float* __restrict__ out_c = bark + (item * tmax + f) * FSEM_PESQ_NBANDS;
+            float* __restrict__ out_d = bark + ((batch + item) * tmax + f) * FSEM_PESQ_NBANDS;
+            out_c[lane] = bands_c[lane] * scale0;
+            out_d[lane] = bands_d[lane] * scale0;
+            if (lane + 32 < FSEM_PESQ_NBANDS) {
+                out_c[lane + 32] = bands_c[lane + 32] * scale1;
+                out_d[lane + 32] = bands_d[lane + 32] * scale1;
+            }
+            __syncwarp();
         }
-        warp_fft512<false>(re, im, buf, tw, lane);
-        float pc[8], pd[8];
-        packed_power8(buf, lane, pc, pd);
-        if (lane == 0) { pc[0] = 0.f; pd[0] = 0.f; }     // "we won't use energy feature" (PESQ.py:136)
-        float* __restrict__ out_c = bark + (item * tmax + f) * FSEM_PESQ_NBANDS;
-        float* __restrict__ out_d = bark + ((batch + item) * tmax + f) * FSEM_PESQ_NBANDS;
-        band_sums8<4>(pc, pd, plan, lane, [&](int band, float sc, float sd) {
-            const float w = __ldg(pow_dens + band);          // power-density correction * Sp (bark.py:132, 204)
-            out_c[band] = sc * w;
-            out_d[band] = sd * w;
-        });
-        __syncwarp();
+        if (++f == tmax) {
+            f = 0;
+            ++item;
+            if (item < batch) { len = item_length(lengths, item, n); T = pesq_num_frames(len); }
+        }
     }
 }
 

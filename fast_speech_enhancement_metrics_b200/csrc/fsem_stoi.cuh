@@ -205,9 +205,11 @@ stoi_tob_kernel(const float* __restrict__ clean10k, const float* __restrict__ de
                 const StoiTables* __restrict__ tab, float* __restrict__ tob /* [2][batch][15][ustride] */) {
     __shared__ __align__(16) float2 s_buf[kTobWarps][kFftBufElems];
     __shared__ int32_t s_starts[FSEM_STOI_NBANDS + 2];
+    __shared__ float s_band[kTobWarps][64];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     float2* buf = s_buf[warp];
+    float* bands = s_band[warp];
     // pseudo-bands: 0 = bins below the first band, 1..15 = the third-octave bands (contiguous), 16 = bins above
     if (threadIdx.x == 0) s_starts[0] = 0;
     if (threadIdx.x < FSEM_STOI_NBANDS) s_starts[1 + threadIdx.x] = tab->band_lo[threadIdx.x];
@@ -222,44 +224,57 @@ stoi_tob_kernel(const float* __restrict__ clean10k, const float* __restrict__ de
     BandPlan plan;
     plan.init(s_starts, FSEM_STOI_NBANDS + 2, lane);
 
+    // every warp owns a contiguous range of the flattened (item, STFT frame) space
     const int64_t units = batch * (int64_t)umax;
-    const int64_t wstride = (int64_t)gridDim.x * kTobWarps;
-    for (int64_t unit = (int64_t)blockIdx.x * kTobWarps + warp; unit < units; unit += wstride) {
-        const int64_t item = unit / umax;
-        const int u = (int)(unit - item * umax);
-        const int K = kept_count[item];
-        if (u >= K - 2) continue;
-        const int32_t* idx = kept_idx + item * t0max + u;
-        const int64_t ta = (int64_t)idx[0] * FSEM_STOI_HOP, tb = (int64_t)idx[1] * FSEM_STOI_HOP,
-                      tc = (int64_t)idx[2] * FSEM_STOI_HOP;
-        const float* __restrict__ xc = clean10k + item * sstride;
-        const float* __restrict__ xd = deg10k + item * sstride;
-        float re[16], im[16];
+    const int64_t nwarps = (int64_t)gridDim.x * kTobWarps;
+    const int64_t per = (units + nwarps - 1) / nwarps;
+    const int64_t u0 = ((int64_t)blockIdx.x * kTobWarps + warp) * per;
+    const int64_t u1 = min(units, u0 + per);
+    if (u0 >= u1) return;
+    int64_t item = u0 / umax;
+    int u = (int)(u0 - item * umax);
+    int U = kept_count[item] - 2;
+    for (int64_t unit = u0; unit < u1; ++unit) {
+        if (u < U) {
+            const int32_t* idx = kept_idx + item * t0max + u;
+            const int ta = idx[0] * FSEM_STOI_HOP, tb = idx[1] * FSEM_STOI_HOP, tc = idx[2] * FSEM_STOI_HOP;
+            const float* __restrict__ xc = clean10k + item * sstride + lane;
+            const float* __restrict__ xd = deg10k + item * sstride + lane;
+            float re[16], im[16];
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const int q = lane + 32 * m;
-            // neighbour frame: first half of the chunk overlaps the tail of frame u, second half the head of frame u+2
-            const int64_t nb = (m < 4) ? (ta + q + 128) : (tc + q - 128);
-            const float wn = (m < 4) ? win[m + 4] : win[m - 4];
-            float c = __fadd_rn(__fmul_rn(win[m], __ldg(xc + tb + q)), __fmul_rn(wn, __ldg(xc + nb)));
-            float d = __fadd_rn(__fmul_rn(win[m], __ldg(xd + tb + q)), __fmul_rn(wn, __ldg(xd + nb)));
-            re[m] = __fmul_rn(win[m], c);
-            im[m] = __fmul_rn(win[m], d);
-        }
-#pragma unroll
-        for (int m = 8; m < 16; ++m) { re[m] = 0.f; im[m] = 0.f; }
-        warp_fft512<true>(re, im, buf, tw, lane);
-        float pc[8], pd[8];
-        packed_power8(buf, lane, pc, pd);
-        float* __restrict__ out_c = tob + (item * FSEM_STOI_NBANDS) * (int64_t)ustride + u;
-        float* __restrict__ out_d = tob + ((batch + item) * FSEM_STOI_NBANDS) * (int64_t)ustride + u;
-        band_sums8<6>(pc, pd, plan, lane, [&](int pseudo, float sc, float sd) {
-            if (pseudo >= 1 && pseudo <= FSEM_STOI_NBANDS) {
-                out_c[(int64_t)(pseudo - 1) * ustride] = sqrtf(sc);      // STOI.py:123-125
-                out_d[(int64_t)(pseudo - 1) * ustride] = sqrtf(sd);
+            for (int m = 0; m < 8; ++m) {
+                const int q = 32 * m;
+                // neighbour frame: first half of the chunk overlaps the tail of frame u, second half the head of frame u+2
+                const int nb = (m < 4) ? (ta + q + 128) : (tc + q - 128);
+                const float wn = (m < 4) ? win[m + 4] : win[m - 4];
+                float c = __fadd_rn(__fmul_rn(win[m], __ldg(xc + tb + q)), __fmul_rn(wn, __ldg(xc + nb)));
+                float d = __fadd_rn(__fmul_rn(win[m], __ldg(xd + tb + q)), __fmul_rn(wn, __ldg(xd + nb)));
+                re[m] = __fmul_rn(win[m], c);
+                im[m] = __fmul_rn(win[m], d);
             }
-        });
-        __syncwarp();
+#pragma unroll
+            for (int m = 8; m < 16; ++m) { re[m] = 0.f; im[m] = 0.f; }
+            warp_fft512<true>(re, im, buf, tw, lane);
+            float pc[8], pd[8];
+            packed_power8(buf, lane, pc, pd);
+            band_sums8<6>(pc, pd, plan, lane, [&](int pseudo, float sc, float sd) {
+                bands[pseudo] = sc;
+                bands[32 + pseudo] = sd;
+            });
+            __syncwarp();
+            // lanes 0..14 store the clean bands, lanes 16..30 the degraded ones (pseudo-band = band + 1)
+            if ((lane & 15) < FSEM_STOI_NBANDS) {
+                const int64_t sig = (lane >> 4) ? (batch + item) : item;
+                tob[(sig * FSEM_STOI_NBANDS + (lane & 15)) * (int64_t)ustride + u] =
+                    sqrtf(bands[(lane & 16) * 2 + (lane & 15) + 1]);     // STOI.py:123-125
+            }
+            __syncwarp();
+        }
+        if (++u == umax) {
+            u = 0;
+            ++item;
+            if (item < batch) U = kept_count[item] - 2;
+        }
     }
 }
 
