@@ -462,9 +462,9 @@ namespace {
 
 struct StoiPlan {
     int64_t batch, n, lmax, ystride;
-    int t0max, mask_words, umax, ustride, mmax, ntiles;
-    bool resample;
-    size_t off_y, off_energy, off_idx, off_count, off_mask, off_tob, off_partial, total;
+    int t0max, mask_words, umax, ustride, mmax, ntiles, hops_max;
+    bool resample, fused_energy;
+    size_t off_hops, off_y, off_energy, off_idx, off_count, off_mask, off_tob, off_partial, total;
 };
 
 StoiPlan stoi_plan(const fsem_stoi_ctx* ctx, int64_t batch, int64_t n) {
@@ -481,7 +481,11 @@ StoiPlan stoi_plan(const fsem_stoi_ctx* ctx, int64_t batch, int64_t n) {
     p.ustride = (int)round_up(p.umax > 0 ? p.umax : 1, 4);
     p.mmax = p.t0max - 31 > 0 ? p.t0max - 31 : 0;
     p.ntiles = (int)ceil_div(p.mmax > 0 ? p.mmax : 1, kSegTile);
+    p.fused_energy = ctx->fast85;
+    // hop energies of the fused resample kernel: whole tiles of 10 hops
+    p.hops_max = (int)(ceil_div(p.lmax > 0 ? p.lmax : 1, kRs85TileOut) * kRs85Hops);
     size_t off = 0;
+    p.off_hops = off;    off = align256(off + (p.fused_energy ? sizeof(double2) * batch * p.hops_max : 0));
     p.off_y = off;       off = align256(off + (p.resample ? sizeof(float) * 2 * batch * p.ystride : 0));
     p.off_energy = off;  off = align256(off + sizeof(float) * batch * p.t0max);
     p.off_idx = off;     off = align256(off + sizeof(int32_t) * batch * p.t0max);
@@ -575,6 +579,7 @@ extern "C" int fsem_stoi_score_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t* in,
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     char* ws = static_cast<char*>(workspace);
     float* y = reinterpret_cast<float*>(ws + p.off_y);
+    double2* hops = reinterpret_cast<double2*>(ws + p.off_hops);
     float* energy = reinterpret_cast<float*>(ws + p.off_energy);
     int32_t* kept_idx = reinterpret_cast<int32_t*>(ws + p.off_idx);
     int32_t* kept_count = reinterpret_cast<int32_t*>(ws + p.off_count);
@@ -587,15 +592,17 @@ extern "C" int fsem_stoi_score_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t* in,
     int64_t sstride = in->stride;
     if (p.resample) {
         if (ctx->fast85) {
-            dim3 grid((unsigned)ceil_div(p.lmax, kRs85TileOut), (unsigned)(2 * in->batch));
+            dim3 grid((unsigned)ceil_div(p.lmax, (int64_t)kRs85TileOut * kRs85TilesPerCta), (unsigned)(2 * in->batch));
             const bool vec4 = aligned16(in->clean) && aligned16(in->deg) && (in->stride % 4 == 0);
             { ProfScope prof_(K_STOI_RESAMPLE, stream);
               if (vec4)
                   stoi_resample85_kernel<true><<<grid, kRs85Threads, 0, stream>>>(
-                      in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, ctx->taps85, y, p.ystride);
+                      in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, ctx->taps85, ctx->d_tab, y,
+                      p.ystride, hops, p.hops_max);
               else
                   stoi_resample85_kernel<false><<<grid, kRs85Threads, 0, stream>>>(
-                      in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, ctx->taps85, y, p.ystride); }
+                      in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, ctx->taps85, ctx->d_tab, y,
+                      p.ystride, hops, p.hops_max); }
         } else {
             dim3 grid((unsigned)ceil_div(p.lmax, 256), (unsigned)(2 * in->batch));
             { ProfScope prof_(K_STOI_RESAMPLE, stream);
@@ -608,11 +615,17 @@ extern "C" int fsem_stoi_score_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t* in,
         d10 = y + in->batch * p.ystride;
         sstride = p.ystride;
     }
-    {
+    if (p.fused_energy) {
+        const int64_t threads = in->batch * (int64_t)p.t0max;
+        { ProfScope prof_(K_STOI_ENERGY, stream);
+          stoi_energy_from_hops_kernel<<<(unsigned)ceil_div(threads, 256), 256, 0, stream>>>(
+              hops, p.hops_max, in->lengths, in->batch, in->n, p.t0max, energy); }
+        FSEM_LAUNCHED();
+    } else {
         const int64_t warps = in->batch * (int64_t)p.t0max;
         { ProfScope prof_(K_STOI_ENERGY, stream);
           stoi_energy_kernel<<<(unsigned)ceil_div(warps * 32, 256), 256, 0, stream>>>(
-              c10, sstride, in->lengths, in->batch, in->n, ctx->orig, ctx->neu, p.t0max, ctx->d_tab, energy); }
+            c10, sstride, in->lengths, in->batch, in->n, ctx->orig, ctx->neu, p.t0max, ctx->d_tab, energy); }
         FSEM_LAUNCHED();
     }
     {

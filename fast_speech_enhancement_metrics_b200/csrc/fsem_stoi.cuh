@@ -69,62 +69,143 @@ constexpr int kRs85Quads = kRs85TileIn / 4 + 10;        // float4s staged per ti
 __host__ __device__ constexpr int rs85_lo(int p) { return p == 0 ? 1 : p == 1 ? 2 : p == 2 ? 4 : p == 3 ? 6 : 7; }
 __host__ __device__ constexpr int rs85_hi(int p) { return p == 0 ? 19 : p == 1 ? 21 : p == 2 ? 22 : p == 3 ? 24 : 26; }
 
+constexpr int kRs85TilesPerCta = 4;
+constexpr int kRs85Hops = kRs85TileOut / FSEM_STOI_HOP;      // 10 hops of 128 output samples per tile
+
+// Each CTA walks kRs85TilesPerCta consecutive tiles of one signal; the next tile's input is prefetched into
+// registers while the current one is computed.  Outputs go through shared memory so that the global stores are
+// coalesced float4 and -- for the CLEAN signal -- so that the silent-frame energies can be fused in:
+// per hop h of 128 output samples the kernel writes
+//     A_h = sum_r (w[r]       * y[128h + r])^2      (hop as FIRST  half of analysis frame h)
+//     B_h = sum_r (w[r + 128] * y[128h + r])^2      (hop as SECOND half of analysis frame h-1)
+// (products rounded to fp32 like the reference, sums in fp64), so that ||w * x_t||^2 = A_t + B_{t+1} (STOI.py:92-98).
 template <bool kVec4>
 __global__ void __launch_bounds__(kRs85Threads)
 stoi_resample85_kernel(const float* __restrict__ clean, const float* __restrict__ deg,
                        const int32_t* __restrict__ lengths, int64_t batch, int64_t n, int64_t stride,
-                       const __grid_constant__ Resample85Taps taps, float* __restrict__ y, int64_t ystride) {
+                       const __grid_constant__ Resample85Taps taps, const StoiTables* __restrict__ tab,
+                       float* __restrict__ y, int64_t ystride, double2* __restrict__ hop_energy, int hops_max) {
     __shared__ float4 s_in[kRs85Quads + kRs85Quads / 4 + 2];
+    __shared__ __align__(16) float s_out[kRs85TileOut];
+    __shared__ __align__(16) float s_win[FSEM_STOI_WIN];
+    const int tid = threadIdx.x;
     const int64_t sig = blockIdx.y;
-    const int64_t item = sig < batch ? sig : sig - batch;
+    const bool is_clean = sig < batch;
+    const int64_t item = is_clean ? sig : sig - batch;
     const int len = item_length(lengths, item, n);
     const int64_t L = stoi_resampled_len(len, 8, 5);
-    const int64_t out0 = (int64_t)blockIdx.x * kRs85TileOut;
-    if (out0 >= L) return;
-    const float* __restrict__ x = (sig < batch ? clean : deg) + item * stride;
-    const int64_t in0 = (int64_t)blockIdx.x * kRs85TileIn - 12;      // first staged sample (multiple of 4)
-    for (int q = threadIdx.x; q < kRs85Quads; q += kRs85Threads) {
-        const int64_t i = in0 + 4 * (int64_t)q;
-        float4 v;
-        if (kVec4 && i >= 0 && i + 4 <= len) {
-            v = __ldg(reinterpret_cast<const float4*>(x + i));
-        } else {
-            v.x = (i >= 0 && i < len) ? __ldg(x + i) : 0.f;
-            v.y = (i + 1 >= 0 && i + 1 < len) ? __ldg(x + i + 1) : 0.f;
-            v.z = (i + 2 >= 0 && i + 2 < len) ? __ldg(x + i + 2) : 0.f;
-            v.w = (i + 3 >= 0 && i + 3 < len) ? __ldg(x + i + 3) : 0.f;
+    const int64_t tile0 = (int64_t)blockIdx.x * kRs85TilesPerCta;
+    if (tile0 * kRs85TileOut >= L) return;
+    const float* __restrict__ x = (is_clean ? clean : deg) + item * stride;
+    float* __restrict__ yrow = y + sig * ystride;
+    for (int i = tid; i < FSEM_STOI_WIN; i += kRs85Threads) s_win[i] = tab->window[i];
+
+    constexpr int kPerThread = (kRs85Quads + kRs85Threads - 1) / kRs85Threads;   // 5 float4 per thread per tile
+    auto fetch = [&](int64_t tile, float4 (&v)[kPerThread]) {
+        const int64_t in0 = tile * kRs85TileIn - 12;                              // first staged sample (multiple of 4)
+#pragma unroll
+        for (int r = 0; r < kPerThread; ++r) {
+            const int q = tid + r * kRs85Threads;
+            const int64_t i = in0 + 4 * (int64_t)q;
+            if (q >= kRs85Quads) { v[r] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+            if (kVec4 && i >= 0 && i + 4 <= len) {
+                v[r] = __ldg(reinterpret_cast<const float4*>(x + i));
+            } else {
+                v[r].x = (i >= 0 && i < len) ? __ldg(x + i) : 0.f;
+                v[r].y = (i + 1 >= 0 && i + 1 < len) ? __ldg(x + i + 1) : 0.f;
+                v[r].z = (i + 2 >= 0 && i + 2 < len) ? __ldg(x + i + 2) : 0.f;
+                v[r].w = (i + 3 >= 0 && i + 3 < len) ? __ldg(x + i + 3) : 0.f;
+            }
         }
-        s_in[q + (q >> 2)] = v;
-    }
-    __syncthreads();
-    // thread t: blocks 2t, 2t+1 of this tile need staged floats [16t + 2, 16t + 38)
-    float xin[40];
-    const float4* src = s_in + 5 * threadIdx.x;
+    };
+    float4 pre[kPerThread];
+    fetch(tile0, pre);
+    for (int k = 0; k < kRs85TilesPerCta; ++k) {
+        const int64_t tile = tile0 + k;
+        const int64_t out0 = tile * kRs85TileOut;
+        if (out0 >= L) break;                                                      // uniform
 #pragma unroll
-    for (int i = 0; i < 10; ++i) {
-        float4 v = src[i + (i >> 2)];
-        xin[4 * i] = v.x; xin[4 * i + 1] = v.y; xin[4 * i + 2] = v.z; xin[4 * i + 3] = v.w;
-    }
-    float out[10];
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-#pragma unroll
-        for (int p = 0; p < 5; ++p) {
-            float acc = 0.f;
-#pragma unroll
-            for (int j = rs85_lo(p); j <= rs85_hi(p); ++j) acc = fmaf(taps.h[p][j], xin[2 + 8 * b + j], acc);
-            out[5 * b + p] = acc;
+        for (int r = 0; r < kPerThread; ++r) {
+            const int q = tid + r * kRs85Threads;
+            if (q < kRs85Quads) s_in[q + (q >> 2)] = pre[r];
         }
-    }
-    const int64_t m0 = out0 + 10 * (int64_t)threadIdx.x;
-    float* __restrict__ dst = y + sig * ystride + m0;
-    if (m0 + 10 <= L) {
+        __syncthreads();
+        if (k + 1 < kRs85TilesPerCta && (out0 + kRs85TileOut) < L) fetch(tile + 1, pre);
+        // thread t: blocks 2t, 2t+1 of this tile need staged floats [16t + 2, 16t + 38)
+        float xin[40];
+        const float4* src = s_in + 5 * tid;
 #pragma unroll
-        for (int i = 0; i < 5; ++i) *reinterpret_cast<float2*>(dst + 2 * i) = make_float2(out[2 * i], out[2 * i + 1]);
-    } else {
+        for (int i = 0; i < 10; ++i) {
+            float4 v = src[i + (i >> 2)];
+            xin[4 * i] = v.x; xin[4 * i + 1] = v.y; xin[4 * i + 2] = v.z; xin[4 * i + 3] = v.w;
+        }
 #pragma unroll
-        for (int i = 0; i < 10; ++i) if (m0 + i < L) dst[i] = out[i];
+        for (int b = 0; b < 2; ++b) {
+#pragma unroll
+            for (int p = 0; p < 5; ++p) {
+                float acc = 0.f;
+#pragma unroll
+                for (int j = rs85_lo(p); j <= rs85_hi(p); ++j) acc = fmaf(taps.h[p][j], xin[2 + 8 * b + j], acc);
+                s_out[10 * tid + 5 * b + p] = acc;
+            }
+        }
+        __syncthreads();
+        // coalesced float4 stores of the 1280 outputs
+        const int64_t valid = min((int64_t)kRs85TileOut, L - out0);
+        for (int q = tid; q < kRs85TileOut / 4; q += kRs85Threads) {
+            const float4 v = *reinterpret_cast<const float4*>(s_out + 4 * q);
+            float* d = yrow + out0 + 4 * q;
+            if (4 * q + 4 <= valid) {
+                *reinterpret_cast<float4*>(d) = v;
+            } else {
+                if (4 * q < valid) d[0] = v.x;
+                if (4 * q + 1 < valid) d[1] = v.y;
+                if (4 * q + 2 < valid) d[2] = v.z;
+            }
+        }
+        if (is_clean) {
+            // hop energies: warp w takes hops w, w+4, w+8 of this tile; lane handles 4 samples of the hop
+            const int lane = tid & 31, warp = tid >> 5;
+            const float4 wa = *reinterpret_cast<const float4*>(s_win + 4 * lane);
+            const float4 wb = *reinterpret_cast<const float4*>(s_win + 128 + 4 * lane);
+            for (int h = warp; h < kRs85Hops; h += kRs85Threads / 32) {
+                if ((int64_t)(h + 1) * FSEM_STOI_HOP > valid) break;               // only complete hops matter
+                const float4 v = *reinterpret_cast<const float4*>(s_out + h * FSEM_STOI_HOP + 4 * lane);
+                double a = 0.0, b = 0.0;
+                float f;
+                f = __fmul_rn(v.x, wa.x); a = fma((double)f, (double)f, a);
+                f = __fmul_rn(v.y, wa.y); a = fma((double)f, (double)f, a);
+                f = __fmul_rn(v.z, wa.z); a = fma((double)f, (double)f, a);
+                f = __fmul_rn(v.w, wa.w); a = fma((double)f, (double)f, a);
+                f = __fmul_rn(v.x, wb.x); b = fma((double)f, (double)f, b);
+                f = __fmul_rn(v.y, wb.y); b = fma((double)f, (double)f, b);
+                f = __fmul_rn(v.z, wb.z); b = fma((double)f, (double)f, b);
+                f = __fmul_rn(v.w, wb.w); b = fma((double)f, (double)f, b);
+                a = warp_sum(a);
+                b = warp_sum(b);
+                if (lane == 0) hop_energy[item * hops_max + tile * kRs85Hops + h] = make_double2(a, b);
+            }
+        }
+        __syncthreads();
     }
+}
+
+// E_t = 20*log10(sqrt(A_t + B_{t+1}) + 1e-9) from the fused hop energies (same fp32 op order as stoi_energy_kernel)
+__global__ void __launch_bounds__(256)
+stoi_energy_from_hops_kernel(const double2* __restrict__ hop_energy, int hops_max, const int32_t* __restrict__ lengths,
+                             int64_t batch, int64_t n, int t0max, float* __restrict__ energy) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= batch * (int64_t)t0max) return;
+    const int64_t item = gid / t0max;
+    const int t = (int)(gid - item * t0max);
+    const int64_t L = stoi_resampled_len(item_length(lengths, item, n), 8, 5);
+    if (t >= stoi_num_frames(L)) return;
+    const double2 h0 = hop_energy[item * hops_max + t];
+    const double2 h1 = hop_energy[item * hops_max + t + 1];
+    float nrm = (float)sqrt(h0.x + h1.y);
+    float v = __fadd_rn(nrm, 1e-9f);
+    float lg = (float)log10((double)v);
+    energy[gid] = __fmul_rn(20.f, lg);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -224,17 +305,17 @@ stoi_tob_kernel(const float* __restrict__ clean10k, const float* __restrict__ de
     BandPlan plan;
     plan.init(s_starts, FSEM_STOI_NBANDS + 2, lane);
 
-    // every warp owns a contiguous range of the flattened (item, STFT frame) space
-    const int64_t units = batch * (int64_t)umax;
+    // units = flattened (item, STFT frame) slots, dealt round-robin to the warps (the number of real frames per
+    // item, K - 2, is data dependent, so contiguous ranges would be unbalanced); index maths stays incremental
     const int64_t nwarps = (int64_t)gridDim.x * kTobWarps;
-    const int64_t per = (units + nwarps - 1) / nwarps;
-    const int64_t u0 = ((int64_t)blockIdx.x * kTobWarps + warp) * per;
-    const int64_t u1 = min(units, u0 + per);
-    if (u0 >= u1) return;
-    int64_t item = u0 / umax;
-    int u = (int)(u0 - item * umax);
-    int U = kept_count[item] - 2;
-    for (int64_t unit = u0; unit < u1; ++unit) {
+    const int64_t wid = (int64_t)blockIdx.x * kTobWarps + warp;
+    const int64_t step_items = nwarps / umax;
+    const int step_u = (int)(nwarps - step_items * umax);
+    int64_t item = wid / umax;
+    int u = (int)(wid - item * umax);
+    for (; item < batch; item += step_items, u += step_u) {
+        if (u >= umax) { u -= umax; ++item; if (item >= batch) break; }
+        const int U = kept_count[item] - 2;
         if (u < U) {
             const int32_t* idx = kept_idx + item * t0max + u;
             const int ta = idx[0] * FSEM_STOI_HOP, tb = idx[1] * FSEM_STOI_HOP, tc = idx[2] * FSEM_STOI_HOP;
@@ -269,11 +350,6 @@ stoi_tob_kernel(const float* __restrict__ clean10k, const float* __restrict__ de
                     sqrtf(bands[(lane & 16) * 2 + (lane & 15) + 1]);     // STOI.py:123-125
             }
             __syncwarp();
-        }
-        if (++u == umax) {
-            u = 0;
-            ++item;
-            if (item < batch) U = kept_count[item] - 2;
         }
     }
 }
