@@ -10,6 +10,7 @@ kcoost/fast_speech_enhancement_metrics).
 from .base import BaseMetric
 from .PESQ import PESQ
 from .STOI import STOI
+from .fused import score_pesq_stoi
 
-__all__ = ["BaseMetric", "PESQ", "STOI"]
+__all__ = ["BaseMetric", "PESQ", "STOI", "score_pesq_stoi"]
 __version__ = "0.1.0"

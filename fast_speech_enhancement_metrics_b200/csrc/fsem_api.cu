@@ -737,3 +737,77 @@ extern "C" int fsem_stoi_score_host_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t
     FSEM_CUDA(cudaStreamSynchronize(P.compute));
     return FSEM_OK;
 }
+
+// ================================================================================================
+// PESQ + STOI on one upload: callers of the reference always score both metrics on the
+// same pair of tensors (README.md:29-30, benchmark_metrics.py:22,24); with host tensors the host->device copy
+// dominates, so this entry point copies every chunk ONCE and runs both kernel pipelines on it.
+// ================================================================================================
+extern "C" int fsem_pesq_stoi_score_host_f32(fsem_pesq_ctx_t* pctx, fsem_stoi_ctx_t* sctx, const fsem_batch_t* in,
+                                             float* mos_out, int32_t* pesq_status_out, float* stoi_out,
+                                             float* estoi_out, int32_t* kept_frames_out, int32_t* stoi_status_out) {
+    if (!pctx || !sctx || !in || !mos_out || !stoi_out || !estoi_out)
+        return fail(FSEM_E_INVALID, "fsem_pesq_stoi_score_host_f32: null argument");
+    if (in->batch < 0 || in->n < 0 || in->stride < in->n)
+        return fail(FSEM_E_INVALID, "fsem_pesq_stoi_score_host_f32: bad shape");
+    if (in->batch == 0) return FSEM_OK;
+    if (!in->lengths && pesq_num_frames(in->n) < 20)
+        return fail(FSEM_E_TOO_SHORT, "PESQ needs at least 20 frames of 512/256 samples; n=%lld gives %d",
+                    (long long)in->n, pesq_num_frames(in->n));
+    int rc = pctx->pipe.init();
+    if (rc != FSEM_OK) return rc;
+    const int64_t n = in->n, dstride = round_up(n, 4);
+    const int64_t per = host_chunk_items(in->batch, n);
+    const size_t sig_bytes = align256(sizeof(float) * per * dstride);
+    const size_t in_bytes = 2 * sig_bytes + align256(sizeof(int32_t) * per);
+    const size_t ws_pesq = align256(fsem_pesq_workspace_bytes(pctx, per, n));
+    const size_t ws_stoi = align256(fsem_stoi_workspace_bytes(sctx, per, n));
+    const size_t col = align256(sizeof(float) * per);
+    rc = pctx->pipe.reserve(in_bytes, ws_pesq + ws_stoi, 6 * col);
+    if (rc != FSEM_OK) return rc;
+    HostPipe& P = pctx->pipe;
+    int64_t done_chunks = 0;
+    for (int64_t i0 = 0; i0 < in->batch; i0 += per, ++done_chunks) {
+        const int slot = (int)(done_chunks & 1);
+        const int64_t cnt = (in->batch - i0 < per) ? (in->batch - i0) : per;
+        char* base = static_cast<char*>(P.in[slot]);
+        float* d_clean = reinterpret_cast<float*>(base);
+        float* d_deg = reinterpret_cast<float*>(base + sig_bytes);
+        int32_t* d_len = reinterpret_cast<int32_t*>(base + 2 * sig_bytes);
+        char* ob = static_cast<char*>(P.out[slot]);
+        float* d_mos = reinterpret_cast<float*>(ob);
+        int32_t* d_pst = reinterpret_cast<int32_t*>(ob + col);
+        float* d_stoi = reinterpret_cast<float*>(ob + 2 * col);
+        float* d_estoi = reinterpret_cast<float*>(ob + 3 * col);
+        int32_t* d_kept = reinterpret_cast<int32_t*>(ob + 4 * col);
+        int32_t* d_sst = reinterpret_cast<int32_t*>(ob + 5 * col);
+        if (done_chunks >= 2) FSEM_CUDA(cudaStreamWaitEvent(P.copy, P.done[slot], 0));
+        FSEM_CUDA(cudaMemcpy2DAsync(d_clean, dstride * sizeof(float), in->clean + i0 * in->stride,
+                                    in->stride * sizeof(float), n * sizeof(float), cnt, cudaMemcpyHostToDevice, P.copy));
+        FSEM_CUDA(cudaMemcpy2DAsync(d_deg, dstride * sizeof(float), in->deg + i0 * in->stride,
+                                    in->stride * sizeof(float), n * sizeof(float), cnt, cudaMemcpyHostToDevice, P.copy));
+        if (in->lengths)
+            FSEM_CUDA(cudaMemcpyAsync(d_len, in->lengths + i0, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, P.copy));
+        FSEM_CUDA(cudaEventRecord(P.copied[slot], P.copy));
+        FSEM_CUDA(cudaStreamWaitEvent(P.compute, P.copied[slot], 0));
+        fsem_batch_t dev{d_clean, d_deg, in->lengths ? d_len : nullptr, cnt, n, dstride};
+        rc = fsem_pesq_score_f32(pctx, &dev, d_mos, d_pst, P.ws, ws_pesq, P.compute);
+        if (rc == FSEM_OK)
+            rc = fsem_stoi_score_f32(sctx, &dev, d_stoi, d_estoi, d_kept, d_sst, static_cast<char*>(P.ws) + ws_pesq,
+                                     ws_stoi, P.compute);
+        if (rc != FSEM_OK) { cudaStreamSynchronize(P.copy); cudaStreamSynchronize(P.compute); return rc; }
+        FSEM_CUDA(cudaMemcpyAsync(mos_out + i0, d_mos, sizeof(float) * cnt, cudaMemcpyDeviceToHost, P.compute));
+        FSEM_CUDA(cudaMemcpyAsync(stoi_out + i0, d_stoi, sizeof(float) * cnt, cudaMemcpyDeviceToHost, P.compute));
+        FSEM_CUDA(cudaMemcpyAsync(estoi_out + i0, d_estoi, sizeof(float) * cnt, cudaMemcpyDeviceToHost, P.compute));
+        if (pesq_status_out)
+            FSEM_CUDA(cudaMemcpyAsync(pesq_status_out + i0, d_pst, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, P.compute));
+        if (kept_frames_out)
+            FSEM_CUDA(cudaMemcpyAsync(kept_frames_out + i0, d_kept, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, P.compute));
+        if (stoi_status_out)
+            FSEM_CUDA(cudaMemcpyAsync(stoi_status_out + i0, d_sst, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, P.compute));
+        FSEM_CUDA(cudaEventRecord(P.done[slot], P.compute));
+    }
+    FSEM_CUDA(cudaStreamSynchronize(P.copy));
+    FSEM_CUDA(cudaStreamSynchronize(P.compute));
+    return FSEM_OK;
+}

@@ -1,0 +1,57 @@
+"""PESQ + STOI/ESTOI on ONE host->device upload.
+
+Callers of the reference always score both metrics on the same pair of tensors
+(README.md:29-30, benchmark_metrics.py:22,24).  With host tensors the PCIe copy dominates the
+end-to-end time, so `score_pesq_stoi` hands the pair to the library once: every chunk is copied
+once and both kernel pipelines run on it.  Results are identical to
+calling the two metric objects separately.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+
+import torch
+
+from . import _lib
+from .PESQ import PESQ
+from .STOI import STOI
+
+
+def score_pesq_stoi(pesq: PESQ, stoi: STOI, clean_speech: torch.Tensor, denoised_speech: torch.Tensor,
+                    lengths=None) -> list[dict[str, float]]:
+    """Returns [{"PESQ": ..., "STOI": ..., "ESTOI": ...}, ...], one dict per batch row.
+    `stoi` must have been built for the tensors' sample rate (e.g. STOI(16000)) and `pesq` for 16 kHz."""
+    if stoi.sample_rate != pesq.sample_rate:
+        raise Exception("both metrics must be built for the sample rate of the audio")
+    clean, deg = pesq.prepare_inputs(clean_speech, denoised_speech)
+    assert clean is not None
+    b, n = clean.shape
+    if clean.is_cuda:
+        # device-resident tensors are shared by the two calls anyway
+        mos, pst = pesq.score_tensors(clean, deg, lengths)
+        sc, kept, _ = stoi.score_tensors(clean, deg, lengths)
+        packed = torch.cat([mos[None], pst.to(torch.float32)[None], sc, kept.to(torch.float32)[None]]).cpu()
+        mos, pst, sc, kept = packed[0], packed[1].to(torch.int32), packed[2:4], packed[4].to(torch.int32)
+    else:
+        lens = pesq._lengths_tensor(lengths, b, n, "cpu")
+        mos = torch.empty(b, dtype=torch.float32)
+        pst = torch.empty(b, dtype=torch.int32)
+        sc = torch.empty(2, b, dtype=torch.float32)
+        kept = torch.empty(b, dtype=torch.int32)
+        sst = torch.empty(b, dtype=torch.int32)
+        if clean.stride(0) != deg.stride(0) and b > 1:
+            clean, deg = clean.contiguous(), deg.contiguous()
+        batch = _lib.Batch(clean.data_ptr(), deg.data_ptr(), lens.data_ptr() if lens is not None else None,
+                           b, n, clean.stride(0) if b > 1 else n)
+        with torch.cuda.device(pesq.device):
+            PESQ._check_score(pesq._lib.fsem_pesq_stoi_score_host_f32(
+                pesq._ctx, stoi._ctx, C.byref(batch), mos.data_ptr(), pst.data_ptr(), sc[0].data_ptr(),
+                sc[1].data_ptr(), kept.data_ptr(), sst.data_ptr()))
+    if lengths is not None and bool((pst == _lib.ITEM_TOO_SHORT).any()):
+        raise RuntimeError("PESQ needs at least 20 frames of 512/256 samples for every item")
+    stoi.last_kept_frames = kept
+    if int(kept.max()) <= stoi.N + 1:
+        warnings.warn("Not enough non-silent frames. Please check your sound files", RuntimeWarning, stacklevel=2)
+        raise TypeError("iteration over a 0-d tensor")
+    return [{"PESQ": p, "STOI": s, "ESTOI": e} for p, s, e in zip(mos.tolist(), sc[0].tolist(), sc[1].tolist())]

@@ -171,6 +171,15 @@ FSEM_API int fsem_stoi_debug_taps(fsem_stoi_ctx_t* ctx, int64_t batch, int64_t n
                          uint32_t* mask_out, float* tob_out, float* resampled_out,
                          int64_t* dims_out, void* stream);
 
+/* ------------------------------------------------------------------ PESQ + STOI, one upload
+ * Host entry point scoring BOTH metrics while copying every chunk of the batch host->device once
+ * (callers of the reference always run both on the same tensors: README.md:29-30,
+ * benchmark_metrics.py:22,24).  The STOI context must be built for the batch's sample rate.
+ * Output arrays are HOST pointers; the *_status_out / kept_frames_out ones may be NULL. */
+FSEM_API int fsem_pesq_stoi_score_host_f32(fsem_pesq_ctx_t* pesq, fsem_stoi_ctx_t* stoi, const fsem_batch_t* in,
+                                  float* mos_out, int32_t* pesq_status_out, float* stoi_out, float* estoi_out,
+                                  int32_t* kept_frames_out, int32_t* stoi_status_out);
+
 #ifdef __cplusplus
 }
 #endif

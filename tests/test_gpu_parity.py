@@ -187,6 +187,23 @@ def test_stoi_host_entry_equals_device_entry(stoi_metrics):
     assert dev == host
 
 
+def test_fused_upload_equals_separate_calls(pesq, stoi_metrics):
+    from fast_speech_enhancement_metrics_b200 import score_pesq_stoi
+    clean, deg, _, fs = STOI_CASES["speech16k_3s"]
+    st = stoi_metrics(16000)
+    c, d = torch.from_numpy(clean), torch.from_numpy(deg)
+    sep_p, sep_s = pesq(c, d), st(c, d)
+    for cc, dd in ((c, d), (c.cuda(), d.cuda())):
+        both = score_pesq_stoi(pesq, st, cc, dd)
+        assert [r["PESQ"] for r in both] == [r["PESQ"] for r in sep_p]
+        assert [(r["STOI"], r["ESTOI"]) for r in both] == [(r["STOI"], r["ESTOI"]) for r in sep_s]
+    lens = [48000, 30000, 20001, 48000, 12345, 40000, 48000, 8000]
+    both = score_pesq_stoi(pesq, st, c, d, lengths=lens)
+    sep_p, sep_s = pesq(c, d, lengths=lens), st(c, d, lengths=lens)
+    assert [r["PESQ"] for r in both] == [r["PESQ"] for r in sep_p]
+    assert np.array_equal(np.array([r["STOI"] for r in both]), np.array([r["STOI"] for r in sep_s]), equal_nan=True)
+
+
 def test_stoi_errors(stoi_metrics, golden_stoi):
     metric = stoi_metrics(10000)
     assert int(golden_stoi["err_no_segments"]) == 1
