@@ -269,3 +269,59 @@ def test_properties_at_full_size(pesq, stoi_metrics):
             continue
         assert int(st.last_kept_frames[0]) == int(kp[i])
         assert abs(r["STOI"] - padded[i]["STOI"]) <= 2e-6 and abs(r["ESTOI"] - padded[i]["ESTOI"]) <= 2e-6
+
+
+def test_variable_length_batch_against_oracle(pesq, stoi_metrics):
+    """BASELINE configs[3]: a padded batch of 1-30 s items with per-item lengths, PESQ + STOI against the
+    oracle run on every slice (the reference called per item: legitimate by batch invariance)."""
+    from fast_speech_enhancement_metrics_b200.synth import synth_item
+    rng = np.random.default_rng(4321)
+    lens = [int(x) for x in rng.integers(16000, 480001, size=24)]
+    lens[0], lens[1] = 480000, 16000
+    nmax = max(lens)
+    clean = np.zeros((len(lens), nmax), np.float32)
+    deg = np.zeros_like(clean)
+    for i, n in enumerate(lens):
+        clean[i, :n], deg[i, :n], _ = synth_item(rng, n)
+        clean[i, n:] = 7.0          # garbage beyond the valid length must not matter
+        deg[i, n:] = -3.0
+    c, d = torch.from_numpy(clean).cuda(), torch.from_numpy(deg).cuda()
+    got_p = np.array([r["PESQ"] for r in pesq(c, d, lengths=lens)])
+    st = stoi_metrics(16000)
+    res = st(c, d, lengths=lens)
+    got_s = np.array([r["STOI"] for r in res]); got_e = np.array([r["ESTOI"] for r in res])
+    kept = st.last_kept_frames.numpy()
+    want_p = po.pesq_batch(clean, deg, lens)
+    want_s, want_e, want_k = so.stoi_batch(clean, deg, 16000, lens)
+    rep = {"pesq": _maxdiff(got_p, want_p), "stoi": _maxdiff(got_s, want_s), "estoi": _maxdiff(got_e, want_e),
+           "K_equal": bool(np.array_equal(kept, want_k))}
+    _report("variable_length", rep)
+    assert rep["pesq"] <= 2e-4 and rep["stoi"] <= 1e-4 and rep["estoi"] <= 1e-4 and rep["K_equal"]
+    # the host entry point (chunked uploads) gives the same numbers
+    host_p = np.array([r["PESQ"] for r in pesq(torch.from_numpy(clean), torch.from_numpy(deg), lengths=lens)])
+    assert np.array_equal(host_p, got_p)
+
+
+def test_large_batch_sample_against_oracle(pesq, stoi_metrics):
+    """BASELINE configs[1] / [2] at full batch (256 x 10 s PESQ, 1024 x 4 s STOI): every item is scored on the
+    GPU, a seeded sample of items is checked against the oracle."""
+    from fast_speech_enhancement_metrics_b200.synth import synth_batch
+    base_c, base_d, _ = synth_batch(555, 16, 160000)
+    c = torch.from_numpy(base_c).cuda().repeat(16, 1)
+    d = torch.from_numpy(base_d).cuda().repeat(16, 1)
+    gains = torch.linspace(0.2, 3.0, 256, device="cuda")[:, None]
+    c, d = (c * gains).contiguous(), (d * gains).contiguous()            # level alignment must cancel the gain
+    got = np.array([r["PESQ"] for r in pesq(c, d)])
+    pick = [0, 17, 100, 255]
+    want = po.pesq_batch(c[pick].cpu().numpy(), d[pick].cpu().numpy())
+    assert _maxdiff(got[pick], want) <= 2e-4
+    assert np.max(np.abs(got.reshape(16, 16) - got[:16][None, :])) <= 2e-5
+    st = stoi_metrics(16000)
+    c4 = c[:, :64000].repeat(4, 1).contiguous()
+    d4 = d[:, 32000:96000].repeat(4, 1).contiguous() * 0.5 + c4 * 0.5
+    res = st(c4, d4)
+    pick = [3, 300, 777, 1023]
+    ws, we, wk = so.stoi_batch(c4[pick].cpu().numpy(), d4[pick].cpu().numpy(), 16000)
+    assert _maxdiff(np.array([res[i]["STOI"] for i in pick]), ws) <= 1e-4
+    assert _maxdiff(np.array([res[i]["ESTOI"] for i in pick]), we) <= 1e-4
+    assert np.array_equal(st.last_kept_frames.numpy()[pick], wk)
