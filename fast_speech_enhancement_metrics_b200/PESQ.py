@@ -21,10 +21,8 @@ class PESQ(BaseMetric):
 
     def __init__(self, sample_rate: int = 16000, use_gpu: bool = False):
         super().__init__(sample_rate, use_gpu)
-        if self.sample_rate != self.EXPECTED_SAMPLING_RATE:
-            raise NotImplementedError(
-                "PESQ resample-on-ingest is not built yet: pass 16 kHz audio (SURVEY.md 8f, rank 2)")
-        self._design = pesq_design()
+        # resample-on-ingest (base.py:13,19-20) runs inside the library as its first kernel
+        self._design, self._taps = pesq_design(self.sample_rate, self.EXPECTED_SAMPLING_RATE)
         handle = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self._lib.fsem_pesq_create(C.byref(handle), C.byref(self._design)))

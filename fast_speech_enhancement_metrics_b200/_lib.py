@@ -108,7 +108,7 @@ def profile_reset() -> None:
 def profile_read() -> dict:
     """{kernel name: (total device ms, launches)} accumulated since the last reset."""
     lib, out = load(), {}
-    for i in range(9):
+    for i in range(16):
         name, ms, cnt = C.c_char_p(), C.c_double(), C.c_int64()
         if lib.fsem_profile_read(i, C.byref(name), C.byref(ms), C.byref(cnt)) != FSEM_OK:
             break

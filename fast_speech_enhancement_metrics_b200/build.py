@@ -35,7 +35,7 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defines=()) -> str:
     if not force and not is_stale():
         return LIB_PATH
     cmd = [
@@ -43,7 +43,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
         "-Xptxas", "-v" if verbose else "-warn-spills",
         "-o", LIB_PATH,
-    ] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart"]
+    ] + ["-D" + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
@@ -53,4 +53,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force=True, verbose="--verbose" in sys.argv))
+    print(build(force=True, verbose="--verbose" in sys.argv, defines=[a[2:] for a in sys.argv[1:] if a.startswith("-D")]))

@@ -46,11 +46,11 @@ inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 // ---- optional per-kernel timing with CUDA events on the launching stream (bench.py only; not thread-safe)
 enum KernelId {
     K_PESQ_FILTER = 0, K_PESQ_SPECTRUM, K_PESQ_BARK, K_STOI_RESAMPLE, K_STOI_ENERGY, K_STOI_COMPACT,
-    K_STOI_TOB, K_STOI_SEGMENT, K_STOI_FINALIZE, K_COUNT
+    K_STOI_TOB, K_STOI_SEGMENT, K_STOI_FINALIZE, K_PESQ_RESAMPLE, K_COUNT
 };
 const char* const kKernelNames[K_COUNT] = {
     "pesq_filter_kernel", "pesq_spectrum_kernel", "pesq_bark_kernel", "stoi_resample_kernel", "stoi_energy_kernel",
-    "stoi_compact_kernel", "stoi_tob_kernel", "stoi_segment_kernel", "stoi_finalize_kernel"};
+    "stoi_compact_kernel", "stoi_tob_kernel", "stoi_segment_kernel", "stoi_finalize_kernel", "pesq_resample_kernel"};
 bool g_profile = false;
 struct ProfRecord { int id; cudaEvent_t start, stop; };
 std::vector<ProfRecord> g_prof_pending;
@@ -196,6 +196,8 @@ struct fsem_pesq_ctx {
     PesqFilterCoef coef;
     int warm = 640;
     PesqTables* d_tab = nullptr;
+    int rs_orig = 1, rs_neu = 1, rs_width = 0, rs_ntaps = 0;   // resample-on-ingest to 16 kHz (base.py:19-20)
+    float* d_rs_taps = nullptr;
     int spec_ctas_per_sm = 2;
     HostPipe pipe;
 };
@@ -203,14 +205,20 @@ struct fsem_pesq_ctx {
 namespace {
 
 struct PesqPlan {
-    int64_t batch, n, zstride;
+    int64_t batch, n, zstride;       // n = samples per item at 16 kHz (after resample-on-ingest)
+    int64_t n_in, rstride;           // input samples per item; row pitch of the resampled signals
+    bool resample;
     int tmax, chunk, nchunks;
-    size_t off_z, off_partial, off_bark, off_dist, off_power, total;
+    size_t off_rs, off_rslen, off_z, off_partial, off_bark, off_dist, off_power, total;
 };
 
-PesqPlan pesq_plan(const fsem_pesq_ctx* ctx, int64_t batch, int64_t n) {
+PesqPlan pesq_plan(const fsem_pesq_ctx* ctx, int64_t batch, int64_t n_in) {
     PesqPlan p{};
     p.batch = batch;
+    p.n_in = n_in;
+    p.resample = ctx->rs_orig != ctx->rs_neu;
+    const int64_t n = stoi_resampled_len(n_in, ctx->rs_orig, ctx->rs_neu);
+    p.rstride = round_up(n > 0 ? n : 1, 4);
     p.n = n;
     p.zstride = round_up(n > 0 ? n : 1, 4);
     p.tmax = pesq_num_frames(n);
@@ -227,6 +235,8 @@ PesqPlan pesq_plan(const fsem_pesq_ctx* ctx, int64_t batch, int64_t n) {
     p.chunk = (int)chunk;
     p.nchunks = (int)nch;
     size_t off = 0;
+    p.off_rs = off;      off = align256(off + (p.resample ? sizeof(float) * 2 * batch * p.rstride : 0));
+    p.off_rslen = off;   off = align256(off + (p.resample ? sizeof(int32_t) * batch : 0));
     p.off_z = off;       off = align256(off + sizeof(float) * 2 * batch * p.zstride);
     p.off_partial = off; off = align256(off + sizeof(double) * 2 * batch * p.nchunks);
     p.off_bark = off;    off = align256(off + sizeof(float) * 2 * batch * p.tmax * FSEM_PESQ_NBANDS);
@@ -286,6 +296,29 @@ extern "C" int fsem_pesq_create(fsem_pesq_ctx_t** out, const fsem_pesq_design_t*
         delete ctx;
         return fail(FSEM_E_CUDA, "fsem_pesq_create: %s", cudaGetErrorString(e));
     }
+    if (e == cudaSuccess && d->rs_orig != d->rs_neu) {
+        if (d->rs_orig <= 0 || d->rs_neu <= 0 || !d->rs_taps || d->rs_ntaps != 2 * d->rs_width + d->rs_orig) {
+            cudaFree(ctx->d_tab);
+            delete ctx;
+            return fail(FSEM_E_INVALID, "fsem_pesq_create: bad resampling kernel (ntaps must be 2*width+orig)");
+        }
+        ctx->rs_orig = d->rs_orig; ctx->rs_neu = d->rs_neu; ctx->rs_width = d->rs_width; ctx->rs_ntaps = d->rs_ntaps;
+        e = cudaMalloc(&ctx->d_rs_taps, sizeof(float) * d->rs_neu * d->rs_ntaps);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(ctx->d_rs_taps, d->rs_taps, sizeof(float) * d->rs_neu * d->rs_ntaps, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(ctx->d_tab);
+            if (ctx->d_rs_taps) cudaFree(ctx->d_rs_taps);
+            delete ctx;
+            return fail(FSEM_E_CUDA, "fsem_pesq_create: %s", cudaGetErrorString(e));
+        }
+    }
+    e = cudaFuncSetAttribute(pesq_bark_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBarkDynSmem);
+    if (e != cudaSuccess) {
+        cudaFree(ctx->d_tab);
+        delete ctx;
+        return fail(FSEM_E_CUDA, "fsem_pesq_create: %s", cudaGetErrorString(e));
+    }
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pesq_spectrum_kernel, kSpecWarps * 32, 0) == cudaSuccess && occ > 0)
         ctx->spec_ctas_per_sm = occ;
@@ -297,6 +330,7 @@ extern "C" int fsem_pesq_destroy(fsem_pesq_ctx_t* ctx) {
     if (!ctx) return FSEM_OK;
     ctx->pipe.destroy();
     if (ctx->d_tab) cudaFree(ctx->d_tab);
+    if (ctx->d_rs_taps) cudaFree(ctx->d_rs_taps);
     delete ctx;
     return FSEM_OK;
 }
@@ -316,12 +350,12 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
     if (in->batch == 0) return FSEM_OK;
     if (!in->clean || !in->deg) return fail(FSEM_E_INVALID, "fsem_pesq_score_f32: null input");
     if (in->n >= (int64_t(1) << 30)) return fail(FSEM_E_INVALID, "fsem_pesq_score_f32: n too large");
+    const PesqPlan p = pesq_plan(ctx, in->batch, in->n);
     // without per-item lengths every item has n samples: fewer than 20 frames is the reference's
     // RuntimeError from unfold (PESQ.py:169)
-    if (!in->lengths && pesq_num_frames(in->n) < 20)
-        return fail(FSEM_E_TOO_SHORT, "PESQ needs at least 20 frames of 512/256 samples; n=%lld gives %d",
-                    (long long)in->n, pesq_num_frames(in->n));
-    const PesqPlan p = pesq_plan(ctx, in->batch, in->n);
+    if (!in->lengths && pesq_num_frames(p.n) < 20)
+        return fail(FSEM_E_TOO_SHORT, "PESQ needs at least 20 frames of 512/256 samples at 16 kHz; n=%lld gives %d",
+                    (long long)in->n, pesq_num_frames(p.n));
     if (!workspace || workspace_bytes < p.total)
         return fail(FSEM_E_WORKSPACE, "fsem_pesq_score_f32: workspace %zu < %zu bytes", workspace_bytes, p.total);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
@@ -331,6 +365,25 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
     float* bark = reinterpret_cast<float*>(ws + p.off_bark);
     float* dist = reinterpret_cast<float*>(ws + p.off_dist);
     double* power = reinterpret_cast<double*>(ws + p.off_power);
+
+    fsem_batch_t rs_batch;
+    if (p.resample) {   // resample-on-ingest to 16 kHz (base.py:19-20), then the pipeline runs on the workspace copy
+        float* y = reinterpret_cast<float*>(ws + p.off_rs);
+        int32_t* rslen = reinterpret_cast<int32_t*>(ws + p.off_rslen);
+        dim3 grid((unsigned)ceil_div(p.n, 256), (unsigned)(2 * in->batch));
+        { ProfScope prof_(K_PESQ_RESAMPLE, stream);
+          stoi_resample_kernel<<<grid, 256, 0, stream>>>(in->clean, in->deg, in->lengths, in->batch, in->n, in->stride,
+                                                        ctx->d_rs_taps, ctx->rs_orig, ctx->rs_neu, ctx->rs_width,
+                                                        ctx->rs_ntaps, y, p.rstride); }
+        FSEM_LAUNCHED();
+        if (in->lengths) {
+            resampled_lengths_kernel<<<(unsigned)ceil_div(in->batch, 256), 256, 0, stream>>>(
+                in->lengths, in->batch, in->n, ctx->rs_orig, ctx->rs_neu, rslen);
+            FSEM_LAUNCHED();
+        }
+        rs_batch = fsem_batch_t{y, y + in->batch * p.rstride, in->lengths ? rslen : nullptr, in->batch, p.n, p.rstride};
+        in = &rs_batch;
+    }
 
     {   // kernel A
         const bool vec4 = aligned16(in->clean) && aligned16(in->deg) && (in->stride % 4 == 0);
@@ -367,7 +420,7 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
     }
     {   // kernel C
         { ProfScope prof_(K_PESQ_BARK, stream);
-          pesq_bark_kernel<<<(unsigned)in->batch, kBarkThreads, 0, stream>>>(bark, partial, p.nchunks, in->lengths,
+          pesq_bark_kernel<<<(unsigned)in->batch, kBarkThreads, kBarkDynSmem, stream>>>(bark, partial, p.nchunks, in->lengths,
                                                                             in->batch, in->n, p.tmax, ctx->d_tab, dist,
                                                                             mos_out, status_out, power); }
         FSEM_LAUNCHED();
@@ -397,9 +450,9 @@ extern "C" int fsem_pesq_score_host_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t
     if (in->batch < 0 || in->n < 0 || in->stride < in->n)
         return fail(FSEM_E_INVALID, "fsem_pesq_score_host_f32: bad shape");
     if (in->batch == 0) return FSEM_OK;
-    if (!in->lengths && pesq_num_frames(in->n) < 20)
-        return fail(FSEM_E_TOO_SHORT, "PESQ needs at least 20 frames of 512/256 samples; n=%lld gives %d",
-                    (long long)in->n, pesq_num_frames(in->n));
+    if (!in->lengths && pesq_num_frames(pesq_plan(ctx, 1, in->n).n) < 20)
+        return fail(FSEM_E_TOO_SHORT, "PESQ needs at least 20 frames of 512/256 samples at 16 kHz; n=%lld is too short",
+                    (long long)in->n);
     int rc = ctx->pipe.init();
     if (rc != FSEM_OK) return rc;
     const int64_t n = in->n, dstride = round_up(n, 4);
@@ -751,9 +804,9 @@ extern "C" int fsem_pesq_stoi_score_host_f32(fsem_pesq_ctx_t* pctx, fsem_stoi_ct
     if (in->batch < 0 || in->n < 0 || in->stride < in->n)
         return fail(FSEM_E_INVALID, "fsem_pesq_stoi_score_host_f32: bad shape");
     if (in->batch == 0) return FSEM_OK;
-    if (!in->lengths && pesq_num_frames(in->n) < 20)
-        return fail(FSEM_E_TOO_SHORT, "PESQ needs at least 20 frames of 512/256 samples; n=%lld gives %d",
-                    (long long)in->n, pesq_num_frames(in->n));
+    if (!in->lengths && pesq_num_frames(pesq_plan(pctx, 1, in->n).n) < 20)
+        return fail(FSEM_E_TOO_SHORT, "PESQ needs at least 20 frames of 512/256 samples at 16 kHz; n=%lld is too short",
+                    (long long)in->n);
     int rc = pctx->pipe.init();
     if (rc != FSEM_OK) return rc;
     const int64_t n = in->n, dstride = round_up(n, 4);

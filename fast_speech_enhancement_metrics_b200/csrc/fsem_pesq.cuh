@@ -316,9 +316,15 @@ pesq_filter_tiled_kernel(const float* __restrict__ clean, const float* __restric
 
 // ------------------------------------------------------------------------------------------------
 // Kernel B: persistent warps; one warp = one (item, frame) unit at a time.
-constexpr int kSpecWarps = 8;
+#ifndef FSEM_FFT_WARPS
+#define FSEM_FFT_WARPS 8
+#endif
+#ifndef FSEM_FFT_MINBLOCKS
+#define FSEM_FFT_MINBLOCKS 2
+#endif
+constexpr int kSpecWarps = FSEM_FFT_WARPS;
 
-__global__ void __launch_bounds__(kSpecWarps * 32)
+__global__ void __launch_bounds__(kSpecWarps * 32, FSEM_FFT_MINBLOCKS)
 pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t* __restrict__ lengths,
                      int64_t batch, int64_t n, int tmax, const PesqTables* __restrict__ tab,
                      float* __restrict__ bark /* [2][batch][tmax][49], unscaled */) {
@@ -401,7 +407,8 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
 // ------------------------------------------------------------------------------------------------
 // Kernel C: one CTA per item; Bark-domain model.
 constexpr int kBarkThreads = 128;
-constexpr int kBarkTile = 64;  // frames per shared-memory tile
+constexpr int kBarkTile = 128;  // frames per shared-memory tile = threads per CTA (one frame per thread)
+constexpr size_t kBarkDynSmem = sizeof(float) * 2 * kBarkTile * FSEM_PESQ_NBANDS;
 
 // x^y for x > 0 through the SFU (lg2.approx / ex2.approx): relative error ~1e-6 for the exponents used here
 // (|y * log2 x| < 10), three orders of magnitude inside the PESQ budget and ~20x cheaper than powf.
@@ -419,7 +426,8 @@ pesq_bark_kernel(const float* __restrict__ bark, const double* __restrict__ part
                  const PesqTables* __restrict__ tab, float* __restrict__ dist_ws /* [2][batch][tmax] */,
                  float* __restrict__ mos_out, int32_t* __restrict__ status_out,
                  double* __restrict__ power_out /* [2][batch] */) {
-    __shared__ float s_tile[2][kBarkTile][FSEM_PESQ_NBANDS];
+    extern __shared__ __align__(16) float s_tile_raw[];            // [2][kBarkTile][49], kBarkDynSmem bytes
+    float (*s_tile)[kBarkTile][FSEM_PESQ_NBANDS] = reinterpret_cast<float (*)[kBarkTile][FSEM_PESQ_NBANDS]>(s_tile_raw);
     __shared__ float s_thr[FSEM_PESQ_NBANDS], s_ithr[FSEM_PESQ_NBANDS], s_exp[FSEM_PESQ_NBANDS],
         s_lsc[FSEM_PESQ_NBANDS], s_w[FSEM_PESQ_NBANDS], s_ratio[FSEM_PESQ_NBANDS];
     __shared__ float s_silent[kBarkTile];
@@ -559,11 +567,8 @@ pesq_bark_kernel(const float* __restrict__ bark, const double* __restrict__ part
                     sym_acc = fmaf(wd, wd, sym_acc);
                     const float ratio = (d + 50.f) / (c + 50.f);
                     float scale = 0.f;
-                    if (!(ratio < 2.49f)) {                // 2.49^1.2 < 3: below that the scale is 0 anyway
-                        scale = fast_pow(ratio, 1.2f);
-                        if (scale < 3.f) scale = 0.f;
-                        scale = fminf(scale, 12.f);
-                    }
+                    // ratio^1.2 < 3  <=>  ratio < 3^(1/1.2): decide on the ratio itself (no pow error in the decision)
+                    if (!(ratio < 2.49804953f)) scale = fminf(fast_pow(ratio, 1.2f), 12.f);
                     asym_acc += fabsf(wd * scale);
                 }
             }

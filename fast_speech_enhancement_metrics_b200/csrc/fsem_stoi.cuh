@@ -52,6 +52,14 @@ stoi_resample_kernel(const float* __restrict__ clean, const float* __restrict__ 
     y[sig * ystride + m] = acc;
 }
 
+// per-item lengths after resampling: ceil(neu * len / orig)
+__global__ void __launch_bounds__(256)
+resampled_lengths_kernel(const int32_t* __restrict__ lengths, int64_t batch, int64_t n, int orig, int neu,
+                         int32_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < batch) out[i] = (int32_t)stoi_resampled_len(item_length(lengths, i, n), orig, neu);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Specialised 16 kHz -> 10 kHz (8:5, half-width 10, 28 taps) resampler.
 //
@@ -277,9 +285,15 @@ stoi_compact_kernel(const float* __restrict__ energy, const int32_t* __restrict_
 //     c_u[q] = w[q] * ( f_{u+1}[q] + (q < 128 ? f_u[q + 128] : f_{u+2}[q - 128]) ),   f_j[q] = w[q] * x[128*t_j + q]
 // zero-padded to 512 (torch.stft centre-pads the 256 window; the circular shift does not change the
 // power spectrum), where t_j is the j-th kept frame.  Every product/sum is rounded to fp32 like the reference.
-constexpr int kTobWarps = 8;
+#ifndef FSEM_FFT_WARPS
+#define FSEM_FFT_WARPS 8
+#endif
+#ifndef FSEM_FFT_MINBLOCKS
+#define FSEM_FFT_MINBLOCKS 2
+#endif
+constexpr int kTobWarps = FSEM_FFT_WARPS;
 
-__global__ void __launch_bounds__(kTobWarps * 32)
+__global__ void __launch_bounds__(kTobWarps * 32, FSEM_FFT_MINBLOCKS)
 stoi_tob_kernel(const float* __restrict__ clean10k, const float* __restrict__ deg10k, int64_t sstride,
                 int64_t batch, int t0max, int umax,
                 int ustride, const int32_t* __restrict__ kept_idx, const int32_t* __restrict__ kept_count,

@@ -34,6 +34,8 @@ class PesqDesign(C.Structure):
         ("pow_dens", C.c_float * NB), ("thresh", C.c_float * NB),
         ("zwicker_exp", C.c_float * NB), ("width_bark", C.c_float * NB),
         ("sl", C.c_float),
+        ("rs_orig", C.c_int32), ("rs_neu", C.c_int32), ("rs_width", C.c_int32), ("rs_ntaps", C.c_int32),
+        ("rs_taps", C.POINTER(C.c_float)),
     ]
 
 
@@ -104,8 +106,17 @@ def _decay_samples(h: np.ndarray, rel: float) -> int:
     return int(idx[0]) if len(idx) else len(h)
 
 
-def pesq_design() -> PesqDesign:
+def pesq_design(sample_rate: int = 16000, target_rate: int = 16000):
+    """Returns (PesqDesign, resampling taps kept alive by the caller or None)."""
     d = PesqDesign()
+    taps = None
+    if sample_rate != target_rate:
+        taps, width, o, nw = sinc_hann_kernel(sample_rate, target_rate)
+        d.rs_orig, d.rs_neu, d.rs_width, d.rs_ntaps = o, nw, width, taps.shape[1]
+        d.rs_taps = taps.ctypes.data_as(C.POINTER(C.c_float))
+    else:
+        d.rs_orig, d.rs_neu, d.rs_width, d.rs_ntaps = 1, 1, 0, 0
+        d.rs_taps = None
     b32, a32 = power_filter_f32()
     k, secs = parallel_sections(b32, a32)
     d.bp_direct = k
@@ -129,7 +140,7 @@ def pesq_design() -> PesqDesign:
     _fill(d.zwicker_exp, exps.tolist())
     _fill(d.width_bark, P862.WIDTH_BARK.tolist())
     d.sl = P862.SL
-    return d
+    return d, taps
 
 
 # ------------------------------------------------------------------------------------------- STOI

@@ -100,6 +100,10 @@ typedef struct fsem_pesq_design {
     float zwicker_exp[FSEM_PESQ_NBANDS]; /* loudness exponents (loudness.py:45-46) */
     float width_bark[FSEM_PESQ_NBANDS];  /* band widths in Bark (bark.py:131) */
     float sl;                            /* Sl (loudness.py:25) */
+    /* resample-on-ingest to 16 kHz (base.py:13,19-20): torchaudio sinc-Hann polyphase kernel, reduced rates;
+     * rs_orig == rs_neu (e.g. both 1): input already is 16 kHz, rs_taps may be NULL */
+    int32_t rs_orig, rs_neu, rs_width, rs_ntaps;
+    const float* rs_taps; /* HOST pointer [rs_neu][rs_ntaps] */
 } fsem_pesq_design_t;
 
 /* Host-designed constants of STOI.__init__ (STOI.py:11-47) and of the ingest resampler
@@ -127,7 +131,7 @@ FSEM_API int64_t fsem_launch_count(void);
 
 /* Optional per-kernel timing (CUDA events on the launching stream).  Bench/diagnostics only,
  * process-global and not thread-safe.  fsem_profile_read synchronises on the recorded events and
- * returns the accumulated device time and launch count of kernel `index` (0 <= index < 9). */
+ * returns the accumulated device time and launch count of kernel `index` (0 <= index < 10). */
 FSEM_API int fsem_profile_enable(int on);
 FSEM_API int fsem_profile_reset(void);
 FSEM_API int fsem_profile_read(int index, const char** name, double* total_ms, int64_t* launches);

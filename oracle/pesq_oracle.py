@@ -190,13 +190,15 @@ def pesq_item(clean: np.ndarray, deg: np.ndarray, taps: dict | None = None) -> f
     return float(mos)
 
 
-def pesq_batch(clean: np.ndarray, deg: np.ndarray, lengths=None) -> np.ndarray:
+def pesq_batch(clean: np.ndarray, deg: np.ndarray, lengths=None, sample_rate: int = 16000) -> np.ndarray:
     """Per-item loop over a [B, n] batch; `lengths` slices each row (the reference
-    called on x[i, :len_i]; legitimate by batch invariance)."""
+    called on x[i, :len_i]; legitimate by batch invariance).  sample_rate != 16000:
+    resample-on-ingest first (base.py:19-20, torchaudio sinc-Hann kernel)."""
+    from .stoi_oracle import resample
     clean = np.atleast_2d(clean)
     deg = np.atleast_2d(deg)
     out = np.empty(clean.shape[0], np.float64)
     for i in range(clean.shape[0]):
         n = clean.shape[1] if lengths is None else int(lengths[i])
-        out[i] = pesq_item(clean[i, :n], deg[i, :n])
+        out[i] = pesq_item(resample(clean[i, :n], sample_rate, 16000), resample(deg[i, :n], sample_rate, 16000))
     return out

@@ -46,6 +46,20 @@ def pesq_cases():
     return cases
 
 
+def pesq_rate_cases():
+    """PESQ with resample-on-ingest (base.py:13,19-20): (clean, degraded, lengths, sample_rate)."""
+    cases = {}
+    c, d, _ = synth_batch(121, 3, 16000, fs=8000)
+    cases["speech8k_2s"] = (c, d, None, 8000)               # 1:2 up-sampling
+    c, d, _ = synth_batch(122, 2, 96000, fs=48000)
+    cases["speech48k_2s"] = (c, d, None, 48000)             # 3:1 down-sampling
+    c, d, _ = synth_batch(123, 2, 44100, fs=44100)
+    cases["speech44k1_1s"] = (c, d, None, 44100)            # 441:160
+    c, d, _ = synth_batch(124, 3, 48000, fs=24000)
+    cases["ragged24k"] = (c, d, [48000, 30001, 12345], 24000)
+    return cases
+
+
 def stoi_cases():
     cases = {}
     c, d, _ = synth_batch(201, 8, 30000, fs=10000)

@@ -35,7 +35,7 @@ import importlib.util  # noqa: E402
 _spec = importlib.util.spec_from_file_location("golden_cases", os.path.join(HERE, "cases.py"))
 _cases = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(_cases)   # (the reference ships its own `tests` package, so import by path)
-pesq_cases, stoi_cases = _cases.pesq_cases, _cases.stoi_cases
+pesq_cases, stoi_cases, pesq_rate_cases = _cases.pesq_cases, _cases.stoi_cases, _cases.pesq_rate_cases
 
 
 def run_pesq():
@@ -51,6 +51,16 @@ def run_pesq():
             res = [metric(c[i:i + 1, :n], d[i:i + 1, :n])[0]["PESQ"] for i, n in enumerate(lengths)]
         out[name] = np.asarray(res, np.float64)
         print(name, out[name])
+    for name, (clean, deg, lengths, fs) in pesq_rate_cases().items():
+        m = PESQ(fs, use_gpu=False)
+        c = torch.from_numpy(clean)
+        d = torch.from_numpy(deg)
+        if lengths is None:
+            res = [r["PESQ"] for r in m(c, d)]
+        else:
+            res = [m(c[i:i + 1, :n], d[i:i + 1, :n])[0]["PESQ"] for i, n in enumerate(lengths)]
+        out["rate/" + name] = np.asarray(res, np.float64)
+        print(name, out["rate/" + name])
     # stage taps for the first "speech2s" item: band power (float32 IIR as the reference
     # runs it) and the Bark-band spectrogram of the clean signal
     clean, deg, _ = pesq_cases()["speech2s"]

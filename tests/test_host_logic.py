@@ -28,7 +28,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header_sizes():
     # sizes implied by include/fsem.h (all members are 4-byte scalars except the taps pointer)
-    assert ctypes.sizeof(design.PesqDesign) == 4 * (1 + 4 * 5 + 3 + 2 + 15 + 1 + 512 + 6 * 49 + 1)
+    assert ctypes.sizeof(design.PesqDesign) == 4 * (1 + 4 * 5 + 3 + 2 + 15 + 1 + 512 + 6 * 49 + 1) + 4 * 4 + 4 + 8   # + resampler, pad, taps*
     assert ctypes.sizeof(design.StoiDesign) == 16 + 8 + 4 * 256 + 4 * 30 + 8
     assert ctypes.sizeof(_lib.Batch) == 48
 
@@ -45,7 +45,7 @@ def test_pesq_design_reproduces_the_reference_filter(golden_pesq):
     b32, a32 = design.power_filter_f32()
     assert np.array_equal(b32, golden_pesq["tap_power_filter"][0])
     assert np.array_equal(a32, golden_pesq["tap_power_filter"][1])
-    d = design.pesq_design()
+    d, _ = design.pesq_design()
     assert np.array_equal(np.array(d.hann[:], np.float32), golden_pesq["tap_hann512"])
     # the float32 parallel form run in float64 reproduces the direct form's band power
     rng = np.random.default_rng(0)
