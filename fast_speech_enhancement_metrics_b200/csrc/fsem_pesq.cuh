@@ -407,7 +407,7 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
 // ------------------------------------------------------------------------------------------------
 // Kernel C: one CTA per item; Bark-domain model.
 constexpr int kBarkThreads = 128;
-constexpr int kBarkTile = 128;  // frames per shared-memory tile = threads per CTA (one frame per thread)
+constexpr int kBarkTile = 64;   // frames per shared-memory tile (128 was slower: fewer resident CTAs to hide the barriers)
 constexpr size_t kBarkDynSmem = sizeof(float) * 2 * kBarkTile * FSEM_PESQ_NBANDS;
 
 // x^y for x > 0 through the SFU (lg2.approx / ex2.approx): relative error ~1e-6 for the exponents used here
