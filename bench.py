@@ -238,6 +238,8 @@ def main():
     ap.add_argument("--batch", type=int, default=8192, help="total items over all ranks")
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--two-streams", action="store_true",
+                    help="experiment: run the PESQ and the STOI kernel chains on two CUDA streams")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -278,9 +280,22 @@ def main():
 
     gathered = torch.empty(args.batch, 3, dtype=torch.float32, device=device)
 
+    side = (torch.cuda.Stream(device), torch.cuda.Stream(device)) if args.two_streams else None
+
     def step_device():
-        mos, _ = pesq.score_tensors(clean, deg)
-        sc, _, _ = stoi.score_tensors(clean, deg)
+        if side is None:
+            mos, _ = pesq.score_tensors(clean, deg)
+            sc, _, _ = stoi.score_tensors(clean, deg)
+        else:
+            cur = torch.cuda.current_stream(device)
+            side[0].wait_stream(cur)
+            side[1].wait_stream(cur)
+            with torch.cuda.stream(side[0]):
+                mos, _ = pesq.score_tensors(clean, deg)
+            with torch.cuda.stream(side[1]):
+                sc, _, _ = stoi.score_tensors(clean, deg)
+            cur.wait_stream(side[0])
+            cur.wait_stream(side[1])
         local = torch.stack([mos, sc[0], sc[1]], dim=1)
         return gather_scores(local, args.batch, world, out=gathered)
 

@@ -313,12 +313,6 @@ extern "C" int fsem_pesq_create(fsem_pesq_ctx_t** out, const fsem_pesq_design_t*
             return fail(FSEM_E_CUDA, "fsem_pesq_create: %s", cudaGetErrorString(e));
         }
     }
-    e = cudaFuncSetAttribute(pesq_bark_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBarkDynSmem);
-    if (e != cudaSuccess) {
-        cudaFree(ctx->d_tab);
-        delete ctx;
-        return fail(FSEM_E_CUDA, "fsem_pesq_create: %s", cudaGetErrorString(e));
-    }
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pesq_spectrum_kernel, kSpecWarps * 32, 0) == cudaSuccess && occ > 0)
         ctx->spec_ctas_per_sm = occ;
@@ -420,7 +414,7 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
     }
     {   // kernel C
         { ProfScope prof_(K_PESQ_BARK, stream);
-          pesq_bark_kernel<<<(unsigned)in->batch, kBarkThreads, kBarkDynSmem, stream>>>(bark, partial, p.nchunks, in->lengths,
+          pesq_bark_kernel<<<(unsigned)in->batch, kBarkThreads, 0, stream>>>(bark, partial, p.nchunks, in->lengths,
                                                                             in->batch, in->n, p.tmax, ctx->d_tab, dist,
                                                                             mos_out, status_out, power); }
         FSEM_LAUNCHED();

@@ -407,8 +407,8 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
 // ------------------------------------------------------------------------------------------------
 // Kernel C: one CTA per item; Bark-domain model.
 constexpr int kBarkThreads = 128;
-constexpr int kBarkTile = 64;   // frames per shared-memory tile (128 was slower: fewer resident CTAs to hide the barriers)
-constexpr size_t kBarkDynSmem = sizeof(float) * 2 * kBarkTile * FSEM_PESQ_NBANDS;
+constexpr int kBarkTile = 64;   // frames per shared-memory tile; two threads per frame (128 frames/tile was slower: fewer
+                                // resident CTAs to hide the barriers)
 
 // x^y for x > 0 through the SFU (lg2.approx / ex2.approx): relative error ~1e-6 for the exponents used here
 // (|y * log2 x| < 10), three orders of magnitude inside the PESQ budget and ~20x cheaper than powf.
@@ -426,8 +426,7 @@ pesq_bark_kernel(const float* __restrict__ bark, const double* __restrict__ part
                  const PesqTables* __restrict__ tab, float* __restrict__ dist_ws /* [2][batch][tmax] */,
                  float* __restrict__ mos_out, int32_t* __restrict__ status_out,
                  double* __restrict__ power_out /* [2][batch] */) {
-    extern __shared__ __align__(16) float s_tile_raw[];            // [2][kBarkTile][49], kBarkDynSmem bytes
-    float (*s_tile)[kBarkTile][FSEM_PESQ_NBANDS] = reinterpret_cast<float (*)[kBarkTile][FSEM_PESQ_NBANDS]>(s_tile_raw);
+    __shared__ float s_tile[2][kBarkTile][FSEM_PESQ_NBANDS];
     __shared__ float s_thr[FSEM_PESQ_NBANDS], s_ithr[FSEM_PESQ_NBANDS], s_exp[FSEM_PESQ_NBANDS],
         s_lsc[FSEM_PESQ_NBANDS], s_w[FSEM_PESQ_NBANDS], s_ratio[FSEM_PESQ_NBANDS];
     __shared__ float s_silent[kBarkTile];
@@ -491,14 +490,18 @@ pesq_bark_kernel(const float* __restrict__ bark, const double* __restrict__ part
         __syncthreads();
         load_tile(f0, nf);
         __syncthreads();
-        if (tid < nf) {
+        {   // two threads per frame (even / odd bands), combined with one shuffle
+            const int fs = tid >> 1, half = tid & 1;
             float a = 0.f;
-#pragma unroll 7
-            for (int b = 0; b < FSEM_PESQ_NBANDS; ++b) {
-                float p = s_tile[0][tid][b];
-                a += p * ((p > s_thr[b] * 100.f) ? 1.f : 0.f);
+            if (fs < nf) {
+#pragma unroll 5
+                for (int b = half; b < FSEM_PESQ_NBANDS; b += 2) {
+                    float p = s_tile[0][fs][b];
+                    a += p * ((p > s_thr[b] * 100.f) ? 1.f : 0.f);
+                }
             }
-            s_silent[tid] = (a < 1.0e7f) ? 1.f : 0.f;
+            a += __shfl_xor_sync(kFull, a, 1);
+            if (fs < nf && half == 0) s_silent[fs] = (a < 1.0e7f) ? 1.f : 0.f;
         }
         __syncthreads();
         if (tid < 2 * FSEM_PESQ_NBANDS) {
@@ -529,31 +532,35 @@ pesq_bark_kernel(const float* __restrict__ bark, const double* __restrict__ part
         __syncthreads();
         load_tile(f0, nf);
         __syncthreads();
-        float afp_c = 0.f;
-        if (tid < nf) {
-            float afp_d = 0.f;
-#pragma unroll 7
-            for (int b = 0; b < FSEM_PESQ_NBANDS; ++b) {
-                float c = s_ratio[b] * s_tile[0][tid][b];
-                float d = s_tile[1][tid][b];
+        // two threads per frame: thread 2*fs handles the even bands, 2*fs+1 the odd ones
+        const int fs = tid >> 1, half = tid & 1;
+        const bool live = fs < nf;
+        float afp_c = 0.f, afp_d = 0.f;
+        if (live) {
+#pragma unroll 5
+            for (int b = half; b < FSEM_PESQ_NBANDS; b += 2) {
+                float c = s_ratio[b] * s_tile[0][fs][b];
+                float d = s_tile[1][fs][b];
                 afp_c += c * ((c > s_thr[b]) ? 1.f : 0.f);
                 afp_d += d * ((d > s_thr[b]) ? 1.f : 0.f);
             }
-            s_fr[tid] = (afp_c + 5.0e3f) / (afp_d + 5.0e3f);
         }
+        afp_c += __shfl_xor_sync(kFull, afp_c, 1);
+        afp_d += __shfl_xor_sync(kFull, afp_d, 1);
+        if (live && half == 0) s_fr[fs] = (afp_c + 5.0e3f) / (afp_d + 5.0e3f);
         __syncthreads();
-        if (tid < nf) {
-            const int f = f0 + tid;
-            float fr = s_fr[tid];
+        float sym_acc = 0.f, asym_acc = 0.f;
+        if (live) {
+            const int f = f0 + fs;
+            float fr = s_fr[fs];
             if (f > 0) {
-                float prev = (tid == 0) ? s_carry : s_fr[tid - 1];
+                float prev = (fs == 0) ? s_carry : s_fr[fs - 1];
                 fr = 0.8f * fr + 0.2f * prev;               // non-recursive smoothing (PESQ.py:159)
             }
             fr = fminf(fmaxf(fr, 3.0e-4f), 5.f);
-            float sym_acc = 0.f, asym_acc = 0.f;
-            for (int b = 0; b < FSEM_PESQ_NBANDS; ++b) {
-                const float c = s_ratio[b] * s_tile[0][tid][b];
-                const float d = fr * s_tile[1][tid][b];
+            for (int b = half; b < FSEM_PESQ_NBANDS; b += 2) {
+                const float c = s_ratio[b] * s_tile[0][fs][b];
+                const float d = fr * s_tile[1][fs][b];
                 const float thr = s_thr[b], ithr = s_ithr[b], e = s_exp[b], lsc = s_lsc[b];
                 const float lc = zwicker_loudness(c, thr, ithr, e, lsc);
                 const float ld = zwicker_loudness(d, thr, ithr, e, lsc);
@@ -565,13 +572,18 @@ pesq_bark_kernel(const float* __restrict__ bark, const double* __restrict__ part
                 if (b >= 1) {                               // band 0 excluded (bark.py:184)
                     const float wd = s_w[b] * dist;
                     sym_acc = fmaf(wd, wd, sym_acc);
-                    const float ratio = (d + 50.f) / (c + 50.f);
+                    const float ratio = __fdividef(d + 50.f, c + 50.f);
                     float scale = 0.f;
                     // ratio^1.2 < 3  <=>  ratio < 3^(1/1.2): decide on the ratio itself (no pow error in the decision)
                     if (!(ratio < 2.49804953f)) scale = fminf(fast_pow(ratio, 1.2f), 12.f);
                     asym_acc += fabsf(wd * scale);
                 }
             }
+        }
+        sym_acc += __shfl_xor_sync(kFull, sym_acc, 1);
+        asym_acc += __shfl_xor_sync(kFull, asym_acc, 1);
+        if (live && half == 0) {
+            const int f = f0 + fs;
             float sym = fmaxf(sqrtf(wtot * sym_acc), 1.0e-20f);
             float asym = fmaxf(asym_acc, 1.0e-20f);
             const float weight = fast_pow((afp_c + 1.0e5f) * 1.0e-7f, 0.04f);
