@@ -163,9 +163,10 @@ __device__ __forceinline__ void warp_fft512(float (&re)[16], float (&im)[16], fl
     for (int h = 0; h < 2; ++h) {
         const int k0 = (lane >> 3) + 4 * h;
         dft8<false>(r2[h], i2[h]);
+        // fft_out_index(k0 + 8*k1 + 64*k2) = k0 + 10*k1 + 80*k2 (k0 < 8): one base address + immediates
+        float2* out = buf + (k0 + 10 * k1);
 #pragma unroll
-        for (int k2 = 0; k2 < 8; ++k2)
-            buf[fft_out_index(k0 + 8 * k1 + 64 * k2)] = make_float2(r2[h][k2], i2[h][k2]);
+        for (int k2 = 0; k2 < 8; ++k2) out[80 * k2] = make_float2(r2[h][k2], i2[h][k2]);
     }
     __syncwarp();
 }
@@ -204,6 +205,7 @@ __device__ __forceinline__ void packed_power8(const float2* buf, int lane, float
 struct BandPlan {
     unsigned start_mask;   // bit j set: bin 8L + j is the first bin of a band
     int first_band;        // index of the band that starts at the lowest set bit (bands are consecutive)
+    unsigned add_mask;     // bit d set: the band open at this lane's right edge also owns the head bins of lane L + d
     // Build from band start bins (ascending, starts[0] == 0 expected so that every bin belongs to a band).
     __device__ __forceinline__ void init(const int32_t* starts, int nbands, int lane) {
         start_mask = 0u;
@@ -214,6 +216,15 @@ struct BandPlan {
                 start_mask |= 1u << (f & 7);
                 first_band = min(first_band, b);
             }
+        }
+        // lanes without a band start are "transparent": the open band of an earlier lane runs through them
+        const unsigned transparent = __ballot_sync(0xffffffffu, start_mask == 0u);
+        add_mask = 0u;
+        bool open = true;
+        for (int d = 1; d < 32; ++d) {
+            if (!open || lane + d >= 32) break;
+            add_mask |= 1u << d;
+            open = (transparent >> (lane + d)) & 1u;
         }
     }
 };
@@ -239,14 +250,11 @@ __device__ __forceinline__ void band_sums8(const float (&pc)[8], const float (&p
     }
     const bool transparent = nb < 0;           // no band starts here: all 8 bins continue an earlier band
     if (transparent) { head_c = run_c; head_d = run_d; run_c = 0.f; run_d = 0.f; }
-    bool open = true;
 #pragma unroll
     for (int d = 1; d <= kSpan; ++d) {
-        float hc = __shfl_down_sync(0xffffffffu, head_c, d);
-        float hd = __shfl_down_sync(0xffffffffu, head_d, d);
-        bool tr = __shfl_down_sync(0xffffffffu, transparent ? 1 : 0, d) != 0;
-        if (open && lane + d < 32) { run_c += hc; run_d += hd; }
-        open = open && tr && (lane + d < 32);
+        const float hc = __shfl_down_sync(0xffffffffu, head_c, d);
+        const float hd = __shfl_down_sync(0xffffffffu, head_d, d);
+        if ((plan.add_mask >> d) & 1u) { run_c += hc; run_d += hd; }
     }
     if (!transparent) emit(plan.first_band + nb, run_c, run_d);
 }
