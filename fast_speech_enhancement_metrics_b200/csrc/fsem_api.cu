@@ -313,8 +313,15 @@ extern "C" int fsem_pesq_create(fsem_pesq_ctx_t** out, const fsem_pesq_design_t*
             return fail(FSEM_E_CUDA, "fsem_pesq_create: %s", cudaGetErrorString(e));
         }
     }
+    e = cudaFuncSetAttribute(pesq_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpecDynSmem);
+    if (e != cudaSuccess) {
+        cudaFree(ctx->d_tab);
+        if (ctx->d_rs_taps) cudaFree(ctx->d_rs_taps);
+        delete ctx;
+        return fail(FSEM_E_CUDA, "fsem_pesq_create: %s", cudaGetErrorString(e));
+    }
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pesq_spectrum_kernel, kSpecWarps * 32, 0) == cudaSuccess && occ > 0)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pesq_spectrum_kernel, kSpecWarps * 32, kSpecDynSmem) == cudaSuccess && occ > 0)
         ctx->spec_ctas_per_sm = occ;
     *out = ctx;
     return FSEM_OK;
@@ -408,7 +415,7 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
         const int64_t cap = (int64_t)ctx->dev.sms * ctx->spec_ctas_per_sm;
         if (grid > cap) grid = cap;
         { ProfScope prof_(K_PESQ_SPECTRUM, stream);
-          pesq_spectrum_kernel<<<(unsigned)grid, kSpecWarps * 32, 0, stream>>>(z, p.zstride, in->lengths, in->batch,
+          pesq_spectrum_kernel<<<(unsigned)grid, kSpecWarps * 32, kSpecDynSmem, stream>>>(z, p.zstride, in->lengths, in->batch,
                                                                               in->n, p.tmax, ctx->d_tab, bark); }
         FSEM_LAUNCHED();
     }

@@ -324,17 +324,40 @@ pesq_filter_tiled_kernel(const float* __restrict__ clean, const float* __restric
 #endif
 constexpr int kSpecWarps = FSEM_FFT_WARPS;
 
+// Shared-memory plan of the spectrum kernel (dynamic): per warp an FFT exchange buffer, a band staging row and a
+// 3-slot ring of half-frames (256 samples of the clean and of the degraded signal per slot) filled by TMA bulk
+// copies: frame f needs halves f and f+1, half f+2 is in flight while frame f is transformed, so the global-load
+// latency is off the critical path and every sample is fetched from L2/HBM once (frames overlap by 50 %).
+struct SpecWarpSmem {
+    float2 fft[kFftBufElems];          // 5120 B
+    float half_c[3][FSEM_PESQ_HOP];    // 3072 B
+    float half_d[3][FSEM_PESQ_HOP];    // 3072 B
+    float bands[2][64];                //  512 B
+    unsigned long long bar[3];         //   24 B (+8 pad)
+    unsigned long long pad_;
+};
+constexpr size_t kSpecDynSmem = sizeof(SpecWarpSmem) * kSpecWarps;
+static_assert(sizeof(SpecWarpSmem) % 16 == 0, "per-warp shared block must keep 16-byte alignment");
+
 __global__ void __launch_bounds__(kSpecWarps * 32, FSEM_FFT_MINBLOCKS)
 pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t* __restrict__ lengths,
                      int64_t batch, int64_t n, int tmax, const PesqTables* __restrict__ tab,
                      float* __restrict__ bark /* [2][batch][tmax][49], unscaled */) {
-    __shared__ __align__(16) float2 s_buf[kSpecWarps][kFftBufElems];
-    __shared__ float s_band[kSpecWarps][2][64];
+    extern __shared__ __align__(16) unsigned char s_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    float2* buf = s_buf[warp];
-    float* bands_c = s_band[warp][0];
-    float* bands_d = s_band[warp][1];
+    SpecWarpSmem& sm = reinterpret_cast<SpecWarpSmem*>(s_raw)[warp];
+    float2* buf = sm.fft;
+    float* bands_c = sm.bands[0];
+    float* bands_d = sm.bands[1];
+    const uint32_t bar0 = smem_u32(&sm.bar[0]);
+    const uint32_t hc0 = smem_u32(&sm.half_c[0][0]), hd0 = smem_u32(&sm.half_d[0][0]);
+    constexpr uint32_t kHalfBytes = FSEM_PESQ_HOP * sizeof(float);
+    if (lane == 0) {
+        for (int i = 0; i < 3; ++i) mbar_init(bar0 + 8 * i, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
 
     FftTwiddles tw;
     tw.init(lane);
@@ -351,56 +374,99 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
     const int64_t units = batch * (int64_t)tmax;
     const int64_t nwarps = (int64_t)gridDim.x * kSpecWarps;
     const int64_t per = (units + nwarps - 1) / nwarps;
-    const int64_t u0 = ((int64_t)blockIdx.x * kSpecWarps + warp) * per;
-    const int64_t u1 = min(units, u0 + per);
-    if (u0 >= u1) return;
-    int64_t item = u0 / tmax;
-    int f = (int)(u0 - item * tmax);
+    int64_t u = ((int64_t)blockIdx.x * kSpecWarps + warp) * per;
+    const int64_t u1 = min(units, u + per);
+    if (u >= u1) return;
+    int64_t item = u / tmax;
+    int f = (int)(u - item * tmax);
     int len = item_length(lengths, item, n);
     int T = pesq_num_frames(len);
-    for (int64_t u = u0; u < u1; ++u) {
-        if (f < T) {
-            const int first = f * FSEM_PESQ_HOP + lane;
-            const float* __restrict__ zc = z + item * zstride + first;
-            const float* __restrict__ zd = z + (batch + item) * zstride + first;
-            // Loads are unconditional: a frame that sticks out of the signal reads on into the workspace (always
-            // mapped), and those samples are then replaced by the zero padding of PESQ.py:128-130.
-            float re[16], im[16];
-#pragma unroll
-            for (int m = 0; m < 16; ++m) {
-                re[m] = __ldg(zc + 32 * m) * win[m];
-                im[m] = __ldg(zd + 32 * m) * win[m];
-            }
-            if (f * FSEM_PESQ_HOP + FSEM_PESQ_NFFT > len) {      // warp-uniform, last frame(s) only
-                const int room = len - first;
-#pragma unroll
-                for (int m = 0; m < 16; ++m)
-                    if (32 * m >= room) { re[m] = 0.f; im[m] = 0.f; }
-            }
-            warp_fft512<false>(re, im, buf, tw, lane);
-            float pc[8], pd[8];
-            packed_power8(buf, lane, pc, pd);
-            if (lane == 0) { pc[0] = 0.f; pd[0] = 0.f; }     // "we won't use energy feature" (PESQ.py:136)
-            band_sums8<4>(pc, pd, plan, lane, [&](int band, float sc, float sd) {
-                bands_c[band] = sc;
-                bands_d[band] = sd;
-            });
-            __syncwarp();
-            float* __restrict__ out_c = bark + (item * tmax + f) * FSEM_PESQ_NBANDS;
-            float* __restrict__ out_d = bark + ((batch + item) * tmax + f) * FSEM_PESQ_NBANDS;
-            out_c[lane] = bands_c[lane] * scale0;
-            out_d[lane] = bands_d[lane] * scale0;
-            if (lane + 32 < FSEM_PESQ_NBANDS) {
-                out_c[lane + 32] = bands_c[lane + 32] * scale1;
-                out_d[lane + 32] = bands_d[lane + 32] * scale1;
-            }
-            __syncwarp();
+    // first valid unit at or after (u, item, f); frames f >= T of a short item are skipped in one step
+    auto seek = [&](int64_t& uu, int64_t& it, int& ff, int& ll, int& tt) -> bool {
+        while (uu < u1) {
+            if (ff < tt) return true;
+            uu += tmax - ff;
+            ff = 0;
+            if (++it >= batch) return false;
+            ll = item_length(lengths, it, n);
+            tt = pesq_num_frames(ll);
         }
-        if (++f == tmax) {
-            f = 0;
-            ++item;
-            if (item < batch) { len = item_length(lengths, item, n); T = pesq_num_frames(len); }
+        return false;
+    };
+    if (!seek(u, item, f, len, T)) return;
+
+    // half h of item `it` = samples [256 h, 256 h + 256) of both signals -> ring slot q % 3, q = issue counter
+    uint32_t q_issued = 0;
+    auto issue_half = [&](int64_t it, int h) -> uint32_t {
+        const uint32_t q = q_issued++;
+        if (lane == 0) {
+            const uint32_t slot = q % 3u;
+            fence_proxy_async();
+            mbar_arrive_expect_tx(bar0 + 8 * slot, 2 * kHalfBytes);
+            bulk_copy_g2s(hc0 + slot * kHalfBytes, z + it * zstride + (int64_t)h * FSEM_PESQ_HOP, kHalfBytes, bar0 + 8 * slot);
+            bulk_copy_g2s(hd0 + slot * kHalfBytes, z + (batch + it) * zstride + (int64_t)h * FSEM_PESQ_HOP, kHalfBytes,
+                          bar0 + 8 * slot);
         }
+        return q;
+    };
+    uint32_t qa = issue_half(item, f);
+    uint32_t qb = issue_half(item, f + 1);
+
+    while (true) {
+        // look ahead: the next valid unit of this warp's range, and the half it will need next
+        int64_t u2 = u + 1, item2 = item;
+        int f2 = f + 1, len2 = len, T2 = T;
+        const bool has_next = seek(u2, item2, f2, len2, T2);
+        uint32_t qa2 = 0, qb2 = 0;
+        bool need_second = false;
+        __syncwarp();                                           // all lanes are done with the slot about to be refilled
+        if (has_next) {
+            if (item2 == item && f2 == f + 1) { qa2 = qb; qb2 = issue_half(item, f + 2); }
+            else { qa2 = issue_half(item2, f2); need_second = true; }
+        }
+        // wait for the two halves of the current frame (slot phase = number of earlier uses of the slot)
+        mbar_wait(bar0 + 8 * (qa % 3u), (qa / 3u) & 1u);
+        mbar_wait(bar0 + 8 * (qb % 3u), (qb / 3u) & 1u);
+        const float* ac = sm.half_c[qa % 3u] + lane;
+        const float* ad = sm.half_d[qa % 3u] + lane;
+        const float* bc = sm.half_c[qb % 3u] + lane;
+        const float* bd = sm.half_d[qb % 3u] + lane;
+        float re[16], im[16];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            re[m] = ac[32 * m] * win[m];
+            im[m] = ad[32 * m] * win[m];
+            re[m + 8] = bc[32 * m] * win[m + 8];
+            im[m + 8] = bd[32 * m] * win[m + 8];
+        }
+        if (f * FSEM_PESQ_HOP + FSEM_PESQ_NFFT > len) {          // warp-uniform, last frame(s) only:
+            const int room = len - (f * FSEM_PESQ_HOP + lane);   // zero padding beyond the signal (PESQ.py:128-130)
+#pragma unroll
+            for (int m = 0; m < 16; ++m)
+                if (32 * m >= room) { re[m] = 0.f; im[m] = 0.f; }
+        }
+        warp_fft512<false>(re, im, buf, tw, lane);
+        float pc[8], pd[8];
+        packed_power8(buf, lane, pc, pd);
+        if (lane == 0) { pc[0] = 0.f; pd[0] = 0.f; }             // "we won't use energy feature" (PESQ.py:136)
+        band_sums8<4>(pc, pd, plan, lane, [&](int band, float sc, float sd) {
+            bands_c[band] = sc;
+            bands_d[band] = sd;
+        });
+        __syncwarp();
+        float* __restrict__ out_c = bark + (item * tmax + f) * FSEM_PESQ_NBANDS;
+        float* __restrict__ out_d = bark + ((batch + item) * tmax + f) * FSEM_PESQ_NBANDS;
+        out_c[lane] = bands_c[lane] * scale0;
+        out_d[lane] = bands_d[lane] * scale0;
+        if (lane + 32 < FSEM_PESQ_NBANDS) {
+            out_c[lane + 32] = bands_c[lane + 32] * scale1;
+            out_d[lane + 32] = bands_d[lane + 32] * scale1;
+        }
+        if (!has_next) break;
+        u = u2; item = item2; f = f2; len = len2; T = T2;
+        qa = qa2;
+        if (need_second) { __syncwarp(); qb = issue_half(item, f + 1); }
+        else qb = qb2;
     }
 }
 
