@@ -395,42 +395,43 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
     };
     if (!seek(u, item, f, len, T)) return;
 
-    // half h of item `it` = samples [256 h, 256 h + 256) of both signals -> ring slot q % 3, q = issue counter
-    uint32_t q_issued = 0;
-    auto issue_half = [&](int64_t it, int h) -> uint32_t {
-        const uint32_t q = q_issued++;
+    // Ring bookkeeping: half h of an item = samples [256 h, 256 h + 256) of both signals.  Slots rotate 0,1,2;
+    // `par` bit s is the mbarrier phase parity the latest copy into slot s completes (flipped at every issue).
+    unsigned par = 7u;
+    auto issue_half = [&](int slot, int64_t it, int h) {
+        par ^= 1u << slot;
         if (lane == 0) {
-            const uint32_t slot = q % 3u;
             fence_proxy_async();
             mbar_arrive_expect_tx(bar0 + 8 * slot, 2 * kHalfBytes);
-            bulk_copy_g2s(hc0 + slot * kHalfBytes, z + it * zstride + (int64_t)h * FSEM_PESQ_HOP, kHalfBytes, bar0 + 8 * slot);
-            bulk_copy_g2s(hd0 + slot * kHalfBytes, z + (batch + it) * zstride + (int64_t)h * FSEM_PESQ_HOP, kHalfBytes,
+            bulk_copy_g2s(hc0 + slot * kHalfBytes, z + it * zstride + h * FSEM_PESQ_HOP, kHalfBytes, bar0 + 8 * slot);
+            bulk_copy_g2s(hd0 + slot * kHalfBytes, z + (batch + it) * zstride + h * FSEM_PESQ_HOP, kHalfBytes,
                           bar0 + 8 * slot);
         }
-        return q;
     };
-    uint32_t qa = issue_half(item, f);
-    uint32_t qb = issue_half(item, f + 1);
+    int sa = 0, sb = 1;                                          // slots of the current frame's two halves
+    issue_half(0, item, f);
+    issue_half(1, item, f + 1);
 
     while (true) {
-        // look ahead: the next valid unit of this warp's range, and the half it will need next
+        const int sn = 3 - sa - sb;                              // the free slot
+        // look ahead: next valid unit of this warp's range; fast path = next frame of the same item
         int64_t u2 = u + 1, item2 = item;
         int f2 = f + 1, len2 = len, T2 = T;
-        const bool has_next = seek(u2, item2, f2, len2, T2);
-        uint32_t qa2 = 0, qb2 = 0;
-        bool need_second = false;
-        __syncwarp();                                           // all lanes are done with the slot about to be refilled
+        bool has_next, same_item;
+        if (f2 < T && u2 < u1) { has_next = true; same_item = true; }
+        else { has_next = seek(u2, item2, f2, len2, T2); same_item = false; }
+        __syncwarp();                                            // all lanes are done with the slot about to be refilled
         if (has_next) {
-            if (item2 == item && f2 == f + 1) { qa2 = qb; qb2 = issue_half(item, f + 2); }
-            else { qa2 = issue_half(item2, f2); need_second = true; }
+            if (same_item) issue_half(sn, item, f + 2);
+            else issue_half(sn, item2, f2);
         }
-        // wait for the two halves of the current frame (slot phase = number of earlier uses of the slot)
-        mbar_wait(bar0 + 8 * (qa % 3u), (qa / 3u) & 1u);
-        mbar_wait(bar0 + 8 * (qb % 3u), (qb / 3u) & 1u);
-        const float* ac = sm.half_c[qa % 3u] + lane;
-        const float* ad = sm.half_d[qa % 3u] + lane;
-        const float* bc = sm.half_c[qb % 3u] + lane;
-        const float* bd = sm.half_d[qb % 3u] + lane;
+        // wait for the two halves of the current frame
+        mbar_wait(bar0 + 8 * sa, (par >> sa) & 1u);
+        mbar_wait(bar0 + 8 * sb, (par >> sb) & 1u);
+        const float* ac = sm.half_c[sa] + lane;
+        const float* ad = sm.half_d[sa] + lane;
+        const float* bc = sm.half_c[sb] + lane;
+        const float* bd = sm.half_d[sb] + lane;
         float re[16], im[16];
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
@@ -463,10 +464,16 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
             out_d[lane + 32] = bands_d[lane + 32] * scale1;
         }
         if (!has_next) break;
-        u = u2; item = item2; f = f2; len = len2; T = T2;
-        qa = qa2;
-        if (need_second) { __syncwarp(); qb = issue_half(item, f + 1); }
-        else qb = qb2;
+        if (same_item) {                                         // frame f+1 = halves (f+1, f+2) = slots (sb, sn)
+            sa = sb; sb = sn;
+            ++u; ++f;
+        } else {                                                 // new item: its first half sits in sn, fetch the second
+            u = u2; item = item2; f = f2; len = len2; T = T2;
+            const int freed = sa;                                // both old slots are free; take the older one
+            sa = sn; sb = freed;
+            __syncwarp();
+            issue_half(sb, item, f + 1);
+        }
     }
 }
 
