@@ -518,7 +518,7 @@ struct StoiPlan {
     int64_t batch, n, lmax, ystride;
     int t0max, mask_words, umax, ustride, mmax, ntiles, hops_max;
     bool resample, fused_energy;
-    size_t off_hops, off_y, off_energy, off_idx, off_count, off_mask, off_tob, off_partial, total;
+    size_t off_hops, off_y, off_energy, off_idx, off_count, off_prefix, off_mask, off_tob, off_partial, total;
 };
 
 StoiPlan stoi_plan(const fsem_stoi_ctx* ctx, int64_t batch, int64_t n) {
@@ -544,6 +544,7 @@ StoiPlan stoi_plan(const fsem_stoi_ctx* ctx, int64_t batch, int64_t n) {
     p.off_energy = off;  off = align256(off + sizeof(float) * batch * p.t0max);
     p.off_idx = off;     off = align256(off + sizeof(int32_t) * batch * p.t0max);
     p.off_count = off;   off = align256(off + sizeof(int32_t) * batch);
+    p.off_prefix = off;  off = align256(off + sizeof(int32_t) * (batch + 1));
     p.off_mask = off;    off = align256(off + sizeof(uint32_t) * batch * p.mask_words);
     p.off_tob = off;     off = align256(off + sizeof(float) * 2 * batch * FSEM_STOI_NBANDS * p.ustride);
     p.off_partial = off; off = align256(off + sizeof(float2) * batch * p.ntiles);
@@ -628,6 +629,8 @@ extern "C" int fsem_stoi_score_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t* in,
     if (!in->clean || !in->deg) return fail(FSEM_E_INVALID, "fsem_stoi_score_f32: null input");
     if (in->n >= (int64_t(1) << 30)) return fail(FSEM_E_INVALID, "fsem_stoi_score_f32: n too large");
     const StoiPlan p = stoi_plan(ctx, in->batch, in->n);
+    if (in->batch * (int64_t)p.t0max >= (int64_t(1) << 31))
+        return fail(FSEM_E_INVALID, "fsem_stoi_score_f32: batch x frames exceeds 2^31; split the batch");
     if (!workspace || workspace_bytes < p.total)
         return fail(FSEM_E_WORKSPACE, "fsem_stoi_score_f32: workspace %zu < %zu bytes", workspace_bytes, p.total);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
@@ -637,6 +640,7 @@ extern "C" int fsem_stoi_score_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t* in,
     float* energy = reinterpret_cast<float*>(ws + p.off_energy);
     int32_t* kept_idx = reinterpret_cast<int32_t*>(ws + p.off_idx);
     int32_t* kept_count = reinterpret_cast<int32_t*>(ws + p.off_count);
+    int32_t* frame_prefix = reinterpret_cast<int32_t*>(ws + p.off_prefix);
     uint32_t* mask = reinterpret_cast<uint32_t*>(ws + p.off_mask);
     float* tob = reinterpret_cast<float*>(ws + p.off_tob);
     float2* partial = reinterpret_cast<float2*>(ws + p.off_partial);
@@ -690,13 +694,16 @@ extern "C" int fsem_stoi_score_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t* in,
         FSEM_LAUNCHED();
     }
     if (p.umax > 0) {
-        const int64_t units = in->batch * (int64_t)p.umax;
+        { ProfScope prof_(K_STOI_COMPACT, stream);
+          stoi_prefix_kernel<<<1, 1024, 0, stream>>>(kept_count, in->batch, frame_prefix); }
+        FSEM_LAUNCHED();
+        const int64_t units = in->batch * (int64_t)p.umax;          // upper bound of the real frame count
         int64_t grid = ceil_div(units, kTobWarps);
         const int64_t cap = (int64_t)ctx->dev.sms * ctx->tob_ctas_per_sm;
         if (grid > cap) grid = cap;
         { ProfScope prof_(K_STOI_TOB, stream);
           stoi_tob_kernel<<<(unsigned)grid, kTobWarps * 32, 0, stream>>>(c10, d10, sstride, in->batch, p.t0max, p.umax,
-                                                                        p.ustride, kept_idx, kept_count, ctx->d_tab, tob); }
+                                                                      p.ustride, kept_idx, frame_prefix, ctx->d_tab, tob); }
         FSEM_LAUNCHED();
     }
     {

@@ -280,6 +280,48 @@ stoi_compact_kernel(const float* __restrict__ energy, const int32_t* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Exclusive prefix sum of the number of STFT frames per item, U_i = max(K_i - 2, 0): prefix[i] = sum_{j<i} U_j,
+// prefix[batch] = total.  One CTA; lets the tob kernel hand every warp an equal, contiguous share of REAL frames
+// (K is data dependent: about half of the [item, frame] slots are empty on speech).
+__global__ void __launch_bounds__(1024)
+stoi_prefix_kernel(const int32_t* __restrict__ kept_count, int64_t batch, int32_t* __restrict__ prefix) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < batch; base += 1024) {
+        const int64_t i = base + tid;
+        const int v = (i < batch) ? max(kept_count[i] - 2, 0) : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(kFull, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(kFull, w, o);
+                if (lane >= o) w += y;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        const int incl = carry + x + (warp > 0 ? s_warp[warp - 1] : 0);
+        if (i < batch) prefix[i] = incl - v;
+        __syncthreads();
+        if (tid == 1023) s_carry = incl;
+        __syncthreads();
+    }
+    if (tid == 0) prefix[batch] = s_carry;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Third-octave spectrogram of the silence-removed signals.  Persistent warps over (item, u).
 // STFT frame u of the reference = FFT512 of the 256-sample chunk
 //     c_u[q] = w[q] * ( f_{u+1}[q] + (q < 128 ? f_u[q + 128] : f_{u+2}[q - 128]) ),   f_j[q] = w[q] * x[128*t_j + q]
@@ -296,7 +338,7 @@ constexpr int kTobWarps = FSEM_FFT_WARPS;
 __global__ void __launch_bounds__(kTobWarps * 32, FSEM_FFT_MINBLOCKS)
 stoi_tob_kernel(const float* __restrict__ clean10k, const float* __restrict__ deg10k, int64_t sstride,
                 int64_t batch, int t0max, int umax,
-                int ustride, const int32_t* __restrict__ kept_idx, const int32_t* __restrict__ kept_count,
+                int ustride, const int32_t* __restrict__ kept_idx, const int32_t* __restrict__ frame_prefix,
                 const StoiTables* __restrict__ tab, float* __restrict__ tob /* [2][batch][15][ustride] */) {
     __shared__ __align__(16) float2 s_buf[kTobWarps][kFftBufElems];
     __shared__ int32_t s_starts[FSEM_STOI_NBANDS + 2];
@@ -319,18 +361,25 @@ stoi_tob_kernel(const float* __restrict__ clean10k, const float* __restrict__ de
     BandPlan plan;
     plan.init(s_starts, FSEM_STOI_NBANDS + 2, lane);
 
-    // units = flattened (item, STFT frame) slots, dealt round-robin to the warps (the number of real frames per
-    // item, K - 2, is data dependent, so contiguous ranges would be unbalanced); index maths stays incremental
+    // work = the REAL STFT frames of all items in (item, u) order; every warp takes an equal contiguous share
+    const int64_t total = frame_prefix[batch];
     const int64_t nwarps = (int64_t)gridDim.x * kTobWarps;
-    const int64_t wid = (int64_t)blockIdx.x * kTobWarps + warp;
-    const int64_t step_items = nwarps / umax;
-    const int step_u = (int)(nwarps - step_items * umax);
-    int64_t item = wid / umax;
-    int u = (int)(wid - item * umax);
-    for (; item < batch; item += step_items, u += step_u) {
-        if (u >= umax) { u -= umax; ++item; if (item >= batch) break; }
-        const int U = kept_count[item] - 2;
-        if (u < U) {
+    const int64_t per = (total + nwarps - 1) / nwarps;
+    const int64_t w0 = ((int64_t)blockIdx.x * kTobWarps + warp) * per;
+    const int64_t w1 = min(total, w0 + per);
+    if (w0 >= w1) return;
+    // item containing frame w0: largest i with prefix[i] <= w0 (binary search, once per warp)
+    int64_t lo_i = 0, hi_i = batch;
+    while (hi_i - lo_i > 1) {
+        const int64_t mid = (lo_i + hi_i) >> 1;
+        if (frame_prefix[mid] <= w0) lo_i = mid; else hi_i = mid;
+    }
+    int64_t item = lo_i;
+    int item_end = frame_prefix[item + 1];                  // first global frame index of the next item
+    int u = (int)(w0 - frame_prefix[item]);
+    for (int64_t w = w0; w < w1; ++w, ++u) {
+        while (w >= item_end) { ++item; item_end = frame_prefix[item + 1]; u = 0; }   // skips items without frames
+        {
             const int32_t* idx = kept_idx + item * t0max + u;
             const int ta = idx[0] * FSEM_STOI_HOP, tb = idx[1] * FSEM_STOI_HOP, tc = idx[2] * FSEM_STOI_HOP;
             const float* __restrict__ xc = clean10k + item * sstride + lane;
