@@ -105,7 +105,7 @@ struct HostPipe {
     size_t in_bytes = 0;
     void* ws = nullptr;
     size_t ws_bytes = 0;
-    void* out[2] = {nullptr, nullptr};    // scores of one chunk
+    void* out = nullptr;                  // device score columns for the WHOLE batch (one D2H at the end)
     size_t out_bytes = 0;
 
     int init() {
@@ -134,11 +134,9 @@ struct HostPipe {
             ws_bytes = ws_b;
         }
         if (out_b > out_bytes) {
-            for (int i = 0; i < 2; ++i) {
-                if (out[i]) cudaFree(out[i]);
-                out[i] = nullptr;
-                FSEM_CUDA(cudaMalloc(&out[i], out_b));
-            }
+            if (out) cudaFree(out);
+            out = nullptr;
+            FSEM_CUDA(cudaMalloc(&out, out_b));
             out_bytes = out_b;
         }
         return FSEM_OK;
@@ -146,11 +144,11 @@ struct HostPipe {
     void destroy() {
         for (int i = 0; i < 2; ++i) {
             if (in[i]) cudaFree(in[i]);
-            if (out[i]) cudaFree(out[i]);
             if (copied[i]) cudaEventDestroy(copied[i]);
             if (done[i]) cudaEventDestroy(done[i]);
         }
         if (ws) cudaFree(ws);
+        if (out) cudaFree(out);
         if (copy) cudaStreamDestroy(copy);
         if (compute) cudaStreamDestroy(compute);
     }
@@ -166,6 +164,15 @@ int64_t host_chunk_items(int64_t batch, int64_t n) {
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// host rows [cnt, n] (pitch `sstride` floats) -> device rows (pitch `dstride` floats); one flat copy when both are dense
+cudaError_t copy_rows_h2d(float* dst, int64_t dstride, const float* src, int64_t sstride, int64_t n, int64_t cnt,
+                          cudaStream_t stream) {
+    if (sstride == n && dstride == n)
+        return cudaMemcpyAsync(dst, src, sizeof(float) * n * cnt, cudaMemcpyHostToDevice, stream);
+    return cudaMemcpy2DAsync(dst, dstride * sizeof(float), src, sstride * sizeof(float), n * sizeof(float), cnt,
+                             cudaMemcpyHostToDevice, stream);
+}
 
 }  // namespace
 
@@ -461,8 +468,8 @@ extern "C" int fsem_pesq_score_host_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t
     const size_t sig_bytes = align256(sizeof(float) * per * dstride);
     const size_t in_bytes = 2 * sig_bytes + align256(sizeof(int32_t) * per);
     const size_t ws_bytes = fsem_pesq_workspace_bytes(ctx, per, n);
-    const size_t out_bytes = align256(sizeof(float) * per) + align256(sizeof(int32_t) * per);
-    rc = ctx->pipe.reserve(in_bytes, ws_bytes, out_bytes);
+    const size_t colb = align256(sizeof(float) * in->batch);
+    rc = ctx->pipe.reserve(in_bytes, ws_bytes, 2 * colb);
     if (rc != FSEM_OK) return rc;
     HostPipe& P = ctx->pipe;
     int64_t done_chunks = 0;
@@ -473,13 +480,11 @@ extern "C" int fsem_pesq_score_host_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t
         float* d_clean = reinterpret_cast<float*>(base);
         float* d_deg = reinterpret_cast<float*>(base + sig_bytes);
         int32_t* d_len = reinterpret_cast<int32_t*>(base + 2 * sig_bytes);
-        float* d_mos = reinterpret_cast<float*>(P.out[slot]);
-        int32_t* d_status = reinterpret_cast<int32_t*>(static_cast<char*>(P.out[slot]) + align256(sizeof(float) * per));
+        float* d_mos = reinterpret_cast<float*>(P.out) + i0;
+        int32_t* d_status = reinterpret_cast<int32_t*>(static_cast<char*>(P.out) + colb) + i0;
         if (done_chunks >= 2) FSEM_CUDA(cudaStreamWaitEvent(P.copy, P.done[slot], 0));   // staging slot free again
-        FSEM_CUDA(cudaMemcpy2DAsync(d_clean, dstride * sizeof(float), in->clean + i0 * in->stride,
-                                    in->stride * sizeof(float), n * sizeof(float), cnt, cudaMemcpyHostToDevice, P.copy));
-        FSEM_CUDA(cudaMemcpy2DAsync(d_deg, dstride * sizeof(float), in->deg + i0 * in->stride,
-                                    in->stride * sizeof(float), n * sizeof(float), cnt, cudaMemcpyHostToDevice, P.copy));
+        FSEM_CUDA(copy_rows_h2d(d_clean, dstride, in->clean + i0 * in->stride, in->stride, n, cnt, P.copy));
+        FSEM_CUDA(copy_rows_h2d(d_deg, dstride, in->deg + i0 * in->stride, in->stride, n, cnt, P.copy));
         if (in->lengths)
             FSEM_CUDA(cudaMemcpyAsync(d_len, in->lengths + i0, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, P.copy));
         FSEM_CUDA(cudaEventRecord(P.copied[slot], P.copy));
@@ -487,11 +492,13 @@ extern "C" int fsem_pesq_score_host_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t
         fsem_batch_t dev{d_clean, d_deg, in->lengths ? d_len : nullptr, cnt, n, dstride};
         rc = fsem_pesq_score_f32(ctx, &dev, d_mos, d_status, P.ws, P.ws_bytes, P.compute);
         if (rc != FSEM_OK) { cudaStreamSynchronize(P.copy); cudaStreamSynchronize(P.compute); return rc; }
-        FSEM_CUDA(cudaMemcpyAsync(mos_out + i0, d_mos, sizeof(float) * cnt, cudaMemcpyDeviceToHost, P.compute));
-        if (status_out)
-            FSEM_CUDA(cudaMemcpyAsync(status_out + i0, d_status, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, P.compute));
         FSEM_CUDA(cudaEventRecord(P.done[slot], P.compute));
     }
+    // one read-back of the score columns (a per-chunk copy into pageable memory would stall the pipeline)
+    FSEM_CUDA(cudaMemcpyAsync(mos_out, P.out, sizeof(float) * in->batch, cudaMemcpyDeviceToHost, P.compute));
+    if (status_out)
+        FSEM_CUDA(cudaMemcpyAsync(status_out, static_cast<char*>(P.out) + colb, sizeof(int32_t) * in->batch,
+                                  cudaMemcpyDeviceToHost, P.compute));
     FSEM_CUDA(cudaStreamSynchronize(P.copy));
     FSEM_CUDA(cudaStreamSynchronize(P.compute));
     return FSEM_OK;
@@ -756,9 +763,8 @@ extern "C" int fsem_stoi_score_host_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t
     const size_t sig_bytes = align256(sizeof(float) * per * dstride);
     const size_t in_bytes = 2 * sig_bytes + align256(sizeof(int32_t) * per);
     const size_t ws_bytes = fsem_stoi_workspace_bytes(ctx, per, n);
-    const size_t col = align256(sizeof(float) * per);
-    const size_t out_bytes = 4 * col;
-    rc = ctx->pipe.reserve(in_bytes, ws_bytes, out_bytes);
+    const size_t col = align256(sizeof(float) * in->batch);
+    rc = ctx->pipe.reserve(in_bytes, ws_bytes, 4 * col);
     if (rc != FSEM_OK) return rc;
     HostPipe& P = ctx->pipe;
     int64_t done_chunks = 0;
@@ -769,16 +775,14 @@ extern "C" int fsem_stoi_score_host_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t
         float* d_clean = reinterpret_cast<float*>(base);
         float* d_deg = reinterpret_cast<float*>(base + sig_bytes);
         int32_t* d_len = reinterpret_cast<int32_t*>(base + 2 * sig_bytes);
-        char* ob = static_cast<char*>(P.out[slot]);
-        float* d_stoi = reinterpret_cast<float*>(ob);
-        float* d_estoi = reinterpret_cast<float*>(ob + col);
-        int32_t* d_kept = reinterpret_cast<int32_t*>(ob + 2 * col);
-        int32_t* d_status = reinterpret_cast<int32_t*>(ob + 3 * col);
+        char* ob = static_cast<char*>(P.out);
+        float* d_stoi = reinterpret_cast<float*>(ob) + i0;
+        float* d_estoi = reinterpret_cast<float*>(ob + col) + i0;
+        int32_t* d_kept = reinterpret_cast<int32_t*>(ob + 2 * col) + i0;
+        int32_t* d_status = reinterpret_cast<int32_t*>(ob + 3 * col) + i0;
         if (done_chunks >= 2) FSEM_CUDA(cudaStreamWaitEvent(P.copy, P.done[slot], 0));
-        FSEM_CUDA(cudaMemcpy2DAsync(d_clean, dstride * sizeof(float), in->clean + i0 * in->stride,
-                                    in->stride * sizeof(float), n * sizeof(float), cnt, cudaMemcpyHostToDevice, P.copy));
-        FSEM_CUDA(cudaMemcpy2DAsync(d_deg, dstride * sizeof(float), in->deg + i0 * in->stride,
-                                    in->stride * sizeof(float), n * sizeof(float), cnt, cudaMemcpyHostToDevice, P.copy));
+        FSEM_CUDA(copy_rows_h2d(d_clean, dstride, in->clean + i0 * in->stride, in->stride, n, cnt, P.copy));
+        FSEM_CUDA(copy_rows_h2d(d_deg, dstride, in->deg + i0 * in->stride, in->stride, n, cnt, P.copy));
         if (in->lengths)
             FSEM_CUDA(cudaMemcpyAsync(d_len, in->lengths + i0, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, P.copy));
         FSEM_CUDA(cudaEventRecord(P.copied[slot], P.copy));
@@ -786,13 +790,15 @@ extern "C" int fsem_stoi_score_host_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t
         fsem_batch_t dev{d_clean, d_deg, in->lengths ? d_len : nullptr, cnt, n, dstride};
         rc = fsem_stoi_score_f32(ctx, &dev, d_stoi, d_estoi, d_kept, d_status, P.ws, P.ws_bytes, P.compute);
         if (rc != FSEM_OK) { cudaStreamSynchronize(P.copy); cudaStreamSynchronize(P.compute); return rc; }
-        FSEM_CUDA(cudaMemcpyAsync(stoi_out + i0, d_stoi, sizeof(float) * cnt, cudaMemcpyDeviceToHost, P.compute));
-        FSEM_CUDA(cudaMemcpyAsync(estoi_out + i0, d_estoi, sizeof(float) * cnt, cudaMemcpyDeviceToHost, P.compute));
-        if (kept_frames_out)
-            FSEM_CUDA(cudaMemcpyAsync(kept_frames_out + i0, d_kept, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, P.compute));
-        if (status_out)
-            FSEM_CUDA(cudaMemcpyAsync(status_out + i0, d_status, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, P.compute));
         FSEM_CUDA(cudaEventRecord(P.done[slot], P.compute));
+    }
+    {
+        char* ob = static_cast<char*>(P.out);
+        const size_t nb = sizeof(float) * in->batch;
+        FSEM_CUDA(cudaMemcpyAsync(stoi_out, ob, nb, cudaMemcpyDeviceToHost, P.compute));
+        FSEM_CUDA(cudaMemcpyAsync(estoi_out, ob + col, nb, cudaMemcpyDeviceToHost, P.compute));
+        if (kept_frames_out) FSEM_CUDA(cudaMemcpyAsync(kept_frames_out, ob + 2 * col, nb, cudaMemcpyDeviceToHost, P.compute));
+        if (status_out) FSEM_CUDA(cudaMemcpyAsync(status_out, ob + 3 * col, nb, cudaMemcpyDeviceToHost, P.compute));
     }
     FSEM_CUDA(cudaStreamSynchronize(P.copy));
     FSEM_CUDA(cudaStreamSynchronize(P.compute));
@@ -823,7 +829,7 @@ extern "C" int fsem_pesq_stoi_score_host_f32(fsem_pesq_ctx_t* pctx, fsem_stoi_ct
     const size_t in_bytes = 2 * sig_bytes + align256(sizeof(int32_t) * per);
     const size_t ws_pesq = align256(fsem_pesq_workspace_bytes(pctx, per, n));
     const size_t ws_stoi = align256(fsem_stoi_workspace_bytes(sctx, per, n));
-    const size_t col = align256(sizeof(float) * per);
+    const size_t col = align256(sizeof(float) * in->batch);
     rc = pctx->pipe.reserve(in_bytes, ws_pesq + ws_stoi, 6 * col);
     if (rc != FSEM_OK) return rc;
     HostPipe& P = pctx->pipe;
@@ -835,18 +841,16 @@ extern "C" int fsem_pesq_stoi_score_host_f32(fsem_pesq_ctx_t* pctx, fsem_stoi_ct
         float* d_clean = reinterpret_cast<float*>(base);
         float* d_deg = reinterpret_cast<float*>(base + sig_bytes);
         int32_t* d_len = reinterpret_cast<int32_t*>(base + 2 * sig_bytes);
-        char* ob = static_cast<char*>(P.out[slot]);
-        float* d_mos = reinterpret_cast<float*>(ob);
-        int32_t* d_pst = reinterpret_cast<int32_t*>(ob + col);
-        float* d_stoi = reinterpret_cast<float*>(ob + 2 * col);
-        float* d_estoi = reinterpret_cast<float*>(ob + 3 * col);
-        int32_t* d_kept = reinterpret_cast<int32_t*>(ob + 4 * col);
-        int32_t* d_sst = reinterpret_cast<int32_t*>(ob + 5 * col);
+        char* ob = static_cast<char*>(P.out);
+        float* d_mos = reinterpret_cast<float*>(ob) + i0;
+        int32_t* d_pst = reinterpret_cast<int32_t*>(ob + col) + i0;
+        float* d_stoi = reinterpret_cast<float*>(ob + 2 * col) + i0;
+        float* d_estoi = reinterpret_cast<float*>(ob + 3 * col) + i0;
+        int32_t* d_kept = reinterpret_cast<int32_t*>(ob + 4 * col) + i0;
+        int32_t* d_sst = reinterpret_cast<int32_t*>(ob + 5 * col) + i0;
         if (done_chunks >= 2) FSEM_CUDA(cudaStreamWaitEvent(P.copy, P.done[slot], 0));
-        FSEM_CUDA(cudaMemcpy2DAsync(d_clean, dstride * sizeof(float), in->clean + i0 * in->stride,
-                                    in->stride * sizeof(float), n * sizeof(float), cnt, cudaMemcpyHostToDevice, P.copy));
-        FSEM_CUDA(cudaMemcpy2DAsync(d_deg, dstride * sizeof(float), in->deg + i0 * in->stride,
-                                    in->stride * sizeof(float), n * sizeof(float), cnt, cudaMemcpyHostToDevice, P.copy));
+        FSEM_CUDA(copy_rows_h2d(d_clean, dstride, in->clean + i0 * in->stride, in->stride, n, cnt, P.copy));
+        FSEM_CUDA(copy_rows_h2d(d_deg, dstride, in->deg + i0 * in->stride, in->stride, n, cnt, P.copy));
         if (in->lengths)
             FSEM_CUDA(cudaMemcpyAsync(d_len, in->lengths + i0, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, P.copy));
         FSEM_CUDA(cudaEventRecord(P.copied[slot], P.copy));
@@ -857,16 +861,17 @@ extern "C" int fsem_pesq_stoi_score_host_f32(fsem_pesq_ctx_t* pctx, fsem_stoi_ct
             rc = fsem_stoi_score_f32(sctx, &dev, d_stoi, d_estoi, d_kept, d_sst, static_cast<char*>(P.ws) + ws_pesq,
                                      ws_stoi, P.compute);
         if (rc != FSEM_OK) { cudaStreamSynchronize(P.copy); cudaStreamSynchronize(P.compute); return rc; }
-        FSEM_CUDA(cudaMemcpyAsync(mos_out + i0, d_mos, sizeof(float) * cnt, cudaMemcpyDeviceToHost, P.compute));
-        FSEM_CUDA(cudaMemcpyAsync(stoi_out + i0, d_stoi, sizeof(float) * cnt, cudaMemcpyDeviceToHost, P.compute));
-        FSEM_CUDA(cudaMemcpyAsync(estoi_out + i0, d_estoi, sizeof(float) * cnt, cudaMemcpyDeviceToHost, P.compute));
-        if (pesq_status_out)
-            FSEM_CUDA(cudaMemcpyAsync(pesq_status_out + i0, d_pst, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, P.compute));
-        if (kept_frames_out)
-            FSEM_CUDA(cudaMemcpyAsync(kept_frames_out + i0, d_kept, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, P.compute));
-        if (stoi_status_out)
-            FSEM_CUDA(cudaMemcpyAsync(stoi_status_out + i0, d_sst, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, P.compute));
         FSEM_CUDA(cudaEventRecord(P.done[slot], P.compute));
+    }
+    {
+        char* ob = static_cast<char*>(P.out);
+        const size_t nb = sizeof(float) * in->batch;
+        FSEM_CUDA(cudaMemcpyAsync(mos_out, ob, nb, cudaMemcpyDeviceToHost, P.compute));
+        if (pesq_status_out) FSEM_CUDA(cudaMemcpyAsync(pesq_status_out, ob + col, nb, cudaMemcpyDeviceToHost, P.compute));
+        FSEM_CUDA(cudaMemcpyAsync(stoi_out, ob + 2 * col, nb, cudaMemcpyDeviceToHost, P.compute));
+        FSEM_CUDA(cudaMemcpyAsync(estoi_out, ob + 3 * col, nb, cudaMemcpyDeviceToHost, P.compute));
+        if (kept_frames_out) FSEM_CUDA(cudaMemcpyAsync(kept_frames_out, ob + 4 * col, nb, cudaMemcpyDeviceToHost, P.compute));
+        if (stoi_status_out) FSEM_CUDA(cudaMemcpyAsync(stoi_status_out, ob + 5 * col, nb, cudaMemcpyDeviceToHost, P.compute));
     }
     FSEM_CUDA(cudaStreamSynchronize(P.copy));
     FSEM_CUDA(cudaStreamSynchronize(P.compute));
