@@ -199,7 +199,7 @@ def run_reference(args):
         return 0
     cores = host_cores()
     n = int(args.seconds * FS)
-    items = max(4 * cores, 64)
+    items = max(8 * cores, 64)
     pool = CpuOraclePool(n, items, cores)
     times = []
     for step in range(args.warmup + args.steps):
@@ -232,7 +232,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=8192, help="total items over all ranks")
@@ -414,7 +414,7 @@ def main():
     cpu = None
     if not args.no_cpu and world == 1:
         cores = host_cores()
-        cpu = cpu_baseline(n, max(64, 4 * cores), cores)
+        cpu = cpu_baseline(n, max(64, 32 * cores), cores)      # ~20-30 CPU-seconds of scoring
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
