@@ -349,3 +349,21 @@ def test_large_batch_sample_against_oracle(pesq, stoi_metrics):
     assert _maxdiff(np.array([res[i]["STOI"] for i in pick]), ws) <= 1e-4
     assert _maxdiff(np.array([res[i]["ESTOI"] for i in pick]), we) <= 1e-4
     assert np.array_equal(st.last_kept_frames.numpy()[pick], wk)
+
+
+def test_readme_example_anchors(pesq, stoi_metrics):
+    """The reference's README example (4 x 10 s of torch.randn, README.md:20-34) scored by the reference's CPU path
+    in the survey container (SURVEY.md 8c "smoke anchors"; torch 2.11 CPU generator, seed 0)."""
+    torch.manual_seed(0)
+    clean = torch.randn(4, 160000)
+    noisy = torch.randn(4, 160000)
+    noisy2 = clean + 0.3 * torch.randn(4, 160000)
+    got = np.array([r["PESQ"] for r in pesq(clean, noisy)])
+    assert np.max(np.abs(got - np.array([1.55451312, 1.53621908, 1.57332395, 1.54720455]))) <= 1e-3
+    res = stoi_metrics(16000)(clean, noisy)
+    assert np.max(np.abs(np.array([r["STOI"] for r in res]) - np.array([0.00901818, -0.00190712, -0.00193275, 0.01228937]))) <= 1e-4
+    assert np.max(np.abs(np.array([r["ESTOI"] for r in res]) - np.array([0.00474734, -0.00370289, -0.00057269, 0.00886550]))) <= 1e-4
+    got2 = np.array([r["PESQ"] for r in pesq(clean, noisy2)])
+    assert np.max(np.abs(got2 - np.array([4.134, 4.112, 4.155, 4.136]))) <= 2e-3      # anchors quoted to 3 decimals
+    res2 = stoi_metrics(16000)(clean, noisy2)
+    assert np.max(np.abs(np.array([r["STOI"] for r in res2]) - np.array([0.9096, 0.9114, 0.9098, 0.9123]))) <= 2e-4
