@@ -604,15 +604,8 @@ extern "C" int fsem_stoi_create(fsem_stoi_ctx_t** out, const fsem_stoi_design_t*
                 if ((j < rs85_lo(p) || j > rs85_hi(p)) && d->taps[p * 28 + j] != 0.f) ctx->fast85 = false;
             }
     }
-    e = cudaFuncSetAttribute(stoi_tob_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTobDynSmem);
-    if (e != cudaSuccess) {
-        if (ctx->d_tab) cudaFree(ctx->d_tab);
-        if (ctx->d_taps) cudaFree(ctx->d_taps);
-        delete ctx;
-        return fail(FSEM_E_CUDA, "fsem_stoi_create: %s", cudaGetErrorString(e));
-    }
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stoi_tob_ring_kernel, kTobWarps * 32, kTobDynSmem) == cudaSuccess && occ > 0)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stoi_tob_kernel, kTobWarps * 32, 0) == cudaSuccess && occ > 0)
         ctx->tob_ctas_per_sm = occ;
     *out = ctx;
     return FSEM_OK;
@@ -715,14 +708,9 @@ extern "C" int fsem_stoi_score_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t* in,
         int64_t grid = ceil_div(units, kTobWarps);
         const int64_t cap = (int64_t)ctx->dev.sms * ctx->tob_ctas_per_sm;
         if (grid > cap) grid = cap;
-        const bool ring = aligned16(c10) && aligned16(d10) && (sstride % 4 == 0);     // TMA needs 16-byte aligned rows
         { ProfScope prof_(K_STOI_TOB, stream);
-          if (ring)
-              stoi_tob_ring_kernel<<<(unsigned)grid, kTobWarps * 32, kTobDynSmem, stream>>>(
-                  c10, d10, sstride, in->batch, p.t0max, p.umax, p.ustride, kept_idx, frame_prefix, ctx->d_tab, tob);
-          else
-              stoi_tob_kernel<<<(unsigned)grid, kTobWarps * 32, 0, stream>>>(
-                  c10, d10, sstride, in->batch, p.t0max, p.umax, p.ustride, kept_idx, frame_prefix, ctx->d_tab, tob); }
+          stoi_tob_kernel<<<(unsigned)grid, kTobWarps * 32, 0, stream>>>(c10, d10, sstride, in->batch, p.t0max, p.umax,
+                                                                      p.ustride, kept_idx, frame_prefix, ctx->d_tab, tob); }
         FSEM_LAUNCHED();
     }
     {

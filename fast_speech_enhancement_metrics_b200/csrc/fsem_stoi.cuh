@@ -418,137 +418,6 @@ stoi_tob_kernel(const float* __restrict__ clean10k, const float* __restrict__ de
 }
 
 // ------------------------------------------------------------------------------------------------
-// TMA-staged variant of the tob kernel (16-byte aligned 10 kHz rows): every kept frame (256 samples of the clean
-// and of the degraded signal) is fetched ONCE by a bulk copy into a 4-slot per-warp ring -- STFT frame u needs kept
-// frames u, u+1, u+2 and kept frame u+3 is in flight while frame u is transformed.  The gather of the
-// silence-removed signal therefore never touches the L1/LSU load path and the global-load latency is hidden.
-struct TobWarpSmem {
-    float2 fft[kFftBufElems];                  // 5120 B
-    float frame_c[4][FSEM_STOI_WIN];           // 4096 B
-    float frame_d[4][FSEM_STOI_WIN];           // 4096 B
-    float bands[64];                           //  256 B
-    unsigned long long bar[4];                 //   32 B
-};
-constexpr size_t kTobDynSmem = sizeof(TobWarpSmem) * kTobWarps;
-static_assert(sizeof(TobWarpSmem) % 16 == 0, "per-warp shared block must keep 16-byte alignment");
-
-__global__ void __launch_bounds__(kTobWarps * 32, FSEM_FFT_MINBLOCKS)
-stoi_tob_ring_kernel(const float* __restrict__ clean10k, const float* __restrict__ deg10k, int64_t sstride,
-                     int64_t batch, int t0max, int umax, int ustride, const int32_t* __restrict__ kept_idx,
-                     const int32_t* __restrict__ frame_prefix, const StoiTables* __restrict__ tab,
-                     float* __restrict__ tob /* [2][batch][15][ustride] */) {
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    __shared__ int32_t s_starts[FSEM_STOI_NBANDS + 2];
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    TobWarpSmem& sm = reinterpret_cast<TobWarpSmem*>(s_raw)[warp];
-    float2* buf = sm.fft;
-    float* bands = sm.bands;
-    if (threadIdx.x == 0) s_starts[0] = 0;
-    if (threadIdx.x < FSEM_STOI_NBANDS) s_starts[1 + threadIdx.x] = tab->band_lo[threadIdx.x];
-    if (threadIdx.x == FSEM_STOI_NBANDS) s_starts[FSEM_STOI_NBANDS + 1] = tab->band_hi[FSEM_STOI_NBANDS - 1];
-    const uint32_t bar0 = smem_u32(&sm.bar[0]);
-    const uint32_t fc0 = smem_u32(&sm.frame_c[0][0]), fd0 = smem_u32(&sm.frame_d[0][0]);
-    constexpr uint32_t kFrameBytes = FSEM_STOI_WIN * sizeof(float);
-    if (lane == 0) {
-        for (int i = 0; i < 4; ++i) mbar_init(bar0 + 8 * i, 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    FftTwiddles tw;
-    tw.init(lane);
-    float win[8];
-#pragma unroll
-    for (int m = 0; m < 8; ++m) win[m] = tab->window[lane + 32 * m];
-    BandPlan plan;
-    plan.init(s_starts, FSEM_STOI_NBANDS + 2, lane);
-
-    const int64_t total = frame_prefix[batch];
-    const int64_t nwarps = (int64_t)gridDim.x * kTobWarps;
-    const int64_t per = (total + nwarps - 1) / nwarps;
-    const int64_t w0 = ((int64_t)blockIdx.x * kTobWarps + warp) * per;
-    const int64_t w1 = min(total, w0 + per);
-    if (w0 >= w1) return;
-    int64_t lo_i = 0, hi_i = batch;
-    while (hi_i - lo_i > 1) {
-        const int64_t mid = (lo_i + hi_i) >> 1;
-        if (frame_prefix[mid] <= w0) lo_i = mid; else hi_i = mid;
-    }
-    int64_t item = lo_i;
-    int item_end = frame_prefix[item + 1];
-    int u = (int)(w0 - frame_prefix[item]);
-
-    unsigned par = 15u;     // bit s: mbarrier phase parity the latest copy into ring slot s completes
-    auto issue_kept = [&](int64_t it, int j) {          // kept frame j of item `it` -> slot j & 3
-        const int slot = j & 3;
-        par ^= 1u << slot;
-        if (lane == 0) {
-            const int64_t off = it * sstride + (int64_t)kept_idx[it * t0max + j] * FSEM_STOI_HOP;
-            fence_proxy_async();
-            mbar_arrive_expect_tx(bar0 + 8 * slot, 2 * kFrameBytes);
-            bulk_copy_g2s(fc0 + slot * kFrameBytes, clean10k + off, kFrameBytes, bar0 + 8 * slot);
-            bulk_copy_g2s(fd0 + slot * kFrameBytes, deg10k + off, kFrameBytes, bar0 + 8 * slot);
-        }
-    };
-    issue_kept(item, u);
-    issue_kept(item, u + 1);
-    issue_kept(item, u + 2);
-
-    for (int64_t w = w0; w < w1; ++w) {
-        const bool more = w + 1 < w1;
-        const bool same_item = more && (w + 1 < item_end);
-        __syncwarp();                                    // the slot refilled below was last read one frame ago
-        if (same_item) issue_kept(item, u + 3);
-        const int sa = u & 3, sb = (u + 1) & 3, sc = (u + 2) & 3;
-        mbar_wait(bar0 + 8 * sa, (par >> sa) & 1u);
-        mbar_wait(bar0 + 8 * sb, (par >> sb) & 1u);
-        mbar_wait(bar0 + 8 * sc, (par >> sc) & 1u);
-        const float* ac = sm.frame_c[sa] + lane; const float* ad = sm.frame_d[sa] + lane;
-        const float* bc = sm.frame_c[sb] + lane; const float* bd = sm.frame_d[sb] + lane;
-        const float* cc = sm.frame_c[sc] + lane; const float* cd = sm.frame_d[sc] + lane;
-        float re[16], im[16];
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const int q = 32 * m;
-            // first half of the chunk overlaps the tail of kept frame u, second half the head of kept frame u+2
-            const float nc = (m < 4) ? ac[q + 128] : cc[q - 128];
-            const float nd = (m < 4) ? ad[q + 128] : cd[q - 128];
-            const float wn = (m < 4) ? win[m + 4] : win[m - 4];
-            float c = __fadd_rn(__fmul_rn(win[m], bc[q]), __fmul_rn(wn, nc));
-            float d = __fadd_rn(__fmul_rn(win[m], bd[q]), __fmul_rn(wn, nd));
-            re[m] = __fmul_rn(win[m], c);
-            im[m] = __fmul_rn(win[m], d);
-        }
-#pragma unroll
-        for (int m = 8; m < 16; ++m) { re[m] = 0.f; im[m] = 0.f; }
-        warp_fft512<true>(re, im, buf, tw, lane);
-        float pc[8], pd[8];
-        packed_power8(buf, lane, pc, pd);
-        band_sums8<6>(pc, pd, plan, lane, [&](int pseudo, float sc_, float sd_) {
-            bands[pseudo] = sc_;
-            bands[32 + pseudo] = sd_;
-        });
-        __syncwarp();
-        if ((lane & 15) < FSEM_STOI_NBANDS) {
-            const int64_t sig = (lane >> 4) ? (batch + item) : item;
-            tob[(sig * FSEM_STOI_NBANDS + (lane & 15)) * (int64_t)ustride + u] =
-                sqrtf(bands[(lane & 16) * 2 + (lane & 15) + 1]);     // STOI.py:123-125
-        }
-        if (same_item) {
-            ++u;
-        } else if (more) {                               // next item that has frames: restart the ring
-            do { ++item; item_end = frame_prefix[item + 1]; } while (w + 1 >= item_end);
-            u = 0;
-            __syncwarp();
-            issue_kept(item, 0);
-            issue_kept(item, 1);
-            issue_kept(item, 2);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // Segment kernel: CTA = (item, tile of kSegTile consecutive segments).
 constexpr int kSegTile = 64;
 constexpr int kSegThreads = 256;
