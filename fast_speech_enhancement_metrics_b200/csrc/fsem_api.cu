@@ -206,6 +206,7 @@ struct fsem_pesq_ctx {
     int rs_orig = 1, rs_neu = 1, rs_width = 0, rs_ntaps = 0;   // resample-on-ingest to 16 kHz (base.py:19-20)
     float* d_rs_taps = nullptr;
     int spec_ctas_per_sm = 2;
+    int filt_ctas_per_sm = 4;
     HostPipe pipe;
 };
 
@@ -230,15 +231,22 @@ PesqPlan pesq_plan(const fsem_pesq_ctx* ctx, int64_t batch, int64_t n_in) {
     p.zstride = round_up(n > 0 ? n : 1, 4);
     p.tmax = pesq_num_frames(n);
     if (p.tmax < 1) p.tmax = 1;
-    // chunking of the serial IIR pass: enough (signal, chunk) threads to fill the chip, chunks as
-    // long as possible (the warm-up prefix is redundant work), multiples of 64 samples
-    const int64_t target_threads = (int64_t)ctx->dev.sms * 768;
-    int64_t nch = ceil_div(target_threads, 2 * (batch > 0 ? batch : 1));
-    const int64_t max_ch = ceil_div(n > 0 ? n : 1, 1024);
-    if (nch > max_ch) nch = max_ch;
-    if (nch < 1) nch = 1;
-    int64_t chunk = round_up(ceil_div(n > 0 ? n : 1, nch), 64);
-    nch = ceil_div(n > 0 ? n : 1, chunk);
+    // Chunking of the serial IIR pass.  A warp-unit = (32 signals, one chunk) and costs chunk + warm-up sample steps;
+    // all units are equal, so the kernel runs in whole "waves" of resident warps.  Pick the chunk count that minimises
+    // waves x (chunk + warm-up): enough units to fill the chip, no half-empty last wave, little redundant warm-up.
+    const int64_t nn = n > 0 ? n : 1;
+    const int64_t groups = 2 * ceil_div(batch > 0 ? batch : 1, 32);
+    const int64_t slots = (int64_t)ctx->dev.sms * ctx->filt_ctas_per_sm * kFiltWarps;
+    const int64_t max_ch = ceil_div(nn, 1024) < 512 ? ceil_div(nn, 1024) : 512;
+    int64_t nch = 1, chunk = round_up(nn, 64);
+    double best = 1e300;
+    for (int64_t c = 1; c <= max_ch; ++c) {
+        const int64_t ch = round_up(ceil_div(nn, c), 64);
+        const int64_t cc = ceil_div(nn, ch);
+        const int64_t waves = ceil_div(groups * cc, slots);
+        const double cost = (double)waves * (double)(ch + (cc > 1 ? ctx->warm : 0));
+        if (cost < best * 0.999) { best = cost; nch = cc; chunk = ch; }
+    }
     p.chunk = (int)chunk;
     p.nchunks = (int)nch;
     size_t off = 0;
@@ -330,6 +338,9 @@ extern "C" int fsem_pesq_create(fsem_pesq_ctx_t** out, const fsem_pesq_design_t*
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pesq_spectrum_kernel, kSpecWarps * 32, kSpecDynSmem) == cudaSuccess && occ > 0)
         ctx->spec_ctas_per_sm = occ;
+    occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pesq_filter_tiled_kernel<false>, kFiltWarps * 32, 0) == cudaSuccess && occ > 0)
+        ctx->filt_ctas_per_sm = occ;
     *out = ctx;
     return FSEM_OK;
 }
