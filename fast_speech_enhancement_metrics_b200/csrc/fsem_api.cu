@@ -338,15 +338,8 @@ extern "C" int fsem_pesq_create(fsem_pesq_ctx_t** out, const fsem_pesq_design_t*
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pesq_spectrum_kernel, kSpecWarps * 32, kSpecDynSmem) == cudaSuccess && occ > 0)
         ctx->spec_ctas_per_sm = occ;
-    e = cudaFuncSetAttribute(pesq_filter_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFiltTmaSmem);
-    if (e != cudaSuccess) {
-        cudaFree(ctx->d_tab);
-        if (ctx->d_rs_taps) cudaFree(ctx->d_rs_taps);
-        delete ctx;
-        return fail(FSEM_E_CUDA, "fsem_pesq_create: %s", cudaGetErrorString(e));
-    }
     occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pesq_filter_tma_kernel, kFiltWarps * 32, kFiltTmaSmem) == cudaSuccess && occ > 0)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pesq_filter_tiled_kernel<false>, kFiltWarps * 32, 0) == cudaSuccess && occ > 0)
         ctx->filt_ctas_per_sm = occ;
     *out = ctx;
     return FSEM_OK;
@@ -422,9 +415,9 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
                       in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, p.chunk, p.nchunks, ctx->warm,
                       ctx->coef, z, p.zstride, partial);
               else
-                  pesq_filter_tma_kernel<<<grid, kFiltWarps * 32, kFiltTmaSmem, stream>>>(
-                      in->clean, in->deg, in->batch, in->n, in->stride, p.chunk, p.nchunks, ctx->warm, ctx->coef, z,
-                      p.zstride, partial); }
+                  pesq_filter_tiled_kernel<false><<<grid, kFiltWarps * 32, 0, stream>>>(
+                      in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, p.chunk, p.nchunks, ctx->warm,
+                      ctx->coef, z, p.zstride, partial); }
         } else {
             const int64_t threads = 2 * in->batch * p.nchunks;
             { ProfScope prof_(K_PESQ_FILTER, stream);

@@ -315,155 +315,6 @@ pesq_filter_tiled_kernel(const float* __restrict__ clean, const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// Kernel A, TMA-staged variant (all rows have n samples and are 16-byte aligned).  Same decomposition as the tiled
-// kernel (warp = 32 signals x one chunk, lane = signal), but the input tiles are fetched by bulk copies
-// (cp.async.bulk + mbarrier): every lane copies the next 128 bytes of ITS OWN signal into its row of a 3-slot ring,
-// two tiles ahead of the one being filtered.  No registers are spent on prefetching and 2-3x more bytes are in
-// flight per warp than with the register prefetch, which is what the HBM-latency-bound tiled kernel lacked
-// (ncu: long-scoreboard 2.9 warps per issue).  z is filtered in place in the ring slot and drained with coalesced
-// stores; the slot is refilled right after its drain.
-constexpr int kFiltRing = 3;
-struct FiltWarpSmem {
-    float tile[kFiltRing][32 * kFiltPitch];     // 3 x 4608 B
-    unsigned long long bar[kFiltRing];
-    unsigned long long pad_;
-};
-constexpr size_t kFiltTmaSmem = sizeof(FiltWarpSmem) * kFiltWarps;
-static_assert(sizeof(FiltWarpSmem) % 16 == 0, "per-warp shared block must keep 16-byte alignment");
-
-__global__ void __launch_bounds__(kFiltWarps * 32)
-pesq_filter_tma_kernel(const float* __restrict__ clean, const float* __restrict__ deg, int64_t batch, int64_t n,
-                       int64_t stride, int chunk, int nchunks, int warm, const __grid_constant__ PesqFilterCoef P,
-                       float* __restrict__ z_out, int64_t zstride, double* __restrict__ partial) {
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    FiltWarpSmem& sm = reinterpret_cast<FiltWarpSmem*>(s_raw)[warp];
-    const int64_t groups = ceil_div(batch, 32);
-    const int64_t unit = (int64_t)blockIdx.x * kFiltWarps + warp;
-    if (unit >= 2 * groups * nchunks) return;
-    const int half = (int)(unit / (groups * nchunks));
-    const int64_t rem = unit - (int64_t)half * groups * nchunks;
-    const int64_t grp = rem / nchunks;
-    const int c = (int)(rem - grp * nchunks);
-    const int64_t row0 = grp * 32;
-    const int64_t my_item = row0 + lane;
-    const bool sig_ok = my_item < batch;
-    const int len = (int)n;
-    const float* __restrict__ my_src = (half ? deg : clean) + (sig_ok ? my_item : 0) * stride;
-    // transfer role of the drain: rows (lane >> 3) + 4*i, float4 column lane & 7
-    const int col = (lane & 7) * 4;
-    const int64_t trow = row0 + (lane >> 3);
-    float* __restrict__ dst0 = z_out + ((int64_t)half * batch + trow) * zstride + col;
-    const int64_t dstep = 4 * zstride;
-    const int rows_ok = (int)min((int64_t)8, (batch - trow + 3) / 4);
-    const uint32_t rows_valid = (uint32_t)min((int64_t)32, batch - row0);
-
-    const uint32_t bar0 = smem_u32(&sm.bar[0]);
-    const uint32_t tile0 = smem_u32(&sm.tile[0][0]);
-    constexpr uint32_t kSlotBytes = 32 * kFiltPitch * sizeof(float);
-    constexpr uint32_t kRowBytes = 32 * sizeof(float);
-    if (lane == 0) {
-        for (int i = 0; i < kFiltRing; ++i) mbar_init(bar0 + 8 * i, 1);
-        mbar_fence_init();
-    }
-    __syncwarp();
-
-    const int t_acc = c * chunk;
-    const int t_stop = min(len, t_acc + chunk);
-    const int t_begin = max(0, t_acc - warm);                // multiple of 32
-    const int ntiles = (t_stop - t_begin + 31) / 32;
-    unsigned par = (1u << kFiltRing) - 1u;
-    auto tile_is_full = [&](int i) { return t_begin + 32 * i + 32 <= len; };
-    auto issue_tile = [&](int i) {                           // bulk-copy tile i (must be full) into slot i % kFiltRing
-        const int slot = i % kFiltRing;
-        par ^= 1u << slot;
-        fence_proxy_async();
-        if (lane == 0) mbar_arrive_expect_tx(bar0 + 8 * slot, rows_valid * kRowBytes);
-        __syncwarp();
-        if (sig_ok)
-            bulk_copy_g2s(tile0 + slot * kSlotBytes + lane * (kFiltPitch * (uint32_t)sizeof(float)),
-                          my_src + t_begin + 32 * i, kRowBytes, bar0 + 8 * slot);
-    };
-    for (int i = 0; i < kFiltRing && i < ntiles; ++i)
-        if (tile_is_full(i)) issue_tile(i);
-
-    IirState st;
-#pragma unroll
-    for (int s = 0; s < FSEM_BP_SECTIONS; ++s) { st.w1[s] = 0.f; st.w2[s] = 0.f; }
-    st.s1 = 0.f; st.s2 = 0.f;
-    double acc_d = 0.0;
-
-    for (int i = 0; i < ntiles; ++i) {
-        const int t = t_begin + 32 * i;
-        const int slot = i % kFiltRing;
-        float* tile = sm.tile[slot];
-        float* row = tile + lane * kFiltPitch;
-        if (tile_is_full(i)) {
-            mbar_wait(bar0 + 8 * slot, (par >> slot) & 1u);
-        } else {                                              // ragged last tile of the signal: plain guarded loads
-#pragma unroll
-            for (int j = 0; j < 32; ++j) row[j] = (sig_ok && t + j < len) ? __ldg(my_src + t + j) : 0.f;
-        }
-        const bool owned = t >= t_acc;
-        float acc = 0.f;
-        if (t >= 16 && t + 48 <= len) {
-            float acc2 = 0.f;
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                float4 q = *reinterpret_cast<const float4*>(row + 4 * g);
-                float y0 = bandpass_step(P, st, q.x); float z0 = preemph_step(P, st, q.x);
-                float y1 = bandpass_step(P, st, q.y); float z1 = preemph_step(P, st, q.y);
-                float y2 = bandpass_step(P, st, q.z); float z2 = preemph_step(P, st, q.z);
-                float y3 = bandpass_step(P, st, q.w); float z3 = preemph_step(P, st, q.w);
-                acc = fmaf(y0, y0, acc); acc2 = fmaf(y1, y1, acc2);
-                acc = fmaf(y2, y2, acc); acc2 = fmaf(y3, y3, acc2);
-                *reinterpret_cast<float4*>(row + 4 * g) = make_float4(z0, z1, z2, z3);
-            }
-            acc += acc2;
-        } else {
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                float4 q = *reinterpret_cast<const float4*>(row + 4 * g);
-                float v[4] = {q.x, q.y, q.z, q.w};
-                float zz[4];
-                const int tg = t + 4 * g;
-                const bool edge = (tg < 16) || (tg + 4 > len - 16);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float yv = bandpass_step(P, st, v[j]);
-                    float xv = edge ? v[j] * taper_weight(tg + j, len) : v[j];
-                    zz[j] = preemph_step(P, st, xv);
-                    if (tg + j < t_stop) acc = fmaf(yv, yv, acc);
-                }
-                *reinterpret_cast<float4*>(row + 4 * g) = make_float4(zz[0], zz[1], zz[2], zz[3]);
-            }
-        }
-        if (owned) acc_d += (double)acc;
-        __syncwarp();
-        if (owned) {                                          // drain z with coalesced 128-byte row segments
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int a = t + col;
-                const int rl = r < rows_ok ? len : 0;
-                float4 q = *reinterpret_cast<const float4*>(tile + ((lane >> 3) + 4 * r) * kFiltPitch + col);
-                float* d = dst0 + r * dstep + t;
-                if (a + 4 <= rl) {
-                    *reinterpret_cast<float4*>(d) = q;
-                } else {
-                    if (a < rl) d[0] = q.x;
-                    if (a + 1 < rl) d[1] = q.y;
-                    if (a + 2 < rl) d[2] = q.z;
-                }
-            }
-        }
-        __syncwarp();
-        if (i + kFiltRing < ntiles && tile_is_full(i + kFiltRing)) issue_tile(i + kFiltRing);
-    }
-    if (sig_ok) partial[((int64_t)half * batch + my_item) * nchunks + c] = acc_d;
-}
-
-// ------------------------------------------------------------------------------------------------
 // Kernel B: persistent warps; one warp = one (item, frame) unit at a time.
 #ifndef FSEM_FFT_WARPS
 #define FSEM_FFT_WARPS 8
