@@ -70,15 +70,26 @@ resampled_lengths_kernel(const int32_t* __restrict__ lengths, int64_t batch, int
 // of each phase is evaluated (97 of 140 FMAs per block); the host checks that the taps outside those
 // ranges are exactly zero before selecting this kernel.
 struct Resample85Taps { float h[5][28]; };
+#ifndef FSEM_RS85_BLOCKS
+#define FSEM_RS85_BLOCKS 2
+#endif
 constexpr int kRs85Threads = 128;
-constexpr int kRs85TileIn = kRs85Threads * 16;          // 2048 new input samples per CTA
-constexpr int kRs85TileOut = kRs85Threads * 10;         // 1280 outputs per CTA
-constexpr int kRs85Quads = kRs85TileIn / 4 + 10;        // float4s staged per tile (12 floats of history + 28 ahead)
+constexpr int kRs85Nb = FSEM_RS85_BLOCKS;                       // polyphase blocks (8 in -> 5 out) per thread
+constexpr int kRs85TileIn = kRs85Threads * 8 * kRs85Nb;         // new input samples per tile (4096)
+constexpr int kRs85TileOut = kRs85Threads * 5 * kRs85Nb;        // outputs per tile (2560 = 20 hops)
+constexpr int kRs85Quads = kRs85TileIn / 4 + 10;                // float4s staged per tile (12 floats of history + 28 ahead)
+constexpr int kRs85ThreadQuads = 2 * kRs85Nb + 6;               // float4s one thread reads (8*NB + 20 inputs, rounded up)
+constexpr int kRs85PadEvery = 2 * kRs85Nb;                      // one pad float4 per 2*NB: lane pitch 2*NB+1 (odd) = conflict-free
+constexpr int kRs85SmemQuads = kRs85Quads + kRs85Quads / kRs85PadEvery + 2;
 __host__ __device__ constexpr int rs85_lo(int p) { return p == 0 ? 1 : p == 1 ? 2 : p == 2 ? 4 : p == 3 ? 6 : 7; }
 __host__ __device__ constexpr int rs85_hi(int p) { return p == 0 ? 19 : p == 1 ? 21 : p == 2 ? 22 : p == 3 ? 24 : 26; }
 
-constexpr int kRs85TilesPerCta = 4;
-constexpr int kRs85Hops = kRs85TileOut / FSEM_STOI_HOP;      // 10 hops of 128 output samples per tile
+#ifndef FSEM_RS85_TILES
+#define FSEM_RS85_TILES 8
+#endif
+constexpr int kRs85TilesPerCta = FSEM_RS85_TILES;
+constexpr int kRs85Hops = kRs85TileOut / FSEM_STOI_HOP;          // hops of 128 output samples per tile
+static_assert(kRs85TileOut % FSEM_STOI_HOP == 0, "tiles must hold whole hops");
 
 // Each CTA walks kRs85TilesPerCta consecutive tiles of one signal; the next tile's input is prefetched into
 // registers while the current one is computed.  Outputs go through shared memory so that the global stores are
@@ -93,7 +104,7 @@ stoi_resample85_kernel(const float* __restrict__ clean, const float* __restrict_
                        const int32_t* __restrict__ lengths, int64_t batch, int64_t n, int64_t stride,
                        const __grid_constant__ Resample85Taps taps, const StoiTables* __restrict__ tab,
                        float* __restrict__ y, int64_t ystride, double2* __restrict__ hop_energy, int hops_max) {
-    __shared__ float4 s_in[kRs85Quads + kRs85Quads / 4 + 2];
+    __shared__ float4 s_in[kRs85SmemQuads];
     __shared__ __align__(16) float s_out[kRs85TileOut];
     __shared__ __align__(16) float s_win[FSEM_STOI_WIN];
     const int tid = threadIdx.x;
@@ -108,7 +119,7 @@ stoi_resample85_kernel(const float* __restrict__ clean, const float* __restrict_
     float* __restrict__ yrow = y + sig * ystride;
     for (int i = tid; i < FSEM_STOI_WIN; i += kRs85Threads) s_win[i] = tab->window[i];
 
-    constexpr int kPerThread = (kRs85Quads + kRs85Threads - 1) / kRs85Threads;   // 5 float4 per thread per tile
+    constexpr int kPerThread = (kRs85Quads + kRs85Threads - 1) / kRs85Threads;   // float4 per thread per tile fill
     auto fetch = [&](int64_t tile, float4 (&v)[kPerThread]) {
         const int64_t in0 = tile * kRs85TileIn - 12;                              // first staged sample (multiple of 4)
 #pragma unroll
@@ -135,30 +146,41 @@ stoi_resample85_kernel(const float* __restrict__ clean, const float* __restrict_
 #pragma unroll
         for (int r = 0; r < kPerThread; ++r) {
             const int q = tid + r * kRs85Threads;
-            if (q < kRs85Quads) s_in[q + (q >> 2)] = pre[r];
+            if (q < kRs85Quads) s_in[q + q / kRs85PadEvery] = pre[r];
         }
         __syncthreads();
         if (k + 1 < kRs85TilesPerCta && (out0 + kRs85TileOut) < L) fetch(tile + 1, pre);
-        // thread t: blocks 2t, 2t+1 of this tile need staged floats [16t + 2, 16t + 38)
-        float xin[40];
-        const float4* src = s_in + 5 * tid;
+        // thread t: blocks NB*t .. NB*t+NB-1 of this tile need staged floats [8*NB*t + 2, 8*NB*t + 8*NB + 22)
+        float xin[4 * kRs85ThreadQuads];
+        const float4* src = s_in + (kRs85PadEvery + 1) * tid;
 #pragma unroll
-        for (int i = 0; i < 10; ++i) {
-            float4 v = src[i + (i >> 2)];
+        for (int i = 0; i < kRs85ThreadQuads; ++i) {
+            float4 v = src[i + i / kRs85PadEvery];
             xin[4 * i] = v.x; xin[4 * i + 1] = v.y; xin[4 * i + 2] = v.z; xin[4 * i + 3] = v.w;
         }
+        float out[5 * kRs85Nb];
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < kRs85Nb; ++b) {
 #pragma unroll
             for (int p = 0; p < 5; ++p) {
                 float acc = 0.f;
 #pragma unroll
                 for (int j = rs85_lo(p); j <= rs85_hi(p); ++j) acc = fmaf(taps.h[p][j], xin[2 + 8 * b + j], acc);
-                s_out[10 * tid + 5 * b + p] = acc;
+                out[5 * b + p] = acc;
             }
         }
+        if (kRs85Nb % 4 == 0) {                                                    // 5*NB floats = whole float4s, lane pitch 5*NB words
+#pragma unroll
+            for (int i = 0; i < 5 * kRs85Nb / 4; ++i)
+                *reinterpret_cast<float4*>(s_out + 5 * kRs85Nb * tid + 4 * i) =
+                    make_float4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 5 * kRs85Nb / 2; ++i)
+                *reinterpret_cast<float2*>(s_out + 5 * kRs85Nb * tid + 2 * i) = make_float2(out[2 * i], out[2 * i + 1]);
+        }
         __syncthreads();
-        // coalesced float4 stores of the 1280 outputs
+        // coalesced float4 stores of the tile's outputs
         const int64_t valid = min((int64_t)kRs85TileOut, L - out0);
         for (int q = tid; q < kRs85TileOut / 4; q += kRs85Threads) {
             const float4 v = *reinterpret_cast<const float4*>(s_out + 4 * q);
@@ -172,7 +194,7 @@ stoi_resample85_kernel(const float* __restrict__ clean, const float* __restrict_
             }
         }
         if (is_clean) {
-            // hop energies: warp w takes hops w, w+4, w+8 of this tile; lane handles 4 samples of the hop
+            // hop energies: warp w takes hops w, w+4, ... of this tile; lane handles 4 samples of the hop
             const int lane = tid & 31, warp = tid >> 5;
             const float4 wa = *reinterpret_cast<const float4*>(s_win + 4 * lane);
             const float4 wb = *reinterpret_cast<const float4*>(s_win + 128 + 4 * lane);
