@@ -372,3 +372,42 @@ def test_readme_example_anchors(pesq, stoi_metrics):
     res2 = stoi_metrics(16000)(clean, noisy2)
     assert np.max(np.abs(np.array([r["STOI"] for r in res2]) - np.array([0.9098063111, 0.9109758735, 0.9116464257, 0.9117136002]))) <= 1e-4
     assert np.max(np.abs(np.array([r["ESTOI"] for r in res2]) - np.array([0.9027701020, 0.9035763741, 0.9050849676, 0.9054367542]))) <= 1e-4
+
+
+def test_random_shapes_against_oracle(pesq, stoi_metrics):
+    """Seeded sweep over awkward shapes: batches that are not multiples of 32, lengths that are not multiples of
+    4 / 32 / 64 / 256, row pitches wider than n (non-contiguous views), misaligned bases, CPU and CUDA inputs,
+    with and without per-item lengths.  Every item is checked against the oracle."""
+    from fast_speech_enhancement_metrics_b200.synth import synth_item
+    rng = np.random.default_rng(2024)
+    st16 = stoi_metrics(16000)
+    worst = {"pesq": 0.0, "stoi": 0.0, "estoi": 0.0}
+    for trial in range(10):
+        b = int(rng.integers(1, 40))
+        n = int(rng.integers(5700, 30000))
+        pitch = n + int(rng.integers(0, 7))
+        off = int(rng.integers(0, 4))
+        clean = np.zeros((b, n), np.float32); deg = np.zeros_like(clean)
+        for i in range(b):
+            clean[i], deg[i], _ = synth_item(rng, n)
+        use_len = bool(trial % 2)
+        lens = [int(x) for x in rng.integers(5700, n + 1, size=b)] if use_len else None
+        if lens is not None:
+            lens[0] = n
+        # strided / misaligned device views of the same data
+        buf_c = torch.zeros(b * pitch + 8, device="cuda"); buf_d = torch.zeros_like(buf_c)
+        vc = buf_c[off:off + b * pitch].view(b, pitch)[:, :n]
+        vd = buf_d[off:off + b * pitch].view(b, pitch)[:, :n]
+        vc.copy_(torch.from_numpy(clean)); vd.copy_(torch.from_numpy(deg))
+        if trial % 3 == 2:                       # host path
+            vc, vd = torch.from_numpy(clean), torch.from_numpy(deg)
+        got_p = np.array([r["PESQ"] for r in pesq(vc, vd, lengths=lens)])
+        res = st16(vc, vd, lengths=lens)
+        want_p = po.pesq_batch(clean, deg, lens)
+        ws, we, wk = so.stoi_batch(clean, deg, 16000, lens)
+        worst["pesq"] = max(worst["pesq"], _maxdiff(got_p, want_p))
+        worst["stoi"] = max(worst["stoi"], _maxdiff(np.array([r["STOI"] for r in res]), ws))
+        worst["estoi"] = max(worst["estoi"], _maxdiff(np.array([r["ESTOI"] for r in res]), we))
+        assert np.array_equal(st16.last_kept_frames.numpy(), wk), (trial, b, n)
+    _report("random_shapes", worst)
+    assert worst["pesq"] <= 1e-3 and worst["stoi"] <= 1e-4 and worst["estoi"] <= 1e-4
