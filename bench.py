@@ -403,7 +403,10 @@ def main():
     traffic_path = os.path.join(ROOT, "profiles", "dram_traffic.json")
     traffic = None
     if os.path.exists(traffic_path):
-        traffic = json.load(open(traffic_path)).get(top_name)
+        tj = json.load(open(traffic_path))
+        per_launch = tj.get("bytes_per_launch", {}).get(top_name)
+        if per_launch is not None:          # measured with ncu at tj["items"] items x 10 s; linear in the item count
+            traffic = per_launch * (local_b * args.seconds) / (tj.get("items", 8192) * 10.0)
     roofline = {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": top_avg_ms,
