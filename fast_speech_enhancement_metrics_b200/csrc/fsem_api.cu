@@ -726,7 +726,7 @@ extern "C" int fsem_stoi_score_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t* in,
     }
     {
         { ProfScope prof_(K_STOI_SEGMENT, stream);
-          stoi_segment_kernel<<<(unsigned)(in->batch * p.ntiles), kSegThreads, 0, stream>>>(
+          stoi_segment_kernel<<<(unsigned)(in->batch * ceil_div(p.ntiles, kSegTilesPerCta)), kSegThreads, 0, stream>>>(
               tob, in->batch, p.ustride, p.ntiles, kept_count, ctx->clip, partial); }
         FSEM_LAUNCHED();
         { ProfScope prof_(K_STOI_FINALIZE, stream);

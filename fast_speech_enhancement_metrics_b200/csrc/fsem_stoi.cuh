@@ -445,6 +445,7 @@ constexpr int kSegTile = 64;
 constexpr int kSegThreads = 256;
 constexpr int kSegCols = kSegTile + FSEM_STOI_SEG - 1;  // 93 frames feed 64 segments
 constexpr int kSegPitch = 97;                            // odd pitch: conflict-free rows
+constexpr int kSegTilesPerCta = 4;                       // consecutive tiles per CTA, next tile prefetched into registers
 
 __device__ __forceinline__ float rsqrt_or_zero(float v) { return v > 0.f ? rsqrtf(v) : 0.f; }
 
@@ -458,26 +459,53 @@ stoi_segment_kernel(const float* __restrict__ tob, int64_t batch, int ustride, i
     __shared__ float s_red[2][kSegThreads / 32];
 
     const int tid = threadIdx.x;
-    const int64_t item = blockIdx.x / ntiles;
-    const int tile = (int)(blockIdx.x - item * ntiles);
+    const int groups = (ntiles + kSegTilesPerCta - 1) / kSegTilesPerCta;
+    const int64_t item = blockIdx.x / groups;
+    const int tile_first = (int)(blockIdx.x - item * groups) * kSegTilesPerCta;
     const int K = kept_count[item];
     const int M = max(K - 31, 0);                     // number of segments (STOI.py:183-186)
+    const float* __restrict__ tx0 = tob + (item * FSEM_STOI_NBANDS) * (int64_t)ustride;
+    const float* __restrict__ ty0 = tob + ((batch + item) * FSEM_STOI_NBANDS) * (int64_t)ustride;
+    // the 2 x 15 x 93 tob values of a tile, spread over the CTA's registers (prefetched one tile ahead)
+    constexpr int kTileVals = 2 * FSEM_STOI_NBANDS * kSegCols;
+    constexpr int kPerThread = (kTileVals + kSegThreads - 1) / kSegThreads;
+    auto fetch = [&](int tile, float (&v)[kPerThread]) {
+        const int m0f = tile * kSegTile;
+        const int ncolf = min(kSegTile, M - m0f) + FSEM_STOI_SEG - 1;
+#pragma unroll
+        for (int r = 0; r < kPerThread; ++r) {
+            const int i = tid + r * kSegThreads;
+            const int sg = i / (FSEM_STOI_NBANDS * kSegCols);
+            const int rem = i - sg * (FSEM_STOI_NBANDS * kSegCols);
+            const int j = rem / kSegCols, c = rem - j * kSegCols;
+            const bool ok = i < kTileVals && c < ncolf;
+            v[r] = ok ? __ldg((sg ? ty0 : tx0) + (int64_t)j * ustride + m0f + c) : 0.f;
+        }
+    };
+    float pre[kPerThread];
+    if (tile_first * kSegTile < M) fetch(tile_first, pre);
+    for (int tk = 0; tk < kSegTilesPerCta; ++tk) {
+    const int tile = tile_first + tk;
+    if (tile >= ntiles) break;
     const int m0 = tile * kSegTile;
-    if (m0 >= M) {
+    if (m0 >= M) {                                    // uniform: no segments in this tile (nor in the following ones)
         if (tid == 0) partial[item * ntiles + tile] = make_float2(0.f, 0.f);
-        return;
+        continue;
     }
     const int nseg = min(kSegTile, M - m0);
-    const int ncol = nseg + FSEM_STOI_SEG - 1;
-    const float* __restrict__ tx = tob + (item * FSEM_STOI_NBANDS) * (int64_t)ustride + m0;
-    const float* __restrict__ ty = tob + ((batch + item) * FSEM_STOI_NBANDS) * (int64_t)ustride + m0;
-    for (int i = tid; i < FSEM_STOI_NBANDS * kSegCols; i += kSegThreads) {
-        int j = i / kSegCols, c = i - j * kSegCols;
-        bool ok = c < ncol;
-        s_x[j][c] = ok ? __ldg(tx + (int64_t)j * ustride + c) : 0.f;
-        s_y[j][c] = ok ? __ldg(ty + (int64_t)j * ustride + c) : 0.f;
+    __syncthreads();                                  // previous tile fully consumed
+#pragma unroll
+    for (int r = 0; r < kPerThread; ++r) {
+        const int i = tid + r * kSegThreads;
+        if (i < kTileVals) {
+            const int sg = i / (FSEM_STOI_NBANDS * kSegCols);
+            const int rem = i - sg * (FSEM_STOI_NBANDS * kSegCols);
+            const int j = rem / kSegCols, c = rem - j * kSegCols;
+            (sg ? s_y : s_x)[j][c] = pre[r];
+        }
     }
     __syncthreads();
+    if (tk + 1 < kSegTilesPerCta && tile + 1 < ntiles && (m0 + kSegTile) < M) fetch(tile + 1, pre);
 
     // ---- part A: per (segment, band) rows: STOI term + row statistics for ESTOI
     float stoi_acc = 0.f;
@@ -554,6 +582,7 @@ stoi_segment_kernel(const float* __restrict__ tob, int64_t batch, int ustride, i
         for (int i = 0; i < kSegThreads / 32; ++i) { a += s_red[0][i]; b += s_red[1][i]; }
         partial[item * ntiles + tile] = make_float2(a, b);
     }
+    }   // tiles of this CTA
 }
 
 __global__ void __launch_bounds__(128)
