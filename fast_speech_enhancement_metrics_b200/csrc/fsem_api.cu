@@ -216,6 +216,7 @@ struct PesqPlan {
     int64_t batch, n, zstride;       // n = samples per item at 16 kHz (after resample-on-ingest)
     int64_t n_in, rstride;           // input samples per item; row pitch of the resampled signals
     bool resample;
+    bool tiled;                      // lane = signal (tiled kernel) vs thread = (signal, chunk) for tiny batches
     int tmax, chunk, nchunks;
     size_t off_rs, off_rslen, off_z, off_partial, off_bark, off_dist, off_power, total;
 };
@@ -240,7 +241,14 @@ PesqPlan pesq_plan(const fsem_pesq_ctx* ctx, int64_t batch, int64_t n_in) {
     const int64_t max_ch = ceil_div(nn, 1024) < 512 ? ceil_div(nn, 1024) : 512;
     int64_t nch = 1, chunk = round_up(nn, 64);
     double best = 1e300;
-    for (int64_t c = 1; c <= max_ch; ++c) {
+    // tiny batches cannot fill the 32 signal lanes of a warp: there a thread takes one (signal, chunk) and the time
+    // axis is cut as finely as the warm-up allows
+    p.tiled = batch >= 16;
+    if (!p.tiled) {
+        chunk = round_up(ceil_div(nn, max_ch), 64);
+        nch = ceil_div(nn, chunk);
+    }
+    for (int64_t c = 1; p.tiled && c <= max_ch; ++c) {
         const int64_t ch = round_up(ceil_div(nn, c), 64);
         const int64_t cc = ceil_div(nn, ch);
         const int64_t waves = ceil_div(groups * cc, slots);
@@ -406,7 +414,7 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
 
     {   // kernel A
         const bool vec4 = aligned16(in->clean) && aligned16(in->deg) && (in->stride % 4 == 0);
-        if (vec4) {
+        if (vec4 && p.tiled) {
             const int64_t units = 2 * ceil_div(in->batch, 32) * p.nchunks;
             const unsigned grid = (unsigned)ceil_div(units, kFiltWarps);
             { ProfScope prof_(K_PESQ_FILTER, stream);
@@ -420,10 +428,16 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
                       ctx->coef, z, p.zstride, partial); }
         } else {
             const int64_t threads = 2 * in->batch * p.nchunks;
+            const unsigned grid = (unsigned)ceil_div(threads, 128);
             { ProfScope prof_(K_PESQ_FILTER, stream);
-              pesq_filter_kernel<false><<<(unsigned)ceil_div(threads, 128), 128, 0, stream>>>(
-                  in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, p.chunk, p.nchunks, ctx->warm,
-                  ctx->coef, z, p.zstride, partial); }
+              if (vec4)
+                  pesq_filter_kernel<true><<<grid, 128, 0, stream>>>(
+                      in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, p.chunk, p.nchunks, ctx->warm,
+                      ctx->coef, z, p.zstride, partial);
+              else
+                  pesq_filter_kernel<false><<<grid, 128, 0, stream>>>(
+                      in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, p.chunk, p.nchunks, ctx->warm,
+                      ctx->coef, z, p.zstride, partial); }
         }
         FSEM_LAUNCHED();
     }
