@@ -238,7 +238,7 @@ PesqPlan pesq_plan(const fsem_pesq_ctx* ctx, int64_t batch, int64_t n_in) {
     const int64_t nn = n > 0 ? n : 1;
     const int64_t groups = 2 * ceil_div(batch > 0 ? batch : 1, 32);
     const int64_t slots = (int64_t)ctx->dev.sms * ctx->filt_ctas_per_sm * kFiltWarps;
-    const int64_t max_ch = ceil_div(nn, 1024) < 512 ? ceil_div(nn, 1024) : 512;
+    const int64_t max_ch = ceil_div(nn, 256) < 1024 ? ceil_div(nn, 256) : 1024;     // chunks of at least 256 samples
     int64_t nch = 1, chunk = round_up(nn, 64);
     double best = 1e300;
     // tiny batches cannot fill the 32 signal lanes of a warp: there a thread takes one (signal, chunk) and the time
