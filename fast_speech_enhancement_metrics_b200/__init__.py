@@ -10,7 +10,8 @@ kcoost/fast_speech_enhancement_metrics).
 from .base import BaseMetric
 from .PESQ import PESQ
 from .STOI import STOI
+from .LSD import LSD
 from .fused import score_pesq_stoi
 
-__all__ = ["BaseMetric", "PESQ", "STOI", "score_pesq_stoi"]
+__all__ = ["BaseMetric", "PESQ", "STOI", "LSD", "score_pesq_stoi"]
 __version__ = "0.1.0"

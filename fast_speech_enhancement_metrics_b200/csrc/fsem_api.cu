@@ -10,6 +10,7 @@
 #include "fsem_common.cuh"
 #include "fsem_pesq.cuh"
 #include "fsem_stoi.cuh"
+#include "fsem_lsd.cuh"
 
 using namespace fsem;
 
@@ -46,11 +47,11 @@ inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 // ---- optional per-kernel timing with CUDA events on the launching stream (bench.py only; not thread-safe)
 enum KernelId {
     K_PESQ_FILTER = 0, K_PESQ_SPECTRUM, K_PESQ_BARK, K_STOI_RESAMPLE, K_STOI_ENERGY, K_STOI_COMPACT,
-    K_STOI_TOB, K_STOI_SEGMENT, K_STOI_FINALIZE, K_PESQ_RESAMPLE, K_COUNT
+    K_STOI_TOB, K_STOI_SEGMENT, K_STOI_FINALIZE, K_PESQ_RESAMPLE, K_LSD_FRAMES, K_COUNT
 };
 const char* const kKernelNames[K_COUNT] = {
     "pesq_filter_kernel", "pesq_spectrum_kernel", "pesq_bark_kernel", "stoi_resample_kernel", "stoi_energy_kernel",
-    "stoi_compact_kernel", "stoi_tob_kernel", "stoi_segment_kernel", "stoi_finalize_kernel", "pesq_resample_kernel"};
+    "stoi_compact_kernel", "stoi_tob_kernel", "stoi_segment_kernel", "stoi_finalize_kernel", "pesq_resample_kernel", "lsd_frames_kernel"};
 bool g_profile = false;
 struct ProfRecord { int id; cudaEvent_t start, stop; };
 std::vector<ProfRecord> g_prof_pending;
@@ -900,5 +901,91 @@ extern "C" int fsem_pesq_stoi_score_host_f32(fsem_pesq_ctx_t* pctx, fsem_stoi_ct
     }
     FSEM_CUDA(cudaStreamSynchronize(P.copy));
     FSEM_CUDA(cudaStreamSynchronize(P.compute));
+    return FSEM_OK;
+}
+
+// ================================================================================================
+// LSD: log-spectral distance on the same packed FFT (fast_se_metrics/LSD.py:6-52)
+// ================================================================================================
+struct fsem_lsd_ctx {
+    DeviceInfo dev;
+    float* d_hann = nullptr;
+    int ctas_per_sm = 2;
+};
+
+namespace {
+struct LsdPlan { int tmax; size_t off_alpha, off_frames, total; };
+LsdPlan lsd_plan(int64_t batch, int64_t n) {
+    LsdPlan p{};
+    p.tmax = lsd_num_frames(n);
+    size_t off = 0;
+    p.off_alpha = off;  off = align256(off + sizeof(float) * batch);
+    p.off_frames = off; off = align256(off + sizeof(float) * batch * p.tmax);
+    p.total = off;
+    return p;
+}
+}  // namespace
+
+extern "C" int fsem_lsd_create(fsem_lsd_ctx_t** out, const float* hann512) {
+    if (!out || !hann512) return fail(FSEM_E_INVALID, "fsem_lsd_create: null argument");
+    *out = nullptr;
+    fsem_lsd_ctx* ctx = new (std::nothrow) fsem_lsd_ctx();
+    if (!ctx) return fail(FSEM_E_INVALID, "out of host memory");
+    int rc = query_device(ctx->dev);
+    if (rc != FSEM_OK) { delete ctx; return rc; }
+    cudaError_t e = cudaMalloc(&ctx->d_hann, sizeof(float) * 512);
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->d_hann, hann512, sizeof(float) * 512, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (ctx->d_hann) cudaFree(ctx->d_hann);
+        delete ctx;
+        return fail(FSEM_E_CUDA, "fsem_lsd_create: %s", cudaGetErrorString(e));
+    }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lsd_frames_kernel, kLsdWarps * 32, 0) == cudaSuccess && occ > 0)
+        ctx->ctas_per_sm = occ;
+    *out = ctx;
+    return FSEM_OK;
+}
+
+extern "C" int fsem_lsd_destroy(fsem_lsd_ctx_t* ctx) {
+    if (!ctx) return FSEM_OK;
+    if (ctx->d_hann) cudaFree(ctx->d_hann);
+    delete ctx;
+    return FSEM_OK;
+}
+
+extern "C" size_t fsem_lsd_workspace_bytes(const fsem_lsd_ctx_t* ctx, int64_t batch, int64_t n) {
+    if (!ctx || batch <= 0 || n <= 0) return 0;
+    return lsd_plan(batch, n).total;
+}
+
+extern "C" int fsem_lsd_score_f32(fsem_lsd_ctx_t* ctx, const fsem_batch_t* in, float* lsd_out, void* workspace,
+                                  size_t workspace_bytes, void* stream_v) {
+    if (!ctx || !in || !lsd_out) return fail(FSEM_E_INVALID, "fsem_lsd_score_f32: null argument");
+    if (in->batch < 0 || in->n <= 0 || in->stride < in->n || in->n >= (int64_t(1) << 30))
+        return fail(FSEM_E_INVALID, "fsem_lsd_score_f32: bad shape");
+    if (in->batch == 0) return FSEM_OK;
+    if (!in->clean || !in->deg) return fail(FSEM_E_INVALID, "fsem_lsd_score_f32: null input");
+    const LsdPlan p = lsd_plan(in->batch, in->n);
+    if (!workspace || workspace_bytes < p.total)
+        return fail(FSEM_E_WORKSPACE, "fsem_lsd_score_f32: workspace %zu < %zu bytes", workspace_bytes, p.total);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    char* ws = static_cast<char*>(workspace);
+    float* alpha = reinterpret_cast<float*>(ws + p.off_alpha);
+    float* frames = reinterpret_cast<float*>(ws + p.off_frames);
+    lsd_scale_kernel<<<(unsigned)in->batch, 256, 0, stream>>>(in->clean, in->deg, in->lengths, in->batch, in->n,
+                                                             in->stride, alpha);
+    FSEM_LAUNCHED();
+    const int64_t units = in->batch * (int64_t)p.tmax;
+    int64_t grid = ceil_div(units, kLsdWarps);
+    const int64_t cap = (int64_t)ctx->dev.sms * ctx->ctas_per_sm;
+    if (grid > cap) grid = cap;
+    { ProfScope prof_(K_LSD_FRAMES, stream);
+      lsd_frames_kernel<<<(unsigned)grid, kLsdWarps * 32, 0, stream>>>(in->clean, in->deg, in->lengths, in->batch, in->n,
+                                                                     in->stride, p.tmax, ctx->d_hann, alpha, frames); }
+    FSEM_LAUNCHED();
+    lsd_finalize_kernel<<<(unsigned)ceil_div(in->batch, 128), 128, 0, stream>>>(frames, in->lengths, in->batch, in->n,
+                                                                               p.tmax, lsd_out);
+    FSEM_LAUNCHED();
     return FSEM_OK;
 }

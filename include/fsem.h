@@ -123,6 +123,7 @@ typedef struct fsem_stoi_design {
 
 typedef struct fsem_pesq_ctx fsem_pesq_ctx_t;
 typedef struct fsem_stoi_ctx fsem_stoi_ctx_t;
+typedef struct fsem_lsd_ctx fsem_lsd_ctx_t;
 
 FSEM_API int fsem_version(void);
 FSEM_API const char* fsem_last_error(void);
@@ -131,7 +132,7 @@ FSEM_API int64_t fsem_launch_count(void);
 
 /* Optional per-kernel timing (CUDA events on the launching stream).  Bench/diagnostics only,
  * process-global and not thread-safe.  fsem_profile_read synchronises on the recorded events and
- * returns the accumulated device time and launch count of kernel `index` (0 <= index < 10). */
+ * returns the accumulated device time and launch count of kernel `index` (0 <= index < 11). */
 FSEM_API int fsem_profile_enable(int on);
 FSEM_API int fsem_profile_reset(void);
 FSEM_API int fsem_profile_read(int index, const char** name, double* total_ms, int64_t* launches);
@@ -183,6 +184,16 @@ FSEM_API int fsem_stoi_debug_taps(fsem_stoi_ctx_t* ctx, int64_t batch, int64_t n
 FSEM_API int fsem_pesq_stoi_score_host_f32(fsem_pesq_ctx_t* pesq, fsem_stoi_ctx_t* stoi, const fsem_batch_t* in,
                                   float* mos_out, int32_t* pesq_status_out, float* stoi_out, float* estoi_out,
                                   int32_t* kept_frames_out, int32_t* stoi_status_out);
+
+/* ------------------------------------------------------------------ LSD (adjacent metric on the same FFT)
+ * Replaces LSD.compute_metric (fast_se_metrics/LSD.py:33-52): scale-matched log-spectral distance on a
+ * centred Hann-512/256 STFT.  `hann512` is the HOST window torch.hann_window(512) (LSD.py:16).
+ * lsd_out[batch] fp32 and all batch pointers are DEVICE pointers; 16 kHz input only. */
+FSEM_API int fsem_lsd_create(fsem_lsd_ctx_t** out, const float* hann512);
+FSEM_API int fsem_lsd_destroy(fsem_lsd_ctx_t* ctx);
+FSEM_API size_t fsem_lsd_workspace_bytes(const fsem_lsd_ctx_t* ctx, int64_t batch, int64_t n);
+FSEM_API int fsem_lsd_score_f32(fsem_lsd_ctx_t* ctx, const fsem_batch_t* in, float* lsd_out, void* workspace,
+                       size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -60,6 +60,18 @@ def pesq_rate_cases():
     return cases
 
 
+def lsd_cases():
+    """LSD (fast_se_metrics/LSD.py): (clean, degraded, lengths)."""
+    cases = {}
+    c, d, _ = synth_batch(301, 6, 32000)
+    cases["speech2s"] = (c, d, None)
+    c, d, _ = synth_batch(302, 4, 40001)
+    cases["ragged"] = (c, d, [40001, 20037, 511, 33333])
+    cw = _white(303, 2, 16000)
+    cases["white_scaled"] = (cw, (0.1 * cw + 0.02 * _white(304, 2, 16000)).astype(np.float32), None)
+    return cases
+
+
 def stoi_cases():
     cases = {}
     c, d, _ = synth_batch(201, 8, 30000, fs=10000)

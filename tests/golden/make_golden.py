@@ -35,7 +35,8 @@ import importlib.util  # noqa: E402
 _spec = importlib.util.spec_from_file_location("golden_cases", os.path.join(HERE, "cases.py"))
 _cases = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(_cases)   # (the reference ships its own `tests` package, so import by path)
-pesq_cases, stoi_cases, pesq_rate_cases = _cases.pesq_cases, _cases.stoi_cases, _cases.pesq_rate_cases
+pesq_cases, stoi_cases, pesq_rate_cases, lsd_cases = (_cases.pesq_cases, _cases.stoi_cases, _cases.pesq_rate_cases,
+                                                       _cases.lsd_cases)
 
 
 def run_pesq():
@@ -146,7 +147,23 @@ def run_stoi():
     np.savez_compressed(os.path.join(HERE, "golden_stoi.npz"), **out)
 
 
+def run_lsd():
+    from fast_se_metrics.LSD import LSD
+    out = {}
+    metric = LSD(16000, use_gpu=False)
+    for name, (clean, deg, lengths) in lsd_cases().items():
+        c, d = torch.from_numpy(clean), torch.from_numpy(deg)
+        if lengths is None:
+            res = [r["LSD"] for r in metric(c, d)]
+        else:
+            res = [metric(c[i:i + 1, :n], d[i:i + 1, :n])[0]["LSD"] for i, n in enumerate(lengths)]
+        out[name] = np.asarray(res, np.float64)
+        print("LSD", name, out[name])
+    np.savez_compressed(os.path.join(HERE, "golden_lsd.npz"), **out)
+
+
 if __name__ == "__main__":
     run_pesq()
     run_stoi()
+    run_lsd()
     print("golden fixtures written to", HERE)
