@@ -240,6 +240,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--two-streams", action="store_true",
                     help="experiment: run the PESQ and the STOI kernel chains on two CUDA streams")
+    ap.add_argument("--overlap", type=int, default=-1,
+                    help="experiment: fused device entry fsem_pesq_stoi_score_f32 with overlap mode 0/1/2")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -284,7 +286,12 @@ def main():
 
     side = (torch.cuda.Stream(device), torch.cuda.Stream(device)) if args.two_streams else None
 
+    from fast_speech_enhancement_metrics_b200 import score_pesq_stoi_tensors
+
     def step_device():
+        if args.overlap >= 0:
+            sc3, _, _, _ = score_pesq_stoi_tensors(pesq, stoi, clean, deg, overlap=args.overlap)
+            return gather_scores(sc3.t().contiguous(), args.batch, world, out=gathered)
         if side is None:
             mos, _ = pesq.score_tensors(clean, deg)
             sc, _, _ = stoi.score_tensors(clean, deg)

@@ -29,7 +29,7 @@ EXPORTS = [
     "fsem_pesq_score_host_f32", "fsem_pesq_debug_taps",
     "fsem_stoi_create", "fsem_stoi_destroy", "fsem_stoi_workspace_bytes", "fsem_stoi_score_f32",
     "fsem_stoi_score_host_f32", "fsem_stoi_debug_taps", "fsem_pesq_stoi_score_host_f32",
-    "fsem_lsd_create", "fsem_lsd_destroy", "fsem_lsd_workspace_bytes", "fsem_lsd_score_f32",
+    "fsem_pesq_stoi_score_f32", "fsem_lsd_create", "fsem_lsd_destroy", "fsem_lsd_workspace_bytes", "fsem_lsd_score_f32",
 ]
 
 
@@ -79,6 +79,8 @@ def load() -> C.CDLL:
     lib.fsem_stoi_score_f32.argtypes = [vp, C.POINTER(Batch), fp, fp, i32p, i32p, vp, C.c_size_t, vp]
     lib.fsem_stoi_score_host_f32.argtypes = [vp, C.POINTER(Batch), fp, fp, i32p, i32p]
     lib.fsem_pesq_stoi_score_host_f32.argtypes = [vp, vp, C.POINTER(Batch), fp, i32p, fp, fp, i32p, i32p]
+    lib.fsem_pesq_stoi_score_f32.argtypes = [vp, vp, C.POINTER(Batch), fp, i32p, fp, fp, i32p, i32p, vp, C.c_size_t, vp,
+                                             C.c_size_t, vp, C.c_int]
     lib.fsem_lsd_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_float)]
     lib.fsem_lsd_destroy.argtypes = [vp]
     lib.fsem_lsd_workspace_bytes.argtypes = [vp, i64, i64]

@@ -18,6 +18,10 @@ using namespace fsem;
 namespace {
 
 thread_local char g_err[512] = "";
+// set by fsem_pesq_stoi_score_f32 around its call of fsem_pesq_score_f32: event to record right after the IIR pass,
+// and a cap on the spectrum kernel's CTAs per SM so that the other metric's kernels can co-reside
+struct OverlapHook { cudaEvent_t after_filter = nullptr; int spec_ctas_per_sm = 0; };
+thread_local OverlapHook g_hook;
 std::atomic<int64_t> g_launches{0};
 
 int fail(int code, const char* fmt, ...) {
@@ -209,6 +213,8 @@ struct fsem_pesq_ctx {
     int spec_ctas_per_sm = 2;
     int filt_ctas_per_sm = 4;
     HostPipe pipe;
+    cudaStream_t side = nullptr;                    // second stream of the overlapped two-metric device entry
+    cudaEvent_t ev_fork = nullptr, ev_filter = nullptr, ev_join = nullptr;
 };
 
 namespace {
@@ -357,6 +363,10 @@ extern "C" int fsem_pesq_create(fsem_pesq_ctx_t** out, const fsem_pesq_design_t*
 extern "C" int fsem_pesq_destroy(fsem_pesq_ctx_t* ctx) {
     if (!ctx) return FSEM_OK;
     ctx->pipe.destroy();
+    if (ctx->side) cudaStreamDestroy(ctx->side);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_filter) cudaEventDestroy(ctx->ev_filter);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->d_tab) cudaFree(ctx->d_tab);
     if (ctx->d_rs_taps) cudaFree(ctx->d_rs_taps);
     delete ctx;
@@ -441,11 +451,14 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
                       ctx->coef, z, p.zstride, partial); }
         }
         FSEM_LAUNCHED();
+        if (g_hook.after_filter) FSEM_CUDA(cudaEventRecord(g_hook.after_filter, stream));
     }
     {   // kernel B
         const int64_t units = in->batch * (int64_t)p.tmax;
         int64_t grid = ceil_div(units, kSpecWarps);
-        const int64_t cap = (int64_t)ctx->dev.sms * ctx->spec_ctas_per_sm;
+        const int per_sm = (g_hook.spec_ctas_per_sm > 0 && g_hook.spec_ctas_per_sm < ctx->spec_ctas_per_sm)
+                               ? g_hook.spec_ctas_per_sm : ctx->spec_ctas_per_sm;
+        const int64_t cap = (int64_t)ctx->dev.sms * per_sm;
         if (grid > cap) grid = cap;
         { ProfScope prof_(K_PESQ_SPECTRUM, stream);
           pesq_spectrum_kernel<<<(unsigned)grid, kSpecWarps * 32, kSpecDynSmem, stream>>>(z, p.zstride, in->lengths, in->batch,
@@ -987,5 +1000,45 @@ extern "C" int fsem_lsd_score_f32(fsem_lsd_ctx_t* ctx, const fsem_batch_t* in, f
     lsd_finalize_kernel<<<(unsigned)ceil_div(in->batch, 128), 128, 0, stream>>>(frames, in->lengths, in->batch, in->n,
                                                                                p.tmax, lsd_out);
     FSEM_LAUNCHED();
+    return FSEM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device entry point for BOTH metrics with kernel overlap: the PESQ chain runs on `stream`, the STOI chain on an
+// internal second stream that starts once PESQ's IIR pass is done, so that STOI's HBM-bound resampler runs in the
+// shadow of PESQ's shared-memory-bound spectrum kernel (and STOI's FFT kernel next to PESQ's Bark kernel).
+// `overlap` = 0 runs the two chains back to back on `stream` (identical results either way).
+extern "C" int fsem_pesq_stoi_score_f32(fsem_pesq_ctx_t* pctx, fsem_stoi_ctx_t* sctx, const fsem_batch_t* in,
+                                        float* mos_out, int32_t* pesq_status_out, float* stoi_out, float* estoi_out,
+                                        int32_t* kept_frames_out, int32_t* stoi_status_out, void* ws_pesq,
+                                        size_t ws_pesq_bytes, void* ws_stoi, size_t ws_stoi_bytes, void* stream_v,
+                                        int overlap) {
+    if (!pctx || !sctx) return fail(FSEM_E_INVALID, "fsem_pesq_stoi_score_f32: null context");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    if (!overlap) {
+        int rc = fsem_pesq_score_f32(pctx, in, mos_out, pesq_status_out, ws_pesq, ws_pesq_bytes, stream);
+        if (rc != FSEM_OK) return rc;
+        return fsem_stoi_score_f32(sctx, in, stoi_out, estoi_out, kept_frames_out, stoi_status_out, ws_stoi,
+                                   ws_stoi_bytes, stream);
+    }
+    if (!pctx->side) {
+        FSEM_CUDA(cudaStreamCreateWithFlags(&pctx->side, cudaStreamNonBlocking));
+        FSEM_CUDA(cudaEventCreateWithFlags(&pctx->ev_fork, cudaEventDisableTiming));
+        FSEM_CUDA(cudaEventCreateWithFlags(&pctx->ev_filter, cudaEventDisableTiming));
+        FSEM_CUDA(cudaEventCreateWithFlags(&pctx->ev_join, cudaEventDisableTiming));
+    }
+    FSEM_CUDA(cudaEventRecord(pctx->ev_fork, stream));
+    g_hook.after_filter = pctx->ev_filter;
+    g_hook.spec_ctas_per_sm = overlap > 1 ? 1 : 0;             // overlap = 2: leave half of every SM to the STOI chain
+    int rc = fsem_pesq_score_f32(pctx, in, mos_out, pesq_status_out, ws_pesq, ws_pesq_bytes, stream);
+    g_hook = OverlapHook{};
+    if (rc != FSEM_OK) return rc;
+    FSEM_CUDA(cudaStreamWaitEvent(pctx->side, pctx->ev_fork, 0));
+    FSEM_CUDA(cudaStreamWaitEvent(pctx->side, pctx->ev_filter, 0));
+    rc = fsem_stoi_score_f32(sctx, in, stoi_out, estoi_out, kept_frames_out, stoi_status_out, ws_stoi, ws_stoi_bytes,
+                             pctx->side);
+    if (rc != FSEM_OK) { cudaStreamSynchronize(pctx->side); return rc; }
+    FSEM_CUDA(cudaEventRecord(pctx->ev_join, pctx->side));
+    FSEM_CUDA(cudaStreamWaitEvent(stream, pctx->ev_join, 0));
     return FSEM_OK;
 }

@@ -18,6 +18,34 @@ from .PESQ import PESQ
 from .STOI import STOI
 
 
+def score_pesq_stoi_tensors(pesq: PESQ, stoi: STOI, clean: torch.Tensor, deg: torch.Tensor, lengths=None,
+                            overlap: int = 1):
+    """Device-resident scoring of both metrics: [B, n] float32 CUDA tensors -> (scores[3, B] f32 = PESQ / STOI /
+    ESTOI rows, pesq_status[B], kept_frames[B], stoi_status[B]) CUDA tensors; stream-ordered, no host sync.
+    overlap = 1 runs the STOI kernel chain on a second stream next to PESQ's spectrum kernel (C ABI
+    fsem_pesq_stoi_score_f32); 0 runs the two chains back to back.  Results are identical."""
+    b, n = clean.shape
+    lens = pesq._lengths_tensor(lengths, b, n, clean.device)
+    scores = torch.empty(3, b, dtype=torch.float32, device=clean.device)
+    pst = torch.empty(b, dtype=torch.int32, device=clean.device)
+    kept = torch.empty(b, dtype=torch.int32, device=clean.device)
+    sst = torch.empty(b, dtype=torch.int32, device=clean.device)
+    with torch.cuda.device(clean.device):
+        if deg.stride(0) != clean.stride(0) and b > 1:
+            deg = deg.contiguous(); clean = clean.contiguous()
+        wp = pesq._get_workspace(pesq._lib.fsem_pesq_workspace_bytes(pesq._ctx, b, n))
+        wsb = stoi._get_workspace(stoi._lib.fsem_stoi_workspace_bytes(stoi._ctx, b, n))
+        batch = _lib.Batch(clean.data_ptr(), deg.data_ptr(), lens.data_ptr() if lens is not None else None,
+                           b, n, clean.stride(0) if b > 1 else max(n, clean.stride(0)))
+        PESQ._check_score(pesq._lib.fsem_pesq_stoi_score_f32(
+            pesq._ctx, stoi._ctx, C.byref(batch), scores[0].data_ptr(), pst.data_ptr(), scores[1].data_ptr(),
+            scores[2].data_ptr(), kept.data_ptr(), sst.data_ptr(), wp.data_ptr(), wp.numel(), wsb.data_ptr(),
+            wsb.numel(), C.c_void_p(torch.cuda.current_stream(clean.device).cuda_stream), int(overlap)))
+    pesq._last_shape = (b, n)
+    stoi._last_shape = (b, n)
+    return scores, pst, kept, sst
+
+
 def score_pesq_stoi(pesq: PESQ, stoi: STOI, clean_speech: torch.Tensor, denoised_speech: torch.Tensor,
                     lengths=None) -> list[dict[str, float]]:
     """Returns [{"PESQ": ..., "STOI": ..., "ESTOI": ...}, ...], one dict per batch row.
@@ -28,11 +56,10 @@ def score_pesq_stoi(pesq: PESQ, stoi: STOI, clean_speech: torch.Tensor, denoised
     assert clean is not None
     b, n = clean.shape
     if clean.is_cuda:
-        # device-resident tensors are shared by the two calls anyway
-        mos, pst = pesq.score_tensors(clean, deg, lengths)
-        sc, kept, _ = stoi.score_tensors(clean, deg, lengths)
-        packed = torch.cat([mos[None], pst.to(torch.float32)[None], sc, kept.to(torch.float32)[None]]).cpu()
-        mos, pst, sc, kept = packed[0], packed[1].to(torch.int32), packed[2:4], packed[4].to(torch.int32)
+        # device-resident tensors: one library call, the two kernel chains overlap on two streams
+        scores, pst, kept, _ = score_pesq_stoi_tensors(pesq, stoi, clean, deg, lengths)
+        packed = torch.cat([scores, pst.to(torch.float32)[None], kept.to(torch.float32)[None]]).cpu()
+        mos, sc, pst, kept = packed[0], packed[1:3], packed[3].to(torch.int32), packed[4].to(torch.int32)
     else:
         lens = pesq._lengths_tensor(lengths, b, n, "cpu")
         mos = torch.empty(b, dtype=torch.float32)

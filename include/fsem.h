@@ -185,6 +185,17 @@ FSEM_API int fsem_pesq_stoi_score_host_f32(fsem_pesq_ctx_t* pesq, fsem_stoi_ctx_
                                   float* mos_out, int32_t* pesq_status_out, float* stoi_out, float* estoi_out,
                                   int32_t* kept_frames_out, int32_t* stoi_status_out);
 
+/* Device entry point for both metrics (device pointers, separate workspaces sized by the two
+ * *_workspace_bytes functions).  overlap = 0: the two kernel chains run back to back on `stream`;
+ * overlap = 1: the STOI chain runs on an internal second stream that starts after PESQ's IIR pass, so its
+ * HBM-bound resampler overlaps PESQ's shared-memory-bound spectrum kernel; overlap = 2: additionally cap the
+ * spectrum kernel at one CTA per SM.  `stream` is joined with the second stream before returning (stream-ordered,
+ * no host synchronisation).  Results are identical in all modes. */
+FSEM_API int fsem_pesq_stoi_score_f32(fsem_pesq_ctx_t* pesq, fsem_stoi_ctx_t* stoi, const fsem_batch_t* in,
+                             float* mos_out, int32_t* pesq_status_out, float* stoi_out, float* estoi_out,
+                             int32_t* kept_frames_out, int32_t* stoi_status_out, void* ws_pesq, size_t ws_pesq_bytes,
+                             void* ws_stoi, size_t ws_stoi_bytes, void* stream, int overlap);
+
 /* ------------------------------------------------------------------ LSD (adjacent metric on the same FFT)
  * Replaces LSD.compute_metric (fast_se_metrics/LSD.py:33-52): scale-matched log-spectral distance on a
  * centred Hann-512/256 STFT.  `hann512` is the HOST window torch.hann_window(512) (LSD.py:16).
