@@ -11,7 +11,8 @@ from .base import BaseMetric
 from .PESQ import PESQ
 from .STOI import STOI
 from .LSD import LSD
+from .SDR import SDR
 from .fused import score_pesq_stoi, score_pesq_stoi_tensors
 
-__all__ = ["BaseMetric", "PESQ", "STOI", "LSD", "score_pesq_stoi", "score_pesq_stoi_tensors"]
+__all__ = ["BaseMetric", "PESQ", "STOI", "LSD", "SDR", "score_pesq_stoi", "score_pesq_stoi_tensors"]
 __version__ = "0.1.0"

@@ -30,6 +30,7 @@ EXPORTS = [
     "fsem_stoi_create", "fsem_stoi_destroy", "fsem_stoi_workspace_bytes", "fsem_stoi_score_f32",
     "fsem_stoi_score_host_f32", "fsem_stoi_debug_taps", "fsem_pesq_stoi_score_host_f32",
     "fsem_pesq_stoi_score_f32", "fsem_lsd_create", "fsem_lsd_destroy", "fsem_lsd_workspace_bytes", "fsem_lsd_score_f32",
+    "fsem_sdr_workspace_bytes", "fsem_sdr_score_f32",
 ]
 
 
@@ -86,6 +87,9 @@ def load() -> C.CDLL:
     lib.fsem_lsd_workspace_bytes.argtypes = [vp, i64, i64]
     lib.fsem_lsd_workspace_bytes.restype = C.c_size_t
     lib.fsem_lsd_score_f32.argtypes = [vp, C.POINTER(Batch), fp, vp, C.c_size_t, vp]
+    lib.fsem_sdr_workspace_bytes.argtypes = [i64, i64]
+    lib.fsem_sdr_workspace_bytes.restype = C.c_size_t
+    lib.fsem_sdr_score_f32.argtypes = [C.POINTER(Batch), fp, vp, C.c_size_t, vp]
     lib.fsem_stoi_debug_taps.argtypes = [vp, i64, i64, vp, vp, fp, fp, C.POINTER(i64), vp]
     for name in EXPORTS:
         fn = getattr(lib, name)

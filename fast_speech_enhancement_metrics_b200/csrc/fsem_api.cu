@@ -11,6 +11,7 @@
 #include "fsem_pesq.cuh"
 #include "fsem_stoi.cuh"
 #include "fsem_lsd.cuh"
+#include "fsem_sdr.cuh"
 
 using namespace fsem;
 
@@ -51,11 +52,11 @@ inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 // ---- optional per-kernel timing with CUDA events on the launching stream (bench.py only; not thread-safe)
 enum KernelId {
     K_PESQ_FILTER = 0, K_PESQ_SPECTRUM, K_PESQ_BARK, K_STOI_RESAMPLE, K_STOI_ENERGY, K_STOI_COMPACT,
-    K_STOI_TOB, K_STOI_SEGMENT, K_STOI_FINALIZE, K_PESQ_RESAMPLE, K_LSD_FRAMES, K_COUNT
+    K_STOI_TOB, K_STOI_SEGMENT, K_STOI_FINALIZE, K_PESQ_RESAMPLE, K_LSD_FRAMES, K_SDR_CORR, K_SDR_SOLVE, K_COUNT
 };
 const char* const kKernelNames[K_COUNT] = {
     "pesq_filter_kernel", "pesq_spectrum_kernel", "pesq_bark_kernel", "stoi_resample_kernel", "stoi_energy_kernel",
-    "stoi_compact_kernel", "stoi_tob_kernel", "stoi_segment_kernel", "stoi_finalize_kernel", "pesq_resample_kernel", "lsd_frames_kernel"};
+    "stoi_compact_kernel", "stoi_tob_kernel", "stoi_segment_kernel", "stoi_finalize_kernel", "pesq_resample_kernel", "lsd_frames_kernel", "sdr_corr_kernel", "sdr_solve_kernel"};
 bool g_profile = false;
 struct ProfRecord { int id; cudaEvent_t start, stop; };
 std::vector<ProfRecord> g_prof_pending;
@@ -1040,5 +1041,54 @@ extern "C" int fsem_pesq_stoi_score_f32(fsem_pesq_ctx_t* pctx, fsem_stoi_ctx_t* 
     if (rc != FSEM_OK) { cudaStreamSynchronize(pctx->side); return rc; }
     FSEM_CUDA(cudaEventRecord(pctx->ev_join, pctx->side));
     FSEM_CUDA(cudaStreamWaitEvent(stream, pctx->ev_join, 0));
+    return FSEM_OK;
+}
+
+// ================================================================================================
+// SDR: fast_se_metrics/SDR.py:52-97
+// ================================================================================================
+namespace {
+struct SdrPlan { int nsuper; size_t off_energy, off_partial, total; };
+SdrPlan sdr_plan(int64_t batch, int64_t n) {
+    SdrPlan p{};
+    p.nsuper = (int)ceil_div(n > 0 ? n : 1, (int64_t)kSdrSuper * kSdrTile);
+    size_t off = 0;
+    p.off_energy = off;  off = align256(off + sizeof(double) * 2 * batch);
+    p.off_partial = off; off = align256(off + sizeof(double) * batch * p.nsuper * 2 * kSdrLags);
+    p.total = off;
+    return p;
+}
+}  // namespace
+
+extern "C" size_t fsem_sdr_workspace_bytes(int64_t batch, int64_t n) {
+    if (batch <= 0 || n <= 0) return 0;
+    return sdr_plan(batch, n).total;
+}
+
+extern "C" int fsem_sdr_score_f32(const fsem_batch_t* in, float* sdr_out, void* workspace, size_t workspace_bytes,
+                                  void* stream_v) {
+    if (!in || !sdr_out) return fail(FSEM_E_INVALID, "fsem_sdr_score_f32: null argument");
+    if (in->batch < 0 || in->n <= 0 || in->stride < in->n || in->n >= (int64_t(1) << 30))
+        return fail(FSEM_E_INVALID, "fsem_sdr_score_f32: bad shape");
+    if (in->batch == 0) return FSEM_OK;
+    if (!in->clean || !in->deg) return fail(FSEM_E_INVALID, "fsem_sdr_score_f32: null input");
+    if (in->batch > 65535) return fail(FSEM_E_INVALID, "fsem_sdr_score_f32: batch > 65535; split the batch");
+    const SdrPlan p = sdr_plan(in->batch, in->n);
+    if (!workspace || workspace_bytes < p.total)
+        return fail(FSEM_E_WORKSPACE, "fsem_sdr_score_f32: workspace %zu < %zu bytes", workspace_bytes, p.total);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    char* ws = static_cast<char*>(workspace);
+    double* energy = reinterpret_cast<double*>(ws + p.off_energy);
+    double* partial = reinterpret_cast<double*>(ws + p.off_partial);
+    sdr_norm_kernel<<<(unsigned)(2 * in->batch), 256, 0, stream>>>(in->clean, in->deg, in->lengths, in->batch, in->n,
+                                                                  in->stride, energy);
+    FSEM_LAUNCHED();
+    { ProfScope prof_(K_SDR_CORR, stream);
+      sdr_corr_kernel<<<dim3((unsigned)p.nsuper, (unsigned)in->batch), kSdrThreads, 0, stream>>>(
+          in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, p.nsuper, partial); }
+    FSEM_LAUNCHED();
+    { ProfScope prof_(K_SDR_SOLVE, stream);
+      sdr_solve_kernel<<<(unsigned)in->batch, kSdrSolveThreads, 0, stream>>>(partial, p.nsuper, energy, in->batch, sdr_out); }
+    FSEM_LAUNCHED();
     return FSEM_OK;
 }

@@ -132,7 +132,7 @@ FSEM_API int64_t fsem_launch_count(void);
 
 /* Optional per-kernel timing (CUDA events on the launching stream).  Bench/diagnostics only,
  * process-global and not thread-safe.  fsem_profile_read synchronises on the recorded events and
- * returns the accumulated device time and launch count of kernel `index` (0 <= index < 11). */
+ * returns the accumulated device time and launch count of kernel `index` (0 <= index < 13). */
 FSEM_API int fsem_profile_enable(int on);
 FSEM_API int fsem_profile_reset(void);
 FSEM_API int fsem_profile_read(int index, const char** name, double* total_ms, int64_t* launches);
@@ -205,6 +205,14 @@ FSEM_API int fsem_lsd_destroy(fsem_lsd_ctx_t* ctx);
 FSEM_API size_t fsem_lsd_workspace_bytes(const fsem_lsd_ctx_t* ctx, int64_t batch, int64_t n);
 FSEM_API int fsem_lsd_score_f32(fsem_lsd_ctx_t* ctx, const fsem_batch_t* in, float* lsd_out, void* workspace,
                        size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ SDR (adjacent metric)
+ * Replaces SDR.compute_metric (fast_se_metrics/SDR.py:72-97; filter_length 512, no zero-mean, no diagonal
+ * loading): unit-norm signals, 512 auto/cross-correlation lags, symmetric Toeplitz solve, coherence -> dB.
+ * Stateless: no context.  sdr_out[batch] fp32 and all batch pointers are DEVICE pointers. */
+FSEM_API size_t fsem_sdr_workspace_bytes(int64_t batch, int64_t n);
+FSEM_API int fsem_sdr_score_f32(const fsem_batch_t* in, float* sdr_out, void* workspace, size_t workspace_bytes,
+                       void* stream);
 
 #ifdef __cplusplus
 }

@@ -72,6 +72,20 @@ def lsd_cases():
     return cases
 
 
+def sdr_cases():
+    """SDR (fast_se_metrics/SDR.py): (clean, degraded, lengths)."""
+    cases = {}
+    c, d, _ = synth_batch(401, 6, 32000)
+    cases["speech2s"] = (c, d, None)
+    c, d, _ = synth_batch(402, 3, 160000)
+    cases["speech10s"] = (c, d, None)
+    c, d, _ = synth_batch(403, 4, 40001)
+    cases["ragged"] = (c, d, [40001, 20037, 2049, 33333])
+    cw = _white(404, 2, 16000)
+    cases["white_scaled"] = (cw, (0.1 * cw + 0.02 * _white(405, 2, 16000)).astype(np.float32), None)
+    return cases
+
+
 def stoi_cases():
     cases = {}
     c, d, _ = synth_batch(201, 8, 30000, fs=10000)

@@ -35,8 +35,8 @@ import importlib.util  # noqa: E402
 _spec = importlib.util.spec_from_file_location("golden_cases", os.path.join(HERE, "cases.py"))
 _cases = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(_cases)   # (the reference ships its own `tests` package, so import by path)
-pesq_cases, stoi_cases, pesq_rate_cases, lsd_cases = (_cases.pesq_cases, _cases.stoi_cases, _cases.pesq_rate_cases,
-                                                       _cases.lsd_cases)
+pesq_cases, stoi_cases, pesq_rate_cases, lsd_cases, sdr_cases = (
+    _cases.pesq_cases, _cases.stoi_cases, _cases.pesq_rate_cases, _cases.lsd_cases, _cases.sdr_cases)
 
 
 def run_pesq():
@@ -162,8 +162,24 @@ def run_lsd():
     np.savez_compressed(os.path.join(HERE, "golden_lsd.npz"), **out)
 
 
+def run_sdr():
+    from fast_se_metrics.SDR import SDR
+    out = {}
+    metric = SDR(16000, use_gpu=False)
+    for name, (clean, deg, lengths) in sdr_cases().items():
+        c, d = torch.from_numpy(clean), torch.from_numpy(deg)
+        if lengths is None:
+            res = [r["SDR"] for r in metric(c, d)]
+        else:
+            res = [metric(c[i:i + 1, :n], d[i:i + 1, :n])[0]["SDR"] for i, n in enumerate(lengths)]
+        out[name] = np.asarray(res, np.float64)
+        print("SDR", name, out[name])
+    np.savez_compressed(os.path.join(HERE, "golden_sdr.npz"), **out)
+
+
 if __name__ == "__main__":
     run_pesq()
     run_stoi()
     run_lsd()
+    run_sdr()
     print("golden fixtures written to", HERE)
