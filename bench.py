@@ -85,7 +85,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -329,6 +329,15 @@ def main():
     launches = _lib.launch_count() - launches0
     _lib.profile_enable(False)
     prof = _lib.profile_read()
+    if rank == 0 and len(sampler.lines) < 4:
+        # a short timed region can end before nvidia-smi has sampled a few times: keep the same load running (untimed)
+        # until there are enough samples to report the clocks under load
+        t_end = time.perf_counter() + 1.0
+        while time.perf_counter() < t_end and len(sampler.lines) < 6:
+            step_device()
+            torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=device)
     if world > 1:
