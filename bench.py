@@ -334,7 +334,8 @@ def main():
         # until there are enough samples to report the clocks under load
         t_end = time.perf_counter() + 1.0
         while time.perf_counter() < t_end and len(sampler.lines) < 6:
-            step_device()
+            pesq.score_tensors(clean, deg)          # rank-local work only: no collective outside the timed steps
+            stoi.score_tensors(clean, deg)
             torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
