@@ -193,7 +193,7 @@ def host_cores() -> int:
 
 
 # ------------------------------------------------------------------------------------------ reference arm
-def run_reference(args):
+def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -224,7 +224,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -245,8 +245,19 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    # stdout carries exactly ONE JSON line (rank 0): anything libraries print there (e.g. NCCL's version banner) is
+    # sent to stderr by pointing fd 1 at fd 2 until the line is written
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: dict):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, emit)
 
     import numpy as np
     import torch
@@ -451,7 +462,7 @@ def main():
         "roofline": roofline, "roofline_step": roofline_step, "kernels": kernels, "cpu_baseline": cpu,
         "finite_score_fraction": finite,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
