@@ -56,4 +56,6 @@ class LSD(BaseMetric):
         if not clean_speech.is_cuda:                                        # host tensors: plain upload (base.py:18)
             clean_speech = clean_speech.to(self.device, non_blocking=True)
             denoised_speech = denoised_speech.to(self.device, non_blocking=True)
+            if clean_speech.dtype != torch.float32:                             # int16 / float16 ingest: widen after the upload
+                clean_speech, denoised_speech = self.prepare_audio(clean_speech), self.prepare_audio(denoised_speech)
         return [{"LSD": v} for v in self.score_tensors(clean_speech, denoised_speech, lengths).cpu().tolist()]

@@ -60,19 +60,19 @@ class PESQ(BaseMetric):
         return mos, status
 
     def score_host(self, clean: torch.Tensor, deg: torch.Tensor, lengths=None):
-        """Host-resident scoring: CPU [B, n] float32 tensors in, CPU tensors out; the library
-        overlaps the host->device copies with compute."""
+        """Host-resident scoring: CPU [B, n] float32 / int16 / float16 tensors in, CPU tensors out; the
+        library overlaps the host->device copies with compute."""
         b, n = clean.shape
         lens = self._lengths_tensor(lengths, b, n, "cpu")
         mos = torch.empty(b, dtype=torch.float32)
         status = torch.empty(b, dtype=torch.int32)
         if clean.stride(0) != deg.stride(0) and b > 1:
             clean, deg = clean.contiguous(), deg.contiguous()
-        batch = _lib.Batch(clean.data_ptr(), deg.data_ptr(), lens.data_ptr() if lens is not None else None,
-                           b, n, clean.stride(0) if b > 1 else n)
         with torch.cuda.device(self.device):
-            self._check_score(self._lib.fsem_pesq_score_host_f32(self._ctx, C.byref(batch), mos.data_ptr(),
-                                                                status.data_ptr()))
+            self._check_score(self._lib.fsem_score_host(
+                self._ctx, None, clean.data_ptr(), deg.data_ptr(), _lib.dtype_code(clean.dtype),
+                lens.data_ptr() if lens is not None else None, b, n, clean.stride(0) if b > 1 else n,
+                mos.data_ptr(), status.data_ptr(), None, None, None, None))
         return mos, status
 
     @staticmethod

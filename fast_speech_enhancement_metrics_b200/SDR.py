@@ -41,4 +41,6 @@ class SDR(BaseMetric):
         if not clean_speech.is_cuda:
             clean_speech = clean_speech.to(self.device, non_blocking=True)
             denoised_speech = denoised_speech.to(self.device, non_blocking=True)
+            if clean_speech.dtype != torch.float32:                             # int16 / float16 ingest: widen after the upload
+                clean_speech, denoised_speech = self.prepare_audio(clean_speech), self.prepare_audio(denoised_speech)
         return [{"SDR": v} for v in self.score_tensors(clean_speech, denoised_speech, lengths).cpu().tolist()]

@@ -62,6 +62,7 @@ class STOI(BaseMetric):
         return scores, kept, status
 
     def score_host(self, clean: torch.Tensor, deg: torch.Tensor, lengths=None):
+        """Host-resident scoring: CPU [B, n] float32 / int16 / float16 tensors in, CPU tensors out."""
         b, n = clean.shape
         lens = self._lengths_tensor(lengths, b, n, "cpu")
         scores = torch.empty(2, b, dtype=torch.float32)
@@ -69,11 +70,11 @@ class STOI(BaseMetric):
         status = torch.empty(b, dtype=torch.int32)
         if clean.stride(0) != deg.stride(0) and b > 1:
             clean, deg = clean.contiguous(), deg.contiguous()
-        batch = _lib.Batch(clean.data_ptr(), deg.data_ptr(), lens.data_ptr() if lens is not None else None,
-                           b, n, clean.stride(0) if b > 1 else n)
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.fsem_stoi_score_host_f32(self._ctx, C.byref(batch), scores[0].data_ptr(),
-                                                          scores[1].data_ptr(), kept.data_ptr(), status.data_ptr()))
+            _lib.check(self._lib.fsem_score_host(
+                None, self._ctx, clean.data_ptr(), deg.data_ptr(), _lib.dtype_code(clean.dtype),
+                lens.data_ptr() if lens is not None else None, b, n, clean.stride(0) if b > 1 else n,
+                None, None, scores[0].data_ptr(), scores[1].data_ptr(), kept.data_ptr(), status.data_ptr()))
         return scores, kept, status
 
     def compute_metric(self, clean_speech, denoised_speech, lengths=None) -> list[dict[str, float]]:

@@ -30,8 +30,21 @@ EXPORTS = [
     "fsem_stoi_create", "fsem_stoi_destroy", "fsem_stoi_workspace_bytes", "fsem_stoi_score_f32",
     "fsem_stoi_score_host_f32", "fsem_stoi_debug_taps", "fsem_pesq_stoi_score_host_f32",
     "fsem_pesq_stoi_score_f32", "fsem_lsd_create", "fsem_lsd_destroy", "fsem_lsd_workspace_bytes", "fsem_lsd_score_f32",
-    "fsem_sdr_workspace_bytes", "fsem_sdr_score_f32",
+    "fsem_sdr_workspace_bytes", "fsem_sdr_score_f32", "fsem_ingest_f32", "fsem_score_host",
 ]
+
+# ingest formats (include/fsem.h FSEM_DTYPE_*)
+DTYPE_F32, DTYPE_I16, DTYPE_F16 = 0, 1, 2
+
+
+def dtype_code(dtype) -> int:
+    """torch dtype -> FSEM_DTYPE_*; raises like the reference for anything else (float64 fails inside
+    lfilter / stft there with "expected scalar type Float")."""
+    import torch
+    codes = {torch.float32: DTYPE_F32, torch.int16: DTYPE_I16, torch.float16: DTYPE_F16}
+    if dtype not in codes:
+        raise RuntimeError("expected scalar type Float but found %s" % str(dtype).replace("torch.", ""))
+    return codes[dtype]
 
 
 class Batch(C.Structure):
@@ -91,6 +104,8 @@ def load() -> C.CDLL:
     lib.fsem_sdr_workspace_bytes.restype = C.c_size_t
     lib.fsem_sdr_score_f32.argtypes = [C.POINTER(Batch), fp, vp, C.c_size_t, vp]
     lib.fsem_stoi_debug_taps.argtypes = [vp, i64, i64, vp, vp, fp, fp, C.POINTER(i64), vp]
+    lib.fsem_ingest_f32.argtypes = [vp, C.c_int, i64, i64, i64, fp, i64, vp]
+    lib.fsem_score_host.argtypes = [vp, vp, vp, vp, C.c_int, i32p, i64, i64, i64, fp, i32p, fp, fp, i32p, i32p]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("fsem_version",):

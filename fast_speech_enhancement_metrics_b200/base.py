@@ -13,10 +13,14 @@ all deliberate:
 * resample-on-ingest (base.py:19-20) is not a separate torchaudio op: STOI fuses
   it into its first kernel;
 * optional `lengths=` (per-item valid samples of a padded batch); `None` gives
-  exactly the reference behaviour.
+  exactly the reference behaviour;
+* ingest formats: besides float32, int16 PCM and float16 tensors are accepted and
+  widened to float32 on the device with a value-preserving cast (bit-identical scores to `x.float()`); a CPU
+  batch then crosses PCIe at 2 bytes per sample.  Anything else raises like the reference.
 """
 from __future__ import annotations
 
+import ctypes as C
 from abc import ABC, abstractmethod
 
 import torch
@@ -40,17 +44,30 @@ class BaseMetric(ABC):
 
     # ------------------------------------------------------------------ reference API
     def prepare_audio(self, audio: torch.Tensor) -> torch.Tensor:
-        """base.py:16-21: at least 2-D, float32, unit stride along time.  The tensor stays
-        where it is (no implicit device move); inputs are never modified."""
+        """base.py:16-21: at least 2-D, unit stride along time.  The tensor stays where it is (no
+        implicit device move); inputs are never modified.  float32 is consumed in place; int16 / float16
+        CUDA tensors are widened to a float32 copy here (fsem_ingest_f32), CPU ones keep their dtype and
+        are widened by the library after the upload."""
         audio = torch.atleast_2d(audio)
         if audio.dim() != 2:
             raise Exception("expected a [batch, samples] tensor")
-        if audio.dtype != torch.float32:
-            # the reference fails inside lfilter / stft with "expected scalar type Float"
-            raise RuntimeError("expected scalar type Float but found %s" % str(audio.dtype).replace("torch.", ""))
+        code = _lib.dtype_code(audio.dtype)           # raises for float64 & co like the reference
         if audio.stride(1) != 1 or (audio.shape[0] > 1 and audio.stride(0) < audio.shape[1]):
             audio = audio.contiguous()
+        if code != _lib.DTYPE_F32 and audio.is_cuda:
+            audio = self._ingest(audio, code)
         return audio
+
+    def _ingest(self, audio: torch.Tensor, code: int) -> torch.Tensor:
+        b, n = audio.shape
+        out = torch.empty(b, (n + 3) // 4 * 4, dtype=torch.float32, device=audio.device)[:, :n]
+        if b and n:
+            with torch.cuda.device(audio.device):
+                _lib.check(self._lib.fsem_ingest_f32(
+                    audio.data_ptr(), code, b, n, audio.stride(0) if b > 1 else max(n, audio.stride(0)),
+                    out.data_ptr(), out.stride(0),
+                    C.c_void_p(torch.cuda.current_stream(audio.device).cuda_stream)))
+        return out
 
     def prepare_inputs(self, clean_speech, denoised_speech):
         if clean_speech is not None and clean_speech.shape != denoised_speech.shape:
@@ -60,6 +77,8 @@ class BaseMetric(ABC):
         denoised_speech = self.prepare_audio(denoised_speech)
         if clean_speech is not None and clean_speech.device != denoised_speech.device:
             raise Exception("`clean_speech` and `denoised_speech` should be on the same device.")
+        if clean_speech is not None and clean_speech.dtype != denoised_speech.dtype:
+            raise Exception("`clean_speech` and `denoised_speech` should have the same dtype.")
         return clean_speech, denoised_speech
 
     @abstractmethod

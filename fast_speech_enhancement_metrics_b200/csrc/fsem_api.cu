@@ -12,6 +12,7 @@
 #include "fsem_stoi.cuh"
 #include "fsem_lsd.cuh"
 #include "fsem_sdr.cuh"
+#include "fsem_ingest.cuh"
 
 using namespace fsem;
 
@@ -52,11 +53,11 @@ inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 // ---- optional per-kernel timing with CUDA events on the launching stream (bench.py only; not thread-safe)
 enum KernelId {
     K_PESQ_FILTER = 0, K_PESQ_SPECTRUM, K_PESQ_BARK, K_STOI_RESAMPLE, K_STOI_ENERGY, K_STOI_COMPACT,
-    K_STOI_TOB, K_STOI_SEGMENT, K_STOI_FINALIZE, K_PESQ_RESAMPLE, K_LSD_FRAMES, K_SDR_CORR, K_SDR_SOLVE, K_COUNT
+    K_STOI_TOB, K_STOI_SEGMENT, K_STOI_FINALIZE, K_PESQ_RESAMPLE, K_LSD_FRAMES, K_SDR_CORR, K_SDR_SOLVE, K_INGEST, K_COUNT
 };
 const char* const kKernelNames[K_COUNT] = {
     "pesq_filter_kernel", "pesq_spectrum_kernel", "pesq_bark_kernel", "stoi_resample_kernel", "stoi_energy_kernel",
-    "stoi_compact_kernel", "stoi_tob_kernel", "stoi_segment_kernel", "stoi_finalize_kernel", "pesq_resample_kernel", "lsd_frames_kernel", "sdr_corr_kernel", "sdr_solve_kernel"};
+    "stoi_compact_kernel", "stoi_tob_kernel", "stoi_segment_kernel", "stoi_finalize_kernel", "pesq_resample_kernel", "lsd_frames_kernel", "sdr_corr_kernel", "sdr_solve_kernel", "ingest_kernel"};
 bool g_profile = false;
 struct ProfRecord { int id; cudaEvent_t start, stop; };
 std::vector<ProfRecord> g_prof_pending;
@@ -492,58 +493,6 @@ extern "C" int fsem_pesq_debug_taps(fsem_pesq_ctx_t* ctx, int64_t batch, int64_t
     return FSEM_OK;
 }
 
-extern "C" int fsem_pesq_score_host_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in, float* mos_out,
-                                        int32_t* status_out) {
-    if (!ctx || !in || !mos_out) return fail(FSEM_E_INVALID, "fsem_pesq_score_host_f32: null argument");
-    if (in->batch < 0 || in->n < 0 || in->stride < in->n)
-        return fail(FSEM_E_INVALID, "fsem_pesq_score_host_f32: bad shape");
-    if (in->batch == 0) return FSEM_OK;
-    if (!in->lengths && pesq_num_frames(pesq_plan(ctx, 1, in->n).n) < 20)
-        return fail(FSEM_E_TOO_SHORT, "PESQ needs at least 20 frames of 512/256 samples at 16 kHz; n=%lld is too short",
-                    (long long)in->n);
-    int rc = ctx->pipe.init();
-    if (rc != FSEM_OK) return rc;
-    const int64_t n = in->n, dstride = round_up(n, 4);
-    const int64_t per = host_chunk_items(in->batch, n);
-    const size_t sig_bytes = align256(sizeof(float) * per * dstride);
-    const size_t in_bytes = 2 * sig_bytes + align256(sizeof(int32_t) * per);
-    const size_t ws_bytes = fsem_pesq_workspace_bytes(ctx, per, n);
-    const size_t colb = align256(sizeof(float) * in->batch);
-    rc = ctx->pipe.reserve(in_bytes, ws_bytes, 2 * colb);
-    if (rc != FSEM_OK) return rc;
-    HostPipe& P = ctx->pipe;
-    int64_t done_chunks = 0;
-    for (int64_t i0 = 0; i0 < in->batch; i0 += per, ++done_chunks) {
-        const int slot = (int)(done_chunks & 1);
-        const int64_t cnt = (in->batch - i0 < per) ? (in->batch - i0) : per;
-        char* base = static_cast<char*>(P.in[slot]);
-        float* d_clean = reinterpret_cast<float*>(base);
-        float* d_deg = reinterpret_cast<float*>(base + sig_bytes);
-        int32_t* d_len = reinterpret_cast<int32_t*>(base + 2 * sig_bytes);
-        float* d_mos = reinterpret_cast<float*>(P.out) + i0;
-        int32_t* d_status = reinterpret_cast<int32_t*>(static_cast<char*>(P.out) + colb) + i0;
-        if (done_chunks >= 2) FSEM_CUDA(cudaStreamWaitEvent(P.copy, P.done[slot], 0));   // staging slot free again
-        FSEM_CUDA(copy_rows_h2d(d_clean, dstride, in->clean + i0 * in->stride, in->stride, n, cnt, P.copy));
-        FSEM_CUDA(copy_rows_h2d(d_deg, dstride, in->deg + i0 * in->stride, in->stride, n, cnt, P.copy));
-        if (in->lengths)
-            FSEM_CUDA(cudaMemcpyAsync(d_len, in->lengths + i0, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, P.copy));
-        FSEM_CUDA(cudaEventRecord(P.copied[slot], P.copy));
-        FSEM_CUDA(cudaStreamWaitEvent(P.compute, P.copied[slot], 0));
-        fsem_batch_t dev{d_clean, d_deg, in->lengths ? d_len : nullptr, cnt, n, dstride};
-        rc = fsem_pesq_score_f32(ctx, &dev, d_mos, d_status, P.ws, P.ws_bytes, P.compute);
-        if (rc != FSEM_OK) { cudaStreamSynchronize(P.copy); cudaStreamSynchronize(P.compute); return rc; }
-        FSEM_CUDA(cudaEventRecord(P.done[slot], P.compute));
-    }
-    // one read-back of the score columns (a per-chunk copy into pageable memory would stall the pipeline)
-    FSEM_CUDA(cudaMemcpyAsync(mos_out, P.out, sizeof(float) * in->batch, cudaMemcpyDeviceToHost, P.compute));
-    if (status_out)
-        FSEM_CUDA(cudaMemcpyAsync(status_out, static_cast<char*>(P.out) + colb, sizeof(int32_t) * in->batch,
-                                  cudaMemcpyDeviceToHost, P.compute));
-    FSEM_CUDA(cudaStreamSynchronize(P.copy));
-    FSEM_CUDA(cudaStreamSynchronize(P.compute));
-    return FSEM_OK;
-}
-
 // ================================================================================================
 // STOI
 // ================================================================================================
@@ -790,132 +739,178 @@ extern "C" int fsem_stoi_debug_taps(fsem_stoi_ctx_t* ctx, int64_t batch, int64_t
     return FSEM_OK;
 }
 
-extern "C" int fsem_stoi_score_host_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t* in, float* stoi_out,
-                                        float* estoi_out, int32_t* kept_frames_out, int32_t* status_out) {
-    if (!ctx || !in || !stoi_out || !estoi_out) return fail(FSEM_E_INVALID, "fsem_stoi_score_host_f32: null argument");
-    if (in->batch < 0 || in->n < 0 || in->stride < in->n)
-        return fail(FSEM_E_INVALID, "fsem_stoi_score_host_f32: bad shape");
-    if (in->batch == 0) return FSEM_OK;
-    int rc = ctx->pipe.init();
+// ================================================================================================
+// Host entry points.  One pipeline serves PESQ only, STOI only and PESQ + STOI on one upload (SURVEY.md 8f rank 1:
+// callers of the reference always score both metrics on the same pair of tensors, README.md:29-30,
+// benchmark_metrics.py:22,24; with host tensors the host->device copy dominates, so every chunk is copied ONCE and
+// all selected kernel chains run on it), for every ingest dtype.
+// ================================================================================================
+namespace {
+
+size_t dtype_size(int dtype) {
+    return dtype == FSEM_DTYPE_F32 ? sizeof(float) : (dtype == FSEM_DTYPE_I16 || dtype == FSEM_DTYPE_F16) ? 2 : 0;
+}
+
+// device rows of `dtype` -> device fp32 rows on `stream`
+int launch_ingest(const void* src, int dtype, int64_t rows, int64_t n, int64_t sstride, float* dst, int64_t dstride,
+                  cudaStream_t stream) {
+    if (rows <= 0 || n <= 0) return FSEM_OK;
+    if (dtype == FSEM_DTYPE_F32) {
+        FSEM_CUDA(cudaMemcpy2DAsync(dst, dstride * sizeof(float), src, sstride * sizeof(float), n * sizeof(float), rows,
+                                    cudaMemcpyDeviceToDevice, stream));
+        return FSEM_OK;
+    }
+    const bool vec = aligned16(src) && aligned16(dst) && sstride % 8 == 0 && dstride % 4 == 0;
+    const int64_t groups = rows * ceil_div(n, 8);
+    int64_t grid = ceil_div(groups, 256);
+    if (grid > (1 << 20)) grid = 1 << 20;
+    { ProfScope prof_(K_INGEST, stream);
+      if (dtype == FSEM_DTYPE_I16) {
+          const int16_t* s = static_cast<const int16_t*>(src);
+          if (vec) ingest_kernel<int16_t, true><<<(unsigned)grid, 256, 0, stream>>>(s, sstride, dst, dstride, rows, n);
+          else ingest_kernel<int16_t, false><<<(unsigned)grid, 256, 0, stream>>>(s, sstride, dst, dstride, rows, n);
+      } else {
+          const __half* s = static_cast<const __half*>(src);
+          if (vec) ingest_kernel<__half, true><<<(unsigned)grid, 256, 0, stream>>>(s, sstride, dst, dstride, rows, n);
+          else ingest_kernel<__half, false><<<(unsigned)grid, 256, 0, stream>>>(s, sstride, dst, dstride, rows, n);
+      } }
+    FSEM_LAUNCHED();
+    return FSEM_OK;
+}
+
+int score_host_any(const char* who, fsem_pesq_ctx* pctx, fsem_stoi_ctx* sctx, const void* clean, const void* deg,
+                   int dtype, const int32_t* lengths, int64_t batch, int64_t n, int64_t stride, float* mos_out,
+                   int32_t* pesq_status_out, float* stoi_out, float* estoi_out, int32_t* kept_frames_out,
+                   int32_t* stoi_status_out) {
+    if ((!pctx && !sctx) || !clean || !deg || (pctx && !mos_out) || (sctx && (!stoi_out || !estoi_out)))
+        return fail(FSEM_E_INVALID, "%s: null argument", who);
+    const size_t es = dtype_size(dtype);
+    if (es == 0) return fail(FSEM_E_INVALID, "%s: unknown dtype %d", who, dtype);
+    if (batch < 0 || n < 0 || stride < n) return fail(FSEM_E_INVALID, "%s: bad shape", who);
+    if (batch == 0) return FSEM_OK;
+    if (pctx && !lengths && pesq_num_frames(pesq_plan(pctx, 1, n).n) < 20)
+        return fail(FSEM_E_TOO_SHORT, "PESQ needs at least 20 frames of 512/256 samples at 16 kHz; n=%lld is too short",
+                    (long long)n);
+    HostPipe& P = pctx ? pctx->pipe : sctx->pipe;
+    int rc = P.init();
     if (rc != FSEM_OK) return rc;
-    const int64_t n = in->n, dstride = round_up(n, 4);
-    const int64_t per = host_chunk_items(in->batch, n);
-    const size_t sig_bytes = align256(sizeof(float) * per * dstride);
-    const size_t in_bytes = 2 * sig_bytes + align256(sizeof(int32_t) * per);
-    const size_t ws_bytes = fsem_stoi_workspace_bytes(ctx, per, n);
-    const size_t col = align256(sizeof(float) * in->batch);
-    rc = ctx->pipe.reserve(in_bytes, ws_bytes, 4 * col);
+    const bool widen = dtype != FSEM_DTYPE_F32;
+    const int64_t dstride = round_up(n, 4);                          // fp32 rows the kernels read
+    const int64_t rstride = widen ? round_up(n, 8) : dstride;        // staged rows as uploaded (16-byte aligned)
+    const int64_t per = host_chunk_items(batch, n);
+    const size_t raw_sig = align256(es * per * rstride);
+    const size_t in_bytes = 2 * raw_sig + align256(sizeof(int32_t) * per);
+    // 2-byte dtypes are widened into ONE fp32 copy of the chunk: the compute stream is serial, only the raw
+    // staging slots are double-buffered against the copy stream
+    const size_t conv_sig = widen ? align256(sizeof(float) * per * dstride) : 0;
+    const size_t ws_pesq = pctx ? align256(fsem_pesq_workspace_bytes(pctx, per, n)) : 0;
+    const size_t ws_stoi = sctx ? align256(fsem_stoi_workspace_bytes(sctx, per, n)) : 0;
+    const size_t col = align256(sizeof(float) * batch);
+    rc = P.reserve(in_bytes, 2 * conv_sig + ws_pesq + ws_stoi, 6 * col);
     if (rc != FSEM_OK) return rc;
-    HostPipe& P = ctx->pipe;
+    char* const ob = static_cast<char*>(P.out);
+    char* const wsb = static_cast<char*>(P.ws);
+    const char* h_clean = static_cast<const char*>(clean);
+    const char* h_deg = static_cast<const char*>(deg);
+    auto upload = [&](void* dst, const char* src, int64_t cnt) -> cudaError_t {
+        if (stride == n && rstride == n)
+            return cudaMemcpyAsync(dst, src, es * n * cnt, cudaMemcpyHostToDevice, P.copy);
+        return cudaMemcpy2DAsync(dst, rstride * es, src, stride * es, n * es, cnt, cudaMemcpyHostToDevice, P.copy);
+    };
     int64_t done_chunks = 0;
-    for (int64_t i0 = 0; i0 < in->batch; i0 += per, ++done_chunks) {
+    for (int64_t i0 = 0; i0 < batch; i0 += per, ++done_chunks) {
         const int slot = (int)(done_chunks & 1);
-        const int64_t cnt = (in->batch - i0 < per) ? (in->batch - i0) : per;
+        const int64_t cnt = (batch - i0 < per) ? (batch - i0) : per;
         char* base = static_cast<char*>(P.in[slot]);
-        float* d_clean = reinterpret_cast<float*>(base);
-        float* d_deg = reinterpret_cast<float*>(base + sig_bytes);
-        int32_t* d_len = reinterpret_cast<int32_t*>(base + 2 * sig_bytes);
-        char* ob = static_cast<char*>(P.out);
-        float* d_stoi = reinterpret_cast<float*>(ob) + i0;
-        float* d_estoi = reinterpret_cast<float*>(ob + col) + i0;
-        int32_t* d_kept = reinterpret_cast<int32_t*>(ob + 2 * col) + i0;
-        int32_t* d_status = reinterpret_cast<int32_t*>(ob + 3 * col) + i0;
-        if (done_chunks >= 2) FSEM_CUDA(cudaStreamWaitEvent(P.copy, P.done[slot], 0));
-        FSEM_CUDA(copy_rows_h2d(d_clean, dstride, in->clean + i0 * in->stride, in->stride, n, cnt, P.copy));
-        FSEM_CUDA(copy_rows_h2d(d_deg, dstride, in->deg + i0 * in->stride, in->stride, n, cnt, P.copy));
-        if (in->lengths)
-            FSEM_CUDA(cudaMemcpyAsync(d_len, in->lengths + i0, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, P.copy));
+        int32_t* d_len = reinterpret_cast<int32_t*>(base + 2 * raw_sig);
+        if (done_chunks >= 2) FSEM_CUDA(cudaStreamWaitEvent(P.copy, P.done[slot], 0));   // staging slot free again
+        FSEM_CUDA(upload(base, h_clean + (size_t)i0 * stride * es, cnt));
+        FSEM_CUDA(upload(base + raw_sig, h_deg + (size_t)i0 * stride * es, cnt));
+        if (lengths)
+            FSEM_CUDA(cudaMemcpyAsync(d_len, lengths + i0, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, P.copy));
         FSEM_CUDA(cudaEventRecord(P.copied[slot], P.copy));
         FSEM_CUDA(cudaStreamWaitEvent(P.compute, P.copied[slot], 0));
-        fsem_batch_t dev{d_clean, d_deg, in->lengths ? d_len : nullptr, cnt, n, dstride};
-        rc = fsem_stoi_score_f32(ctx, &dev, d_stoi, d_estoi, d_kept, d_status, P.ws, P.ws_bytes, P.compute);
+        float* d_clean = reinterpret_cast<float*>(base);
+        float* d_deg = reinterpret_cast<float*>(base + raw_sig);
+        if (widen) {
+            d_clean = reinterpret_cast<float*>(wsb);
+            d_deg = reinterpret_cast<float*>(wsb + conv_sig);
+            rc = launch_ingest(base, dtype, cnt, n, rstride, d_clean, dstride, P.compute);
+            if (rc == FSEM_OK) rc = launch_ingest(base + raw_sig, dtype, cnt, n, rstride, d_deg, dstride, P.compute);
+        }
+        fsem_batch_t dev{d_clean, d_deg, lengths ? d_len : nullptr, cnt, n, dstride};
+        if (rc == FSEM_OK && pctx)
+            rc = fsem_pesq_score_f32(pctx, &dev, reinterpret_cast<float*>(ob) + i0,
+                                     reinterpret_cast<int32_t*>(ob + col) + i0, wsb + 2 * conv_sig, ws_pesq, P.compute);
+        if (rc == FSEM_OK && sctx)
+            rc = fsem_stoi_score_f32(sctx, &dev, reinterpret_cast<float*>(ob + 2 * col) + i0,
+                                     reinterpret_cast<float*>(ob + 3 * col) + i0,
+                                     reinterpret_cast<int32_t*>(ob + 4 * col) + i0,
+                                     reinterpret_cast<int32_t*>(ob + 5 * col) + i0, wsb + 2 * conv_sig + ws_pesq, ws_stoi,
+                                     P.compute);
         if (rc != FSEM_OK) { cudaStreamSynchronize(P.copy); cudaStreamSynchronize(P.compute); return rc; }
         FSEM_CUDA(cudaEventRecord(P.done[slot], P.compute));
     }
-    {
-        char* ob = static_cast<char*>(P.out);
-        const size_t nb = sizeof(float) * in->batch;
-        FSEM_CUDA(cudaMemcpyAsync(stoi_out, ob, nb, cudaMemcpyDeviceToHost, P.compute));
-        FSEM_CUDA(cudaMemcpyAsync(estoi_out, ob + col, nb, cudaMemcpyDeviceToHost, P.compute));
-        if (kept_frames_out) FSEM_CUDA(cudaMemcpyAsync(kept_frames_out, ob + 2 * col, nb, cudaMemcpyDeviceToHost, P.compute));
-        if (status_out) FSEM_CUDA(cudaMemcpyAsync(status_out, ob + 3 * col, nb, cudaMemcpyDeviceToHost, P.compute));
+    // one read-back of the score columns (a per-chunk copy into pageable memory would stall the pipeline)
+    const size_t nb = sizeof(float) * batch;
+    auto readback = [&](void* dst, size_t column) -> cudaError_t {
+        return dst ? cudaMemcpyAsync(dst, ob + column * col, nb, cudaMemcpyDeviceToHost, P.compute) : cudaSuccess;
+    };
+    if (pctx) {
+        FSEM_CUDA(readback(mos_out, 0));
+        FSEM_CUDA(readback(pesq_status_out, 1));
+    }
+    if (sctx) {
+        FSEM_CUDA(readback(stoi_out, 2));
+        FSEM_CUDA(readback(estoi_out, 3));
+        FSEM_CUDA(readback(kept_frames_out, 4));
+        FSEM_CUDA(readback(stoi_status_out, 5));
     }
     FSEM_CUDA(cudaStreamSynchronize(P.copy));
     FSEM_CUDA(cudaStreamSynchronize(P.compute));
     return FSEM_OK;
 }
 
-// ================================================================================================
-// PESQ + STOI on one upload: callers of the reference always score both metrics on the
-// same pair of tensors (README.md:29-30, benchmark_metrics.py:22,24); with host tensors the host->device copy
-// dominates, so this entry point copies every chunk ONCE and runs both kernel pipelines on it.
-// ================================================================================================
+}  // namespace
+
+extern "C" int fsem_ingest_f32(const void* src, int dtype, int64_t rows, int64_t n, int64_t src_stride, float* dst,
+                               int64_t dst_stride, void* stream) {
+    if (!src || !dst) return fail(FSEM_E_INVALID, "fsem_ingest_f32: null argument");
+    if (dtype_size(dtype) == 0) return fail(FSEM_E_INVALID, "fsem_ingest_f32: unknown dtype %d", dtype);
+    if (rows < 0 || n < 0 || src_stride < n || dst_stride < n) return fail(FSEM_E_INVALID, "fsem_ingest_f32: bad shape");
+    return launch_ingest(src, dtype, rows, n, src_stride, dst, dst_stride, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int fsem_score_host(fsem_pesq_ctx_t* pesq, fsem_stoi_ctx_t* stoi, const void* clean, const void* deg, int dtype,
+                               const int32_t* lengths, int64_t batch, int64_t n, int64_t stride, float* mos_out,
+                               int32_t* pesq_status_out, float* stoi_out, float* estoi_out, int32_t* kept_frames_out,
+                               int32_t* stoi_status_out) {
+    return score_host_any("fsem_score_host", pesq, stoi, clean, deg, dtype, lengths, batch, n, stride, mos_out,
+                          pesq_status_out, stoi_out, estoi_out, kept_frames_out, stoi_status_out);
+}
+
+extern "C" int fsem_pesq_score_host_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in, float* mos_out,
+                                        int32_t* status_out) {
+    if (!ctx || !in) return fail(FSEM_E_INVALID, "fsem_pesq_score_host_f32: null argument");
+    return score_host_any("fsem_pesq_score_host_f32", ctx, nullptr, in->clean, in->deg, FSEM_DTYPE_F32, in->lengths,
+                          in->batch, in->n, in->stride, mos_out, status_out, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int fsem_stoi_score_host_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t* in, float* stoi_out,
+                                        float* estoi_out, int32_t* kept_frames_out, int32_t* status_out) {
+    if (!ctx || !in) return fail(FSEM_E_INVALID, "fsem_stoi_score_host_f32: null argument");
+    return score_host_any("fsem_stoi_score_host_f32", nullptr, ctx, in->clean, in->deg, FSEM_DTYPE_F32, in->lengths,
+                          in->batch, in->n, in->stride, nullptr, nullptr, stoi_out, estoi_out, kept_frames_out,
+                          status_out);
+}
+
 extern "C" int fsem_pesq_stoi_score_host_f32(fsem_pesq_ctx_t* pctx, fsem_stoi_ctx_t* sctx, const fsem_batch_t* in,
                                              float* mos_out, int32_t* pesq_status_out, float* stoi_out,
                                              float* estoi_out, int32_t* kept_frames_out, int32_t* stoi_status_out) {
-    if (!pctx || !sctx || !in || !mos_out || !stoi_out || !estoi_out)
-        return fail(FSEM_E_INVALID, "fsem_pesq_stoi_score_host_f32: null argument");
-    if (in->batch < 0 || in->n < 0 || in->stride < in->n)
-        return fail(FSEM_E_INVALID, "fsem_pesq_stoi_score_host_f32: bad shape");
-    if (in->batch == 0) return FSEM_OK;
-    if (!in->lengths && pesq_num_frames(pesq_plan(pctx, 1, in->n).n) < 20)
-        return fail(FSEM_E_TOO_SHORT, "PESQ needs at least 20 frames of 512/256 samples at 16 kHz; n=%lld is too short",
-                    (long long)in->n);
-    int rc = pctx->pipe.init();
-    if (rc != FSEM_OK) return rc;
-    const int64_t n = in->n, dstride = round_up(n, 4);
-    const int64_t per = host_chunk_items(in->batch, n);
-    const size_t sig_bytes = align256(sizeof(float) * per * dstride);
-    const size_t in_bytes = 2 * sig_bytes + align256(sizeof(int32_t) * per);
-    const size_t ws_pesq = align256(fsem_pesq_workspace_bytes(pctx, per, n));
-    const size_t ws_stoi = align256(fsem_stoi_workspace_bytes(sctx, per, n));
-    const size_t col = align256(sizeof(float) * in->batch);
-    rc = pctx->pipe.reserve(in_bytes, ws_pesq + ws_stoi, 6 * col);
-    if (rc != FSEM_OK) return rc;
-    HostPipe& P = pctx->pipe;
-    int64_t done_chunks = 0;
-    for (int64_t i0 = 0; i0 < in->batch; i0 += per, ++done_chunks) {
-        const int slot = (int)(done_chunks & 1);
-        const int64_t cnt = (in->batch - i0 < per) ? (in->batch - i0) : per;
-        char* base = static_cast<char*>(P.in[slot]);
-        float* d_clean = reinterpret_cast<float*>(base);
-        float* d_deg = reinterpret_cast<float*>(base + sig_bytes);
-        int32_t* d_len = reinterpret_cast<int32_t*>(base + 2 * sig_bytes);
-        char* ob = static_cast<char*>(P.out);
-        float* d_mos = reinterpret_cast<float*>(ob) + i0;
-        int32_t* d_pst = reinterpret_cast<int32_t*>(ob + col) + i0;
-        float* d_stoi = reinterpret_cast<float*>(ob + 2 * col) + i0;
-        float* d_estoi = reinterpret_cast<float*>(ob + 3 * col) + i0;
-        int32_t* d_kept = reinterpret_cast<int32_t*>(ob + 4 * col) + i0;
-        int32_t* d_sst = reinterpret_cast<int32_t*>(ob + 5 * col) + i0;
-        if (done_chunks >= 2) FSEM_CUDA(cudaStreamWaitEvent(P.copy, P.done[slot], 0));
-        FSEM_CUDA(copy_rows_h2d(d_clean, dstride, in->clean + i0 * in->stride, in->stride, n, cnt, P.copy));
-        FSEM_CUDA(copy_rows_h2d(d_deg, dstride, in->deg + i0 * in->stride, in->stride, n, cnt, P.copy));
-        if (in->lengths)
-            FSEM_CUDA(cudaMemcpyAsync(d_len, in->lengths + i0, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, P.copy));
-        FSEM_CUDA(cudaEventRecord(P.copied[slot], P.copy));
-        FSEM_CUDA(cudaStreamWaitEvent(P.compute, P.copied[slot], 0));
-        fsem_batch_t dev{d_clean, d_deg, in->lengths ? d_len : nullptr, cnt, n, dstride};
-        rc = fsem_pesq_score_f32(pctx, &dev, d_mos, d_pst, P.ws, ws_pesq, P.compute);
-        if (rc == FSEM_OK)
-            rc = fsem_stoi_score_f32(sctx, &dev, d_stoi, d_estoi, d_kept, d_sst, static_cast<char*>(P.ws) + ws_pesq,
-                                     ws_stoi, P.compute);
-        if (rc != FSEM_OK) { cudaStreamSynchronize(P.copy); cudaStreamSynchronize(P.compute); return rc; }
-        FSEM_CUDA(cudaEventRecord(P.done[slot], P.compute));
-    }
-    {
-        char* ob = static_cast<char*>(P.out);
-        const size_t nb = sizeof(float) * in->batch;
-        FSEM_CUDA(cudaMemcpyAsync(mos_out, ob, nb, cudaMemcpyDeviceToHost, P.compute));
-        if (pesq_status_out) FSEM_CUDA(cudaMemcpyAsync(pesq_status_out, ob + col, nb, cudaMemcpyDeviceToHost, P.compute));
-        FSEM_CUDA(cudaMemcpyAsync(stoi_out, ob + 2 * col, nb, cudaMemcpyDeviceToHost, P.compute));
-        FSEM_CUDA(cudaMemcpyAsync(estoi_out, ob + 3 * col, nb, cudaMemcpyDeviceToHost, P.compute));
-        if (kept_frames_out) FSEM_CUDA(cudaMemcpyAsync(kept_frames_out, ob + 4 * col, nb, cudaMemcpyDeviceToHost, P.compute));
-        if (stoi_status_out) FSEM_CUDA(cudaMemcpyAsync(stoi_status_out, ob + 5 * col, nb, cudaMemcpyDeviceToHost, P.compute));
-    }
-    FSEM_CUDA(cudaStreamSynchronize(P.copy));
-    FSEM_CUDA(cudaStreamSynchronize(P.compute));
-    return FSEM_OK;
+    if (!pctx || !sctx || !in) return fail(FSEM_E_INVALID, "fsem_pesq_stoi_score_host_f32: null argument");
+    return score_host_any("fsem_pesq_stoi_score_host_f32", pctx, sctx, in->clean, in->deg, FSEM_DTYPE_F32, in->lengths,
+                          in->batch, in->n, in->stride, mos_out, pesq_status_out, stoi_out, estoi_out, kept_frames_out,
+                          stoi_status_out);
 }
 
 // ================================================================================================

@@ -70,12 +70,11 @@ def score_pesq_stoi(pesq: PESQ, stoi: STOI, clean_speech: torch.Tensor, denoised
         sst = torch.empty(b, dtype=torch.int32)
         if clean.stride(0) != deg.stride(0) and b > 1:
             clean, deg = clean.contiguous(), deg.contiguous()
-        batch = _lib.Batch(clean.data_ptr(), deg.data_ptr(), lens.data_ptr() if lens is not None else None,
-                           b, n, clean.stride(0) if b > 1 else n)
         with torch.cuda.device(pesq.device):
-            PESQ._check_score(pesq._lib.fsem_pesq_stoi_score_host_f32(
-                pesq._ctx, stoi._ctx, C.byref(batch), mos.data_ptr(), pst.data_ptr(), sc[0].data_ptr(),
-                sc[1].data_ptr(), kept.data_ptr(), sst.data_ptr()))
+            PESQ._check_score(pesq._lib.fsem_score_host(
+                pesq._ctx, stoi._ctx, clean.data_ptr(), deg.data_ptr(), _lib.dtype_code(clean.dtype),
+                lens.data_ptr() if lens is not None else None, b, n, clean.stride(0) if b > 1 else n,
+                mos.data_ptr(), pst.data_ptr(), sc[0].data_ptr(), sc[1].data_ptr(), kept.data_ptr(), sst.data_ptr()))
     if lengths is not None and bool((pst == _lib.ITEM_TOO_SHORT).any()):
         raise RuntimeError("PESQ needs at least 20 frames of 512/256 samples for every item")
     stoi.last_kept_frames = kept

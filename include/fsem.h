@@ -196,6 +196,30 @@ FSEM_API int fsem_pesq_stoi_score_f32(fsem_pesq_ctx_t* pesq, fsem_stoi_ctx_t* st
                              int32_t* kept_frames_out, int32_t* stoi_status_out, void* ws_pesq, size_t ws_pesq_bytes,
                              void* ws_stoi, size_t ws_stoi_bytes, void* stream, int overlap);
 
+/* ------------------------------------------------------------------ ingest formats
+ * The reference's boundary is float32 (base.py:16-21).  These entry points also take int16 PCM and fp16 sample
+ * rows; samples are widened to fp32 with a value-preserving cast (no 1/32768 scaling -- both metrics are
+ * scale-free), so the scores are bit-identical to scoring the same values as float32. */
+#define FSEM_DTYPE_F32 0
+#define FSEM_DTYPE_I16 1
+#define FSEM_DTYPE_F16 2
+
+/* Device rows [rows, n] of `dtype` (pitch src_stride ELEMENTS) -> device fp32 rows (pitch dst_stride floats);
+ * stream-ordered.  FSEM_DTYPE_F32 is a strided device-to-device copy. */
+FSEM_API int fsem_ingest_f32(const void* src, int dtype, int64_t rows, int64_t n, int64_t src_stride, float* dst,
+                    int64_t dst_stride, void* stream);
+
+/* Host entry point for any ingest dtype and any subset of the two metrics: `pesq` or `stoi` may be NULL (that
+ * metric is skipped and its output pointers are ignored).  clean / deg are HOST rows [batch, n] of `dtype` with
+ * pitch `stride` elements (pinned memory for full PCIe speed), lengths [batch] HOST int32 or NULL.  Every chunk
+ * crosses PCIe once at sizeof(dtype) bytes per sample, is widened on the device and scored by the selected kernel
+ * chains while the next chunk is in flight.  With FSEM_DTYPE_F32 this is exactly fsem_pesq_score_host_f32 /
+ * fsem_stoi_score_host_f32 / fsem_pesq_stoi_score_host_f32 (which forward here). */
+FSEM_API int fsem_score_host(fsem_pesq_ctx_t* pesq, fsem_stoi_ctx_t* stoi, const void* clean, const void* deg, int dtype,
+                    const int32_t* lengths, int64_t batch, int64_t n, int64_t stride, float* mos_out,
+                    int32_t* pesq_status_out, float* stoi_out, float* estoi_out, int32_t* kept_frames_out,
+                    int32_t* stoi_status_out);
+
 /* ------------------------------------------------------------------ LSD (adjacent metric on the same FFT)
  * Replaces LSD.compute_metric (fast_se_metrics/LSD.py:33-52): scale-matched log-spectral distance on a
  * centred Hann-512/256 STFT.  `hann512` is the HOST window torch.hann_window(512) (LSD.py:16).

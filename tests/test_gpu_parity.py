@@ -411,3 +411,65 @@ def test_random_shapes_against_oracle(pesq, stoi_metrics):
         assert np.array_equal(st16.last_kept_frames.numpy(), wk), (trial, b, n)
     _report("random_shapes", worst)
     assert worst["pesq"] <= 1e-3 and worst["stoi"] <= 1e-4 and worst["estoi"] <= 1e-4
+
+
+# ------------------------------------------------------------------ ingest formats
+def _as_dtype(x, dtype):
+    """float32 synth signal -> (tensor of `dtype`, the float32 tensor holding exactly the same values)."""
+    t = torch.from_numpy(x)
+    narrow = (t * 20000.0).round().clamp(-32768, 32767).to(torch.int16) if dtype == torch.int16 else t.to(torch.float16)
+    return narrow, narrow.to(torch.float32)
+
+
+@pytest.mark.parametrize("dtype", [torch.int16, torch.float16])
+def test_ingest_kernel_is_a_value_preserving_cast(dtype):
+    import ctypes as C
+    from fast_speech_enhancement_metrics_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(5)
+    for rows, n, pad in ((3, 4096, 0), (5, 1001, 0), (4, 777, 3), (1, 5, 0), (2, 8, 8)):
+        src = (torch.randn(rows, n + pad, generator=g) * 3000).to(dtype).cuda()
+        view = src[:, :n]                                              # pitch n + pad elements: odd pitches take the scalar path
+        out = torch.full((rows, n + 2), -7.0, dtype=torch.float32, device="cuda")
+        _lib.check(lib.fsem_ingest_f32(view.data_ptr(), _lib.dtype_code(dtype), rows, n, view.stride(0) if rows > 1 else n + pad,
+                                       out.data_ptr(), out.stride(0), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        assert torch.equal(out[:, :n], view.to(torch.float32))
+        assert bool((out[:, n:] == -7.0).all())                        # nothing written beyond the row
+    assert lib.fsem_ingest_f32(None, 1, 1, 1, 1, None, 1, None) == _lib.FSEM_E_INVALID
+    x = torch.zeros(8, device="cuda")
+    assert lib.fsem_ingest_f32(x.data_ptr(), 9, 1, 8, 8, x.data_ptr(), 8, None) == _lib.FSEM_E_INVALID
+
+
+@pytest.mark.parametrize("dtype", [torch.int16, torch.float16])
+def test_int16_and_fp16_inputs_score_like_their_float32_values(dtype, pesq, stoi_metrics):
+    from fast_speech_enhancement_metrics_b200 import LSD, SDR, score_pesq_stoi
+    clean, deg, _, fs = STOI_CASES["speech16k_3s"]                      # 8 x 48000
+    st = stoi_metrics(16000)
+    cn, cf = _as_dtype(clean, dtype)
+    dn, df = _as_dtype(deg, dtype)
+    lens = [48000, 30000, 20001, 48000, 12345, 40000, 48000, 8000]
+    for lengths in (None, lens):
+        want_p, want_s = pesq(cf, df, lengths=lengths), st(cf, df, lengths=lengths)
+        for cc, dd in ((cn, dn), (cn.cuda(), dn.cuda())):               # host pipeline (2-byte upload) and device tensors
+            assert pesq(cc, dd, lengths=lengths) == want_p
+            got_s = st(cc, dd, lengths=lengths)
+            assert np.array_equal(np.array([[r["STOI"], r["ESTOI"]] for r in got_s]),
+                                  np.array([[r["STOI"], r["ESTOI"]] for r in want_s]), equal_nan=True)
+            both = score_pesq_stoi(pesq, st, cc, dd, lengths=lengths)
+            assert [r["PESQ"] for r in both] == [r["PESQ"] for r in want_p]
+            assert np.array_equal(np.array([r["ESTOI"] for r in both]), np.array([r["ESTOI"] for r in want_s]),
+                                  equal_nan=True)
+    # rows that are not a multiple of 8 samples (ragged 16-byte groups on the way in) and a strided host batch
+    c2, d2 = cn[:5, :40001], dn[:5, :40001]
+    ref_p, ref_s = pesq(cf[:5, :40001], df[:5, :40001]), st(cf[:5, :40001], df[:5, :40001])
+    got_p, got_s = pesq(c2, d2), st(c2, d2)
+    assert _maxdiff([r["PESQ"] for r in got_p], [r["PESQ"] for r in ref_p]) <= 1e-5
+    assert _maxdiff([r["STOI"] for r in got_s], [r["STOI"] for r in ref_s]) <= 1e-6
+    # the adjacent metrics take the same formats
+    for metric in (LSD(16000, use_gpu=True), SDR(16000, use_gpu=True)):
+        assert metric(cn, dn) == metric(cf, df)
+        assert metric(cn.cuda(), dn.cuda()) == metric(cf, df)
+    with pytest.raises(Exception, match="same dtype"):
+        pesq(cn, df)
+    with pytest.raises(RuntimeError, match="expected scalar type Float"):
+        pesq(cf.double(), df.double())

@@ -94,3 +94,20 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
                 assert "/root/reference" not in text, f
+
+
+def test_ingest_dtype_codes_follow_the_header():
+    """FSEM_DTYPE_* in include/fsem.h <-> _lib.dtype_code; unsupported dtypes fail like the reference
+    (float64 raises "expected scalar type Float" inside lfilter / stft there)."""
+    import re
+    import torch
+    from fast_speech_enhancement_metrics_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "fsem.h")).read()
+    codes = {name: int(val) for name, val in re.findall(r"#define FSEM_DTYPE_(\w+) (\d+)", header)}
+    assert codes == {"F32": _lib.DTYPE_F32, "I16": _lib.DTYPE_I16, "F16": _lib.DTYPE_F16}
+    assert _lib.dtype_code(torch.float32) == codes["F32"]
+    assert _lib.dtype_code(torch.int16) == codes["I16"]
+    assert _lib.dtype_code(torch.float16) == codes["F16"]
+    for bad in (torch.float64, torch.int32, torch.bfloat16):
+        with pytest.raises(RuntimeError, match="expected scalar type Float"):
+            _lib.dtype_code(bad)
