@@ -227,7 +227,7 @@ struct PesqPlan {
     bool resample;
     bool tiled;                      // lane = signal (tiled kernel) vs thread = (signal, chunk) for tiny batches
     int tmax, chunk, nchunks;
-    size_t off_rs, off_rslen, off_z, off_partial, off_bark, off_dist, off_power, total;
+    size_t off_rs, off_rslen, off_z, off_partial, off_bark, off_dist, off_power, off_order, off_fprefix, total;
 };
 
 PesqPlan pesq_plan(const fsem_pesq_ctx* ctx, int64_t batch, int64_t n_in) {
@@ -274,6 +274,8 @@ PesqPlan pesq_plan(const fsem_pesq_ctx* ctx, int64_t batch, int64_t n_in) {
     p.off_bark = off;    off = align256(off + sizeof(float) * 2 * batch * p.tmax * FSEM_PESQ_NBANDS);
     p.off_dist = off;    off = align256(off + sizeof(float) * 2 * batch * p.tmax);
     p.off_power = off;   off = align256(off + sizeof(double) * 2 * batch);
+    p.off_order = off;   off = align256(off + sizeof(int32_t) * batch);              // variable-length batches only
+    p.off_fprefix = off; off = align256(off + sizeof(int64_t) * (batch + 1));
     p.total = off;
     return p;
 }
@@ -425,6 +427,16 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
         in = &rs_batch;
     }
 
+    // variable-length batches: length-sorted item order (IIR warps of similar signals, longest Bark CTAs first) and
+    // the prefix sum of valid frames (balanced spectrum warps)
+    int32_t* order = nullptr;
+    int64_t* fprefix = nullptr;
+    if (in->lengths) {
+        order = reinterpret_cast<int32_t*>(ws + p.off_order);
+        fprefix = reinterpret_cast<int64_t*>(ws + p.off_fprefix);
+        pesq_order_kernel<<<1, kOrderThreads, 0, stream>>>(in->lengths, in->batch, in->n, order, fprefix);
+        FSEM_LAUNCHED();
+    }
     {   // kernel A
         const bool vec4 = aligned16(in->clean) && aligned16(in->deg) && (in->stride % 4 == 0);
         if (vec4 && p.tiled) {
@@ -433,12 +445,12 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
             { ProfScope prof_(K_PESQ_FILTER, stream);
               if (in->lengths)
                   pesq_filter_tiled_kernel<true><<<grid, kFiltWarps * 32, 0, stream>>>(
-                      in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, p.chunk, p.nchunks, ctx->warm,
-                      ctx->coef, z, p.zstride, partial);
+                      in->clean, in->deg, in->lengths, order, in->batch, in->n, in->stride, p.chunk, p.nchunks,
+                      ctx->warm, ctx->coef, z, p.zstride, partial);
               else
                   pesq_filter_tiled_kernel<false><<<grid, kFiltWarps * 32, 0, stream>>>(
-                      in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, p.chunk, p.nchunks, ctx->warm,
-                      ctx->coef, z, p.zstride, partial); }
+                      in->clean, in->deg, nullptr, nullptr, in->batch, in->n, in->stride, p.chunk, p.nchunks,
+                      ctx->warm, ctx->coef, z, p.zstride, partial); }
         } else {
             const int64_t threads = 2 * in->batch * p.nchunks;
             const unsigned grid = (unsigned)ceil_div(threads, 128);
@@ -463,13 +475,13 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
         const int64_t cap = (int64_t)ctx->dev.sms * per_sm;
         if (grid > cap) grid = cap;
         { ProfScope prof_(K_PESQ_SPECTRUM, stream);
-          pesq_spectrum_kernel<<<(unsigned)grid, kSpecWarps * 32, kSpecDynSmem, stream>>>(z, p.zstride, in->lengths, in->batch,
-                                                                              in->n, p.tmax, ctx->d_tab, bark); }
+          pesq_spectrum_kernel<<<(unsigned)grid, kSpecWarps * 32, kSpecDynSmem, stream>>>(
+              z, p.zstride, in->lengths, fprefix, in->batch, in->n, p.tmax, ctx->d_tab, bark); }
         FSEM_LAUNCHED();
     }
     {   // kernel C
         { ProfScope prof_(K_PESQ_BARK, stream);
-          pesq_bark_kernel<<<(unsigned)in->batch, kBarkThreads, 0, stream>>>(bark, partial, p.nchunks, in->lengths,
+          pesq_bark_kernel<<<(unsigned)in->batch, kBarkThreads, 0, stream>>>(bark, partial, p.nchunks, in->lengths, order,
                                                                             in->batch, in->n, p.tmax, ctx->d_tab, dist,
                                                                             mos_out, status_out, power); }
         FSEM_LAUNCHED();

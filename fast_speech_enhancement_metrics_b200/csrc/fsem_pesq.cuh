@@ -179,12 +179,17 @@ pesq_filter_kernel(const float* __restrict__ clean, const float* __restrict__ de
 constexpr int kFiltWarps = 4;
 constexpr int kFiltPitch = 36;   // floats per tile row (32 + 4 pad)
 
+// Variable-length batches (kHasLengths): `order` is a permutation that puts items of similar length next to each
+// other (pesq_order_kernel), so the 32 signals of a warp end together; a warp stops at its longest signal and a lane
+// whose signal has ended skips the arithmetic.  Results do not depend on the grouping: every lane runs the same
+// recurrence on the same chunk grid whatever its neighbours are.
 template <bool kHasLengths>
 __global__ void __launch_bounds__(kFiltWarps * 32)
 pesq_filter_tiled_kernel(const float* __restrict__ clean, const float* __restrict__ deg,
-                         const int32_t* __restrict__ lengths, int64_t batch, int64_t n, int64_t stride,
-                         int chunk, int nchunks, int warm, const __grid_constant__ PesqFilterCoef P,
-                         float* __restrict__ z_out, int64_t zstride, double* __restrict__ partial) {
+                         const int32_t* __restrict__ lengths, const int32_t* __restrict__ order, int64_t batch,
+                         int64_t n, int64_t stride, int chunk, int nchunks, int warm,
+                         const __grid_constant__ PesqFilterCoef P, float* __restrict__ z_out, int64_t zstride,
+                         double* __restrict__ partial) {
     __shared__ __align__(16) float s_tile[kFiltWarps][32 * kFiltPitch];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -199,28 +204,45 @@ pesq_filter_tiled_kernel(const float* __restrict__ clean, const float* __restric
     const int c = (int)(rem - grp * nchunks);
     const int64_t row0 = grp * 32;
 
-    // own signal (compute role)
-    const int64_t my_item = row0 + lane;
-    const bool sig_ok = my_item < batch;
+    // own signal (compute role): slot row0 + lane of the (possibly permuted) batch
+    const bool sig_ok = row0 + lane < batch;
+    const int64_t my_item = !sig_ok ? 0 : (kHasLengths && order != nullptr) ? (int64_t)order[row0 + lane] : row0 + lane;
     const int len = sig_ok ? item_length(lengths, my_item, n) : 0;
-    // rows this lane helps to move (transfer role): rows (lane >> 3) + 4*i, float4 column lane & 7
+    // rows this lane helps to move (transfer role): slots (lane >> 3) + 4*i, float4 column lane & 7
     const int col = (lane & 7) * 4;
     const int64_t trow = row0 + (lane >> 3);
-    const float* __restrict__ src0 = (half ? deg : clean) + trow * stride + col;
-    float* __restrict__ dst0 = z_out + ((int64_t)half * batch + trow) * zstride + col;
+    const float* __restrict__ sbase = (half ? deg : clean) + col;
+    float* __restrict__ dbase = z_out + (int64_t)half * batch * zstride + col;
+    const float* __restrict__ src0 = sbase + trow * stride;
+    float* __restrict__ dst0 = dbase + trow * zstride;
     const int64_t sstep = 4 * stride, dstep = 4 * zstride;
     int row_len[kHasLengths ? 8 : 1];
+    int row_item[kHasLengths ? 8 : 1];
     if (kHasLengths) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) row_len[i] = (trow + 4 * i < batch) ? item_length(lengths, trow + 4 * i, n) : 0;
+        for (int i = 0; i < 8; ++i) {
+            const int64_t slot = trow + 4 * i;
+            const int64_t it = slot >= batch ? 0 : (order != nullptr ? (int64_t)order[slot] : slot);
+            row_item[i] = (int)it;
+            row_len[i] = slot < batch ? item_length(lengths, it, n) : 0;
+        }
     }
-    const int rows_ok = (int)min((int64_t)8, (batch - trow + 3) / 4);      // rows trow + 4i < batch  <=>  i < rows_ok
+    const int rows_ok = (int)min((int64_t)8, (batch - trow + 3) / 4);      // slots trow + 4i < batch  <=>  i < rows_ok
     auto rlen = [&](int i) -> int { return kHasLengths ? row_len[kHasLengths ? i : 0] : (i < rows_ok ? (int)n : 0); };
+    auto src_row = [&](int i) -> const float* {
+        return kHasLengths ? sbase + (int64_t)row_item[kHasLengths ? i : 0] * stride : src0 + i * sstep;
+    };
+    auto dst_row = [&](int i) -> float* {
+        return kHasLengths ? dbase + (int64_t)row_item[kHasLengths ? i : 0] * zstride : dst0 + i * dstep;
+    };
 
     const int t_acc = c * chunk;
-    const int t_stop = min((int)n, t_acc + chunk);           // common upper bound of the chunk
+    // common upper bound of the chunk: nothing to do beyond the longest of the warp's 32 signals
+    const int grp_len = kHasLengths ? __reduce_max_sync(kFull, len) : (int)n;
+    const int t_stop = min(grp_len, t_acc + chunk);
     const int t_end = min(len, t_stop);                      // this lane's own bound
     int t = max(0, t_acc - warm);                            // multiple of 32
+    if (t_acc >= grp_len) t = t_stop;                        // the whole chunk lies beyond every signal: no warm-up either
 
     IirState st;
 #pragma unroll
@@ -233,7 +255,7 @@ pesq_filter_tiled_kernel(const float* __restrict__ clean, const float* __restric
         for (int i = 0; i < 8; ++i) {
             const int a = tt + col;
             const int rl = rlen(i);
-            const float* q = src0 + i * sstep + tt;
+            const float* q = src_row(i) + tt;
             if (a + 4 <= rl) {
                 v[i] = __ldg(reinterpret_cast<const float4*>(q));
             } else {
@@ -272,7 +294,7 @@ pesq_filter_tiled_kernel(const float* __restrict__ clean, const float* __restric
                 *reinterpret_cast<float4*>(row + 4 * g) = make_float4(z0, z1, z2, z3);
             }
             acc += acc2;
-        } else {
+        } else if (t < len) {                                // a lane whose signal has ended has nothing left to compute
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
                 float4 q = *reinterpret_cast<const float4*>(row + 4 * g);
@@ -299,7 +321,7 @@ pesq_filter_tiled_kernel(const float* __restrict__ clean, const float* __restric
                 const int a = t + col;
                 const int rl = rlen(i);
                 float4 q = *reinterpret_cast<const float4*>(tile + ((lane >> 3) + 4 * i) * kFiltPitch + col);
-                float* d = dst0 + i * dstep + t;
+                float* d = dst_row(i) + t;
                 if (a + 4 <= rl) {
                     *reinterpret_cast<float4*>(d) = q;
                 } else {
@@ -312,6 +334,64 @@ pesq_filter_tiled_kernel(const float* __restrict__ clean, const float* __restric
         __syncwarp();
     }
     if (sig_ok) partial[((int64_t)half * batch + my_item) * nchunks + c] = acc_d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Variable-length batches only (one CTA): `order` = item indices bucket-sorted by length (256 buckets, ascending;
+// the order inside a bucket is arbitrary and does not affect any result), and frame_prefix[i] = number of valid
+// STFT frames of items 0..i-1 (frame_prefix[batch] = total).
+constexpr int kOrderThreads = 1024;
+
+__device__ __forceinline__ int length_bucket(int len, int64_t n) { return (int)(((int64_t)len * 256) / (n + 1)); }
+
+__global__ void __launch_bounds__(kOrderThreads)
+pesq_order_kernel(const int32_t* __restrict__ lengths, int64_t batch, int64_t n, int32_t* __restrict__ order,
+                  int64_t* __restrict__ frame_prefix) {
+    __shared__ int s_hist[256];
+    __shared__ long long s_warp[kOrderThreads / 32];
+    __shared__ long long s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 256) s_hist[tid] = 0;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t i = tid; i < batch; i += kOrderThreads) atomicAdd(&s_hist[length_bucket(item_length(lengths, i, n), n)], 1);
+    __syncthreads();
+    if (tid == 0) {                                               // exclusive scan of the 256 bucket counts
+        int run = 0;
+        for (int k = 0; k < 256; ++k) { const int c = s_hist[k]; s_hist[k] = run; run += c; }
+    }
+    __syncthreads();
+    for (int64_t i = tid; i < batch; i += kOrderThreads)
+        order[atomicAdd(&s_hist[length_bucket(item_length(lengths, i, n), n)], 1)] = (int32_t)i;
+    // exclusive prefix sum of the frame counts, 1024 items per round
+    for (int64_t base = 0; base < batch; base += kOrderThreads) {
+        const int64_t i = base + tid;
+        const long long T = i < batch ? pesq_num_frames(item_length(lengths, i, n)) : 0;
+        long long v = T;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long up = __shfl_up_sync(kFull, v, o);
+            if (lane >= o) v += up;
+        }
+        if (lane == 31) s_warp[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long up = __shfl_up_sync(kFull, w, o);
+                if (lane >= o) w += up;
+            }
+            s_warp[lane] = w;                                     // inclusive totals of warps 0..lane
+        }
+        __syncthreads();
+        const long long before = s_carry + (warp > 0 ? s_warp[warp - 1] : 0);
+        if (i < batch) frame_prefix[i] = before + v - T;
+        __syncthreads();
+        if (tid == kOrderThreads - 1) s_carry = before + v;
+        __syncthreads();
+    }
+    if (tid == 0) frame_prefix[batch] = s_carry;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -341,8 +421,8 @@ static_assert(sizeof(SpecWarpSmem) % 16 == 0, "per-warp shared block must keep 1
 
 __global__ void __launch_bounds__(kSpecWarps * 32, FSEM_FFT_MINBLOCKS)
 pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t* __restrict__ lengths,
-                     int64_t batch, int64_t n, int tmax, const PesqTables* __restrict__ tab,
-                     float* __restrict__ bark /* [2][batch][tmax][49], unscaled */) {
+                     const int64_t* __restrict__ frame_prefix, int64_t batch, int64_t n, int tmax,
+                     const PesqTables* __restrict__ tab, float* __restrict__ bark /* [2][batch][tmax][49], unscaled */) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -370,30 +450,31 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
     const float scale0 = tab->pow_dens[lane];
     const float scale1 = (lane + 32 < FSEM_PESQ_NBANDS) ? tab->pow_dens[lane + 32] : 0.f;
 
-    // every warp owns a contiguous range of the flattened (item, frame) space: one division per warp
-    const int64_t units = batch * (int64_t)tmax;
+    // Work units = VALID (item, frame) pairs in item-major order; frame_prefix[i] = number of units before item i
+    // (nullptr: every item has tmax frames).  Every warp owns a contiguous, equally long range of them, so ragged
+    // batches are balanced by frames, not by padded length.
+    const int64_t units = frame_prefix ? frame_prefix[batch] : batch * (int64_t)tmax;
     const int64_t nwarps = (int64_t)gridDim.x * kSpecWarps;
     const int64_t per = (units + nwarps - 1) / nwarps;
-    int64_t u = ((int64_t)blockIdx.x * kSpecWarps + warp) * per;
-    const int64_t u1 = min(units, u + per);
-    if (u >= u1) return;
-    int64_t item = u / tmax;
-    int f = (int)(u - item * tmax);
+    const int64_t v0 = ((int64_t)blockIdx.x * kSpecWarps + warp) * per;
+    int64_t remaining = min(units, v0 + per) - v0;
+    if (remaining <= 0) return;
+    int64_t item;
+    int f;
+    if (frame_prefix) {                                          // last item with frame_prefix[item] <= v0
+        int64_t lo = 0, hi = batch;
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (frame_prefix[mid] <= v0) lo = mid; else hi = mid;
+        }
+        item = lo;
+        f = (int)(v0 - frame_prefix[lo]);
+    } else {
+        item = v0 / tmax;
+        f = (int)(v0 - item * tmax);
+    }
     int len = item_length(lengths, item, n);
     int T = pesq_num_frames(len);
-    // first valid unit at or after (u, item, f); frames f >= T of a short item are skipped in one step
-    auto seek = [&](int64_t& uu, int64_t& it, int& ff, int& ll, int& tt) -> bool {
-        while (uu < u1) {
-            if (ff < tt) return true;
-            uu += tmax - ff;
-            ff = 0;
-            if (++it >= batch) return false;
-            ll = item_length(lengths, it, n);
-            tt = pesq_num_frames(ll);
-        }
-        return false;
-    };
-    if (!seek(u, item, f, len, T)) return;
 
     // Ring bookkeeping: half h of an item = samples [256 h, 256 h + 256) of both signals.  Slots rotate 0,1,2;
     // `par` bit s is the mbarrier phase parity the latest copy into slot s completes (flipped at every issue).
@@ -415,15 +496,21 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
     while (true) {
         const int sn = 3 - sa - sb;                              // the free slot
         // look ahead: next valid unit of this warp's range; fast path = next frame of the same item
-        int64_t u2 = u + 1, item2 = item;
-        int f2 = f + 1, len2 = len, T2 = T;
-        bool has_next, same_item;
-        if (f2 < T && u2 < u1) { has_next = true; same_item = true; }
-        else { has_next = seek(u2, item2, f2, len2, T2); same_item = false; }
+        const bool has_next = remaining > 1;
+        const bool same_item = has_next && f + 1 < T;
+        int64_t item2 = item;
+        int len2 = len, T2 = T;
+        if (has_next && !same_item) {                            // next item that has frames (one exists: remaining > 1)
+            do {
+                ++item2;
+                len2 = item_length(lengths, item2, n);
+                T2 = pesq_num_frames(len2);
+            } while (T2 == 0 && item2 + 1 < batch);
+        }
         __syncwarp();                                            // all lanes are done with the slot about to be refilled
         if (has_next) {
             if (same_item) issue_half(sn, item, f + 2);
-            else issue_half(sn, item2, f2);
+            else issue_half(sn, item2, 0);
         }
         // wait for the two halves of the current frame
         mbar_wait(bar0 + 8 * sa, (par >> sa) & 1u);
@@ -464,11 +551,12 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
             out_d[lane + 32] = bands_d[lane + 32] * scale1;
         }
         if (!has_next) break;
+        --remaining;
         if (same_item) {                                         // frame f+1 = halves (f+1, f+2) = slots (sb, sn)
             sa = sb; sb = sn;
-            ++u; ++f;
+            ++f;
         } else {                                                 // new item: its first half sits in sn, fetch the second
-            u = u2; item = item2; f = f2; len = len2; T = T2;
+            item = item2; f = 0; len = len2; T = T2;
             const int freed = sa;                                // both old slots are free; take the older one
             sa = sn; sb = freed;
             __syncwarp();
@@ -495,7 +583,7 @@ __device__ __forceinline__ float zwicker_loudness(float p, float thr, float inv_
 
 __global__ void __launch_bounds__(kBarkThreads)
 pesq_bark_kernel(const float* __restrict__ bark, const double* __restrict__ partial, int nchunks,
-                 const int32_t* __restrict__ lengths, int64_t batch, int64_t n, int tmax,
+                 const int32_t* __restrict__ lengths, const int32_t* __restrict__ order, int64_t batch, int64_t n, int tmax,
                  const PesqTables* __restrict__ tab, float* __restrict__ dist_ws /* [2][batch][tmax] */,
                  float* __restrict__ mos_out, int32_t* __restrict__ status_out,
                  double* __restrict__ power_out /* [2][batch] */) {
@@ -510,7 +598,8 @@ pesq_bark_kernel(const float* __restrict__ bark, const double* __restrict__ part
     __shared__ float s_red[2][kBarkThreads / 32];
 
     const int tid = threadIdx.x;
-    const int64_t item = blockIdx.x;
+    // ragged batches: CTAs are scheduled in launch order, so the longest items go first (no long item left for the tail)
+    const int64_t item = order ? (int64_t)order[batch - 1 - blockIdx.x] : (int64_t)blockIdx.x;
     const int len = item_length(lengths, item, n);
     const int T = pesq_num_frames(len);
 

@@ -473,3 +473,31 @@ def test_int16_and_fp16_inputs_score_like_their_float32_values(dtype, pesq, stoi
         pesq(cn, df)
     with pytest.raises(RuntimeError, match="expected scalar type Float"):
         pesq(cf.double(), df.double())
+
+
+def test_pesq_ragged_batch_with_empty_and_short_items(pesq):
+    """Variable-length batches go through the length-sorted IIR pass and the frame-prefix work split of the
+    spectrum kernel: items without a single frame (T = 0) and items below 20 frames must neither disturb their
+    neighbours nor the unit bookkeeping, whatever their position in the batch."""
+    from fast_speech_enhancement_metrics_b200 import _lib
+    from fast_speech_enhancement_metrics_b200.synth import synth_batch
+    b, n = 70, 48000
+    clean, deg, _ = synth_batch(977, b, n)
+    rng = np.random.default_rng(3)
+    lens = rng.integers(5376, n + 1, size=b)
+    lens[[0, 7, 8, 9, 33, 68, 69]] = [0, 100, 255, 0, 3000, 5120, 1]       # T = 0, 0, 0, 0, 10, 19, 0
+    lens[[1, 34]] = [n, 5376]
+    c, d = torch.from_numpy(clean).cuda(), torch.from_numpy(deg).cuda()
+    mos, status = pesq.score_tensors(c, d, lens.tolist())
+    mos, status = mos.cpu().numpy(), status.cpu().numpy()
+    padded = lens + lens % 256                                              # PESQ.py:128-133
+    short = np.where(padded < 512, 0, 1 + (padded - 512) // 256) < 20
+    assert short.sum() == 7
+    assert np.array_equal(status == _lib.ITEM_TOO_SHORT, short)
+    assert np.isnan(mos[short]).all() and np.isfinite(mos[~short]).all()
+    for i in np.flatnonzero(~short)[::3]:
+        one, _ = pesq.score_tensors(c[i:i + 1, :lens[i]].contiguous(), d[i:i + 1, :lens[i]].contiguous())
+        assert abs(float(one[0]) - mos[i]) <= 1e-5, (i, lens[i], float(one[0]), mos[i])
+    for i in np.flatnonzero(~short)[:8]:
+        want = po.pesq_item(clean[i, :lens[i]], deg[i, :lens[i]])
+        assert abs(want - mos[i]) <= 2e-4, (i, lens[i], want, mos[i])
