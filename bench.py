@@ -241,7 +241,7 @@ def main():
     ap.add_argument("--two-streams", action="store_true",
                     help="experiment: run the PESQ and the STOI kernel chains on two CUDA streams")
     ap.add_argument("--overlap", type=int, default=-1,
-                    help="experiment: fused device entry fsem_pesq_stoi_score_f32 with overlap mode 0/1/2")
+                    help="experiment: fused device entry fsem_pesq_stoi_score_f32 with overlap mode 0/1/2/3 (3 = single-read first pass)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

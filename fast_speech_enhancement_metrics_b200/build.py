@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_NAME = "libfsem_b200.so"
 LIB_PATH = os.path.join(HERE, LIB_NAME)
 SOURCES = ["fsem_api.cu"]
-HEADERS = ["fsem_common.cuh", "fsem_fft.cuh", "fsem_pesq.cuh", "fsem_stoi.cuh", os.path.join("..", "..", "include", "fsem.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "fsem.h")]
 
 
 def find_nvcc() -> str:

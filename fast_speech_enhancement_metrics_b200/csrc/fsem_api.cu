@@ -13,6 +13,7 @@
 #include "fsem_lsd.cuh"
 #include "fsem_sdr.cuh"
 #include "fsem_ingest.cuh"
+#include "fsem_first_pass.cuh"
 
 using namespace fsem;
 
@@ -22,7 +23,15 @@ namespace {
 thread_local char g_err[512] = "";
 // set by fsem_pesq_stoi_score_f32 around its call of fsem_pesq_score_f32: event to record right after the IIR pass,
 // and a cap on the spectrum kernel's CTAs per SM so that the other metric's kernels can co-reside
-struct OverlapHook { cudaEvent_t after_filter = nullptr; int spec_ctas_per_sm = 0; };
+// first_pass_done: the single-read first pass (fsem_first_pass.cuh) has already produced z / partials (PESQ side,
+// together with the length order and frame prefix) and y / hop energies (STOI side) in the workspaces, with IIR chunks
+// of `chunk_quantum` granularity: the two score functions skip their own first kernels
+struct OverlapHook {
+    cudaEvent_t after_filter = nullptr;
+    int spec_ctas_per_sm = 0;
+    bool first_pass_done = false;
+    int chunk_quantum = 0;
+};
 thread_local OverlapHook g_hook;
 std::atomic<int64_t> g_launches{0};
 
@@ -53,11 +62,11 @@ inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 // ---- optional per-kernel timing with CUDA events on the launching stream (bench.py only; not thread-safe)
 enum KernelId {
     K_PESQ_FILTER = 0, K_PESQ_SPECTRUM, K_PESQ_BARK, K_STOI_RESAMPLE, K_STOI_ENERGY, K_STOI_COMPACT,
-    K_STOI_TOB, K_STOI_SEGMENT, K_STOI_FINALIZE, K_PESQ_RESAMPLE, K_LSD_FRAMES, K_SDR_CORR, K_SDR_SOLVE, K_INGEST, K_COUNT
+    K_STOI_TOB, K_STOI_SEGMENT, K_STOI_FINALIZE, K_PESQ_RESAMPLE, K_LSD_FRAMES, K_SDR_CORR, K_SDR_SOLVE, K_INGEST, K_FIRST_PASS, K_COUNT
 };
 const char* const kKernelNames[K_COUNT] = {
     "pesq_filter_kernel", "pesq_spectrum_kernel", "pesq_bark_kernel", "stoi_resample_kernel", "stoi_energy_kernel",
-    "stoi_compact_kernel", "stoi_tob_kernel", "stoi_segment_kernel", "stoi_finalize_kernel", "pesq_resample_kernel", "lsd_frames_kernel", "sdr_corr_kernel", "sdr_solve_kernel", "ingest_kernel"};
+    "stoi_compact_kernel", "stoi_tob_kernel", "stoi_segment_kernel", "stoi_finalize_kernel", "pesq_resample_kernel", "lsd_frames_kernel", "sdr_corr_kernel", "sdr_solve_kernel", "ingest_kernel", "first_pass_kernel"};
 bool g_profile = false;
 struct ProfRecord { int id; cudaEvent_t start, stop; };
 std::vector<ProfRecord> g_prof_pending;
@@ -214,6 +223,7 @@ struct fsem_pesq_ctx {
     float* d_rs_taps = nullptr;
     int spec_ctas_per_sm = 2;
     int filt_ctas_per_sm = 4;
+    int fp_ctas_per_sm = 7;                         // single-read first pass (fsem_first_pass.cuh)
     HostPipe pipe;
     cudaStream_t side = nullptr;                    // second stream of the overlapped two-metric device entry
     cudaEvent_t ev_fork = nullptr, ev_filter = nullptr, ev_join = nullptr;
@@ -230,7 +240,7 @@ struct PesqPlan {
     size_t off_rs, off_rslen, off_z, off_partial, off_bark, off_dist, off_power, off_order, off_fprefix, total;
 };
 
-PesqPlan pesq_plan(const fsem_pesq_ctx* ctx, int64_t batch, int64_t n_in) {
+PesqPlan pesq_plan(const fsem_pesq_ctx* ctx, int64_t batch, int64_t n_in, int quantum = 64) {
     PesqPlan p{};
     p.batch = batch;
     p.n_in = n_in;
@@ -246,9 +256,11 @@ PesqPlan pesq_plan(const fsem_pesq_ctx* ctx, int64_t batch, int64_t n_in) {
     // waves x (chunk + warm-up): enough units to fill the chip, no half-empty last wave, little redundant warm-up.
     const int64_t nn = n > 0 ? n : 1;
     const int64_t groups = 2 * ceil_div(batch > 0 ? batch : 1, 32);
-    const int64_t slots = (int64_t)ctx->dev.sms * ctx->filt_ctas_per_sm * kFiltWarps;
+    // resident warps of the kernel that walks the chunks: the IIR pass, or (coarse grid) the single-read first pass
+    const int64_t slots = quantum == kFpQuantum ? (int64_t)ctx->dev.sms * ctx->fp_ctas_per_sm * kFpWarps
+                                                : (int64_t)ctx->dev.sms * ctx->filt_ctas_per_sm * kFiltWarps;
     const int64_t max_ch = ceil_div(nn, 256) < 1024 ? ceil_div(nn, 256) : 1024;     // chunks of at least 256 samples
-    int64_t nch = 1, chunk = round_up(nn, 64);
+    int64_t nch = 1, chunk = round_up(nn, quantum);
     double best = 1e300;
     // tiny batches cannot fill the 32 signal lanes of a warp: there a thread takes one (signal, chunk) and the time
     // axis is cut as finely as the warm-up allows
@@ -258,7 +270,7 @@ PesqPlan pesq_plan(const fsem_pesq_ctx* ctx, int64_t batch, int64_t n_in) {
         nch = ceil_div(nn, chunk);
     }
     for (int64_t c = 1; p.tiled && c <= max_ch; ++c) {
-        const int64_t ch = round_up(ceil_div(nn, c), 64);
+        const int64_t ch = round_up(ceil_div(nn, c), quantum);
         const int64_t cc = ceil_div(nn, ch);
         const int64_t waves = ceil_div(groups * cc, slots);
         const double cost = (double)waves * (double)(ch + (cc > 1 ? ctx->warm : 0));
@@ -270,12 +282,13 @@ PesqPlan pesq_plan(const fsem_pesq_ctx* ctx, int64_t batch, int64_t n_in) {
     p.off_rs = off;      off = align256(off + (p.resample ? sizeof(float) * 2 * batch * p.rstride : 0));
     p.off_rslen = off;   off = align256(off + (p.resample ? sizeof(int32_t) * batch : 0));
     p.off_z = off;       off = align256(off + sizeof(float) * 2 * batch * p.zstride);
-    p.off_partial = off; off = align256(off + sizeof(double) * 2 * batch * p.nchunks);
     p.off_bark = off;    off = align256(off + sizeof(float) * 2 * batch * p.tmax * FSEM_PESQ_NBANDS);
     p.off_dist = off;    off = align256(off + sizeof(float) * 2 * batch * p.tmax);
     p.off_power = off;   off = align256(off + sizeof(double) * 2 * batch);
     p.off_order = off;   off = align256(off + sizeof(int32_t) * batch);              // variable-length batches only
     p.off_fprefix = off; off = align256(off + sizeof(int64_t) * (batch + 1));
+    // last, so that no other offset depends on the chunk count (the two-metric entry point plans a coarser chunk grid)
+    p.off_partial = off; off = align256(off + sizeof(double) * 2 * batch * p.nchunks);
     p.total = off;
     return p;
 }
@@ -348,6 +361,12 @@ extern "C" int fsem_pesq_create(fsem_pesq_ctx_t** out, const fsem_pesq_design_t*
         }
     }
     e = cudaFuncSetAttribute(pesq_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpecDynSmem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(pesq_stoi_first_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)kFpDynSmem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(pesq_stoi_first_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)kFpDynSmem);
     if (e != cudaSuccess) {
         cudaFree(ctx->d_tab);
         if (ctx->d_rs_taps) cudaFree(ctx->d_rs_taps);
@@ -360,6 +379,9 @@ extern "C" int fsem_pesq_create(fsem_pesq_ctx_t** out, const fsem_pesq_design_t*
     occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pesq_filter_tiled_kernel<false>, kFiltWarps * 32, 0) == cudaSuccess && occ > 0)
         ctx->filt_ctas_per_sm = occ;
+    occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pesq_stoi_first_pass_kernel<false>, kFpWarps * 32, kFpDynSmem) == cudaSuccess && occ > 0)
+        ctx->fp_ctas_per_sm = occ;
     *out = ctx;
     return FSEM_OK;
 }
@@ -379,7 +401,9 @@ extern "C" int fsem_pesq_destroy(fsem_pesq_ctx_t* ctx) {
 
 extern "C" size_t fsem_pesq_workspace_bytes(const fsem_pesq_ctx_t* ctx, int64_t batch, int64_t n) {
     if (!ctx || batch <= 0 || n <= 0) return 0;
-    return pesq_plan(ctx, batch, n).total;
+    // the single-read first pass of the two-metric entry point plans its IIR chunks on a coarser grid
+    const size_t a = pesq_plan(ctx, batch, n).total, b = pesq_plan(ctx, batch, n, kFpQuantum).total;
+    return a > b ? a : b;
 }
 
 extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in, float* mos_out,
@@ -392,7 +416,8 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
     if (in->batch == 0) return FSEM_OK;
     if (!in->clean || !in->deg) return fail(FSEM_E_INVALID, "fsem_pesq_score_f32: null input");
     if (in->n >= (int64_t(1) << 30)) return fail(FSEM_E_INVALID, "fsem_pesq_score_f32: n too large");
-    const PesqPlan p = pesq_plan(ctx, in->batch, in->n);
+    const bool first_pass_done = g_hook.first_pass_done;
+    const PesqPlan p = pesq_plan(ctx, in->batch, in->n, first_pass_done ? g_hook.chunk_quantum : 64);
     // without per-item lengths every item has n samples: fewer than 20 frames is the reference's
     // RuntimeError from unfold (PESQ.py:169)
     if (!in->lengths && pesq_num_frames(p.n) < 20)
@@ -434,10 +459,12 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
     if (in->lengths) {
         order = reinterpret_cast<int32_t*>(ws + p.off_order);
         fprefix = reinterpret_cast<int64_t*>(ws + p.off_fprefix);
-        pesq_order_kernel<<<1, kOrderThreads, 0, stream>>>(in->lengths, in->batch, in->n, order, fprefix);
-        FSEM_LAUNCHED();
+        if (!first_pass_done) {
+            pesq_order_kernel<<<1, kOrderThreads, 0, stream>>>(in->lengths, in->batch, in->n, order, fprefix);
+            FSEM_LAUNCHED();
+        }
     }
-    {   // kernel A
+    if (!first_pass_done) {   // kernel A
         const bool vec4 = aligned16(in->clean) && aligned16(in->deg) && (in->stride % 4 == 0);
         if (vec4 && p.tiled) {
             const int64_t units = 2 * ceil_div(in->batch, 32) * p.nchunks;
@@ -514,6 +541,7 @@ struct fsem_stoi_ctx {
     float* d_taps = nullptr;
     bool fast85 = false;        // taps fit the specialised 8:5 kernel
     Resample85Taps taps85;
+    StoiWindowArg win_arg;      // analysis window as a kernel argument of the single-read first pass
     StoiTables* d_tab = nullptr;
     float clip = 0.f, dyn_range = 40.f;
     int tob_ctas_per_sm = 2;
@@ -582,6 +610,7 @@ extern "C" int fsem_stoi_create(fsem_stoi_ctx_t** out, const fsem_stoi_design_t*
     ctx->clip = d->clip; ctx->dyn_range = d->dyn_range;
     StoiTables h{};
     memcpy(h.window, d->window, sizeof(h.window));
+    memcpy(ctx->win_arg.w, d->window, sizeof(ctx->win_arg.w));
     for (int b = 0; b < FSEM_STOI_NBANDS; ++b) { h.band_lo[b] = d->band_lo[b]; h.band_hi[b] = d->band_hi[b]; }
     h.clip = d->clip; h.dyn_range = d->dyn_range;
     cudaError_t e = cudaMalloc(&ctx->d_tab, sizeof(StoiTables));
@@ -656,7 +685,11 @@ extern "C" int fsem_stoi_score_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t* in,
     const float* c10 = in->clean;
     const float* d10 = in->deg;
     int64_t sstride = in->stride;
-    if (p.resample) {
+    if (p.resample && g_hook.first_pass_done) {                  // y and the hop energies are already in the workspace
+        c10 = y;
+        d10 = y + in->batch * p.ystride;
+        sstride = p.ystride;
+    } else if (p.resample) {
         if (ctx->fast85) {
             dim3 grid((unsigned)ceil_div(p.lmax, (int64_t)kRs85TileOut * kRs85TilesPerCta), (unsigned)(2 * in->batch));
             const bool vec4 = aligned16(in->clean) && aligned16(in->deg) && (in->stride % 4 == 0);
@@ -851,10 +884,18 @@ int score_host_any(const char* who, fsem_pesq_ctx* pctx, fsem_stoi_ctx* sctx, co
             if (rc == FSEM_OK) rc = launch_ingest(base + raw_sig, dtype, cnt, n, rstride, d_deg, dstride, P.compute);
         }
         fsem_batch_t dev{d_clean, d_deg, lengths ? d_len : nullptr, cnt, n, dstride};
-        if (rc == FSEM_OK && pctx)
+        if (rc == FSEM_OK && pctx && sctx)
+            rc = fsem_pesq_stoi_score_f32(pctx, sctx, &dev, reinterpret_cast<float*>(ob) + i0,
+                                          reinterpret_cast<int32_t*>(ob + col) + i0,
+                                          reinterpret_cast<float*>(ob + 2 * col) + i0,
+                                          reinterpret_cast<float*>(ob + 3 * col) + i0,
+                                          reinterpret_cast<int32_t*>(ob + 4 * col) + i0,
+                                          reinterpret_cast<int32_t*>(ob + 5 * col) + i0, wsb + 2 * conv_sig, ws_pesq,
+                                          wsb + 2 * conv_sig + ws_pesq, ws_stoi, P.compute, 0);
+        else if (rc == FSEM_OK && pctx)
             rc = fsem_pesq_score_f32(pctx, &dev, reinterpret_cast<float*>(ob) + i0,
                                      reinterpret_cast<int32_t*>(ob + col) + i0, wsb + 2 * conv_sig, ws_pesq, P.compute);
-        if (rc == FSEM_OK && sctx)
+        else if (rc == FSEM_OK && sctx)
             rc = fsem_stoi_score_f32(sctx, &dev, reinterpret_cast<float*>(ob + 2 * col) + i0,
                                      reinterpret_cast<float*>(ob + 3 * col) + i0,
                                      reinterpret_cast<int32_t*>(ob + 4 * col) + i0,
@@ -1023,11 +1064,59 @@ extern "C" int fsem_pesq_stoi_score_f32(fsem_pesq_ctx_t* pctx, fsem_stoi_ctx_t* 
                                         int overlap) {
     if (!pctx || !sctx) return fail(FSEM_E_INVALID, "fsem_pesq_stoi_score_f32: null context");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-    if (!overlap) {
+    if (overlap <= 0 || overlap == 3) {
+        // overlap = 3: single-read first pass (fsem_first_pass.cuh) -- needs 16 kHz input for PESQ, the 8:5 resampler for
+        // STOI, 16-byte aligned rows and enough items to fill the 32 signal lanes of a warp; otherwise, and with
+        // overlap = 0, the two kernel chains run back to back, each reading the input itself.  Measured on B200
+        // (8192 x 10 s): 9.5 ms for the single-read kernel against 4.4 + 3.7 ms for the two separate first kernels
+        // (it saves 9 GB of HBM traffic but is issue-bound, not HBM-bound), so it is not the default.
+        bool fuse = overlap == 3 && in && in->clean && in->deg && in->batch >= 16 && in->n > 0 && in->stride >= in->n &&
+                    in->n < (int64_t(1) << 30) && pctx->rs_orig == pctx->rs_neu && sctx->fast85 && sctx->orig == 8 &&
+                    sctx->neu == 5 && aligned16(in->clean) && aligned16(in->deg) && in->stride % 4 == 0 && ws_pesq &&
+                    ws_stoi;
+        if (fuse) {
+            const PesqPlan pp = pesq_plan(pctx, in->batch, in->n, kFpQuantum);
+            const StoiPlan sp = stoi_plan(sctx, in->batch, in->n);
+            fuse = pp.tiled && ws_pesq_bytes >= pp.total && ws_stoi_bytes >= sp.total &&
+                   (in->lengths || pesq_num_frames(pp.n) >= 20);
+            if (fuse) {
+                char* wp = static_cast<char*>(ws_pesq);
+                char* wsb = static_cast<char*>(ws_stoi);
+                int32_t* order = nullptr;
+                if (in->lengths) {
+                    order = reinterpret_cast<int32_t*>(wp + pp.off_order);
+                    pesq_order_kernel<<<1, kOrderThreads, 0, stream>>>(in->lengths, in->batch, in->n, order,
+                                                                       reinterpret_cast<int64_t*>(wp + pp.off_fprefix));
+                    FSEM_LAUNCHED();
+                }
+                const int64_t units = 2 * ceil_div(in->batch, 32) * pp.nchunks;
+                const unsigned grid = (unsigned)ceil_div(units, kFpWarps);
+                float* z = reinterpret_cast<float*>(wp + pp.off_z);
+                double* partial = reinterpret_cast<double*>(wp + pp.off_partial);
+                float* y = reinterpret_cast<float*>(wsb + sp.off_y);
+                double2* hops = reinterpret_cast<double2*>(wsb + sp.off_hops);
+                { ProfScope prof_(K_FIRST_PASS, stream);
+                  if (in->lengths)
+                      pesq_stoi_first_pass_kernel<true><<<grid, kFpWarps * 32, kFpDynSmem, stream>>>(
+                          in->clean, in->deg, in->lengths, order, in->batch, in->n, in->stride, pp.chunk, pp.nchunks,
+                          pctx->warm, pctx->coef, sctx->taps85, sctx->win_arg, z, pp.zstride, partial, y, sp.ystride, hops,
+                          sp.hops_max);
+                  else
+                      pesq_stoi_first_pass_kernel<false><<<grid, kFpWarps * 32, kFpDynSmem, stream>>>(
+                          in->clean, in->deg, nullptr, nullptr, in->batch, in->n, in->stride, pp.chunk, pp.nchunks,
+                          pctx->warm, pctx->coef, sctx->taps85, sctx->win_arg, z, pp.zstride, partial, y, sp.ystride, hops,
+                          sp.hops_max); }
+                FSEM_LAUNCHED();
+                g_hook.first_pass_done = true;
+                g_hook.chunk_quantum = kFpQuantum;
+            }
+        }
         int rc = fsem_pesq_score_f32(pctx, in, mos_out, pesq_status_out, ws_pesq, ws_pesq_bytes, stream);
-        if (rc != FSEM_OK) return rc;
-        return fsem_stoi_score_f32(sctx, in, stoi_out, estoi_out, kept_frames_out, stoi_status_out, ws_stoi,
-                                   ws_stoi_bytes, stream);
+        if (rc == FSEM_OK)
+            rc = fsem_stoi_score_f32(sctx, in, stoi_out, estoi_out, kept_frames_out, stoi_status_out, ws_stoi,
+                                     ws_stoi_bytes, stream);
+        g_hook = OverlapHook{};
+        return rc;
     }
     if (!pctx->side) {
         FSEM_CUDA(cudaStreamCreateWithFlags(&pctx->side, cudaStreamNonBlocking));

@@ -4,7 +4,9 @@ Callers of the reference always score both metrics on the same pair of tensors
 (README.md:29-30, benchmark_metrics.py:22,24).  With host tensors the PCIe copy dominates the
 end-to-end time, so `score_pesq_stoi` hands the pair to the library once: every chunk is copied
 once and both kernel pipelines run on it.  Results are identical to
-calling the two metric objects separately.
+calling the two metric objects separately.  (A single-READ first-pass kernel exists as well --
+`score_pesq_stoi_tensors(..., overlap=3)` -- but it is slower than the two separate first kernels on
+B200, see include/fsem.h.)
 """
 from __future__ import annotations
 
@@ -22,9 +24,9 @@ def score_pesq_stoi_tensors(pesq: PESQ, stoi: STOI, clean: torch.Tensor, deg: to
                             overlap: int = 0):
     """Device-resident scoring of both metrics: [B, n] float32 CUDA tensors -> (scores[3, B] f32 = PESQ / STOI /
     ESTOI rows, pesq_status[B], kept_frames[B], stoi_status[B]) CUDA tensors; stream-ordered, no host sync.
-    overlap = 0 (default) runs the two kernel chains back to back; 1 / 2 run the STOI chain on a second stream next
-    to PESQ's spectrum kernel (C ABI fsem_pesq_stoi_score_f32) -- measured on B200: no gain (21.4 vs 21.5 ms) because
-    the spectrum kernel needs its full occupancy, so the default stays sequential.  Results are identical."""
+    overlap = 0 (default): the two kernel chains back to back; 1 / 2: the STOI chain on a second stream next to
+    PESQ's spectrum kernel (measured on B200: no gain); 3: single-read first pass (one kernel feeds both metrics
+    from one read of the input; measured slower).  See include/fsem.h (fsem_pesq_stoi_score_f32)."""
     b, n = clean.shape
     lens = pesq._lengths_tensor(lengths, b, n, clean.device)
     scores = torch.empty(3, b, dtype=torch.float32, device=clean.device)

@@ -220,6 +220,47 @@ def test_fused_upload_equals_separate_calls(pesq, stoi_metrics):
     assert np.array_equal(np.array([r["STOI"] for r in both]), np.array([r["STOI"] for r in sep_s]), equal_nan=True)
 
 
+@pytest.mark.parametrize("shape", [(64, 48000, False), (33, 40004, False), (40, 64000, True), (16, 17000, True),
+                                   (150, 5380, False)])
+def test_single_read_first_pass_matches_the_two_separate_kernels(shape, pesq, stoi_metrics):
+    """fsem_pesq_stoi_score_f32 with overlap = 3 runs ONE first-pass kernel that reads every sample once and
+    produces PESQ's filtered signal + band power and STOI's 10 kHz signal + hop energies; overlap = 0 runs the two
+    separate first kernels.  The 10 kHz signals must be bit-identical, the silent-frame masks and K equal,
+    STOI/ESTOI equal; PESQ agrees to the chunk-grid noise (the single-read pass cuts the IIR time axis on a
+    1024-sample grid instead of a 64-sample one: the same effect as changing the batch size)."""
+    from fast_speech_enhancement_metrics_b200 import score_pesq_stoi_tensors
+    from fast_speech_enhancement_metrics_b200.synth import synth_batch
+    b, n, ragged = shape
+    clean, deg, _ = synth_batch(4242 + b, b, n)
+    c, d = torch.from_numpy(clean).cuda(), torch.from_numpy(deg).cuda()
+    lens = None
+    if ragged:
+        lens = np.random.default_rng(b).integers(5400, n + 1, size=b)
+        lens[0], lens[-1] = n, 5400
+        lens = lens.tolist()
+    st = stoi_metrics(16000)
+    out = {}
+    for mode in (0, 3):
+        scores, pst, kept, sst = score_pesq_stoi_tensors(pesq, st, c, d, lens, overlap=mode)
+        taps = st.debug_taps()
+        bark, power = pesq.debug_taps()
+        out[mode] = dict(scores=scores.cpu().numpy(), pst=pst.cpu().numpy(), kept=kept.cpu().numpy(), sst=sst.cpu().numpy(),
+                         y=taps["resampled"].cpu().numpy(), mask=taps["mask"].cpu().numpy(), tob=taps["tob"].cpu().numpy(),
+                         power=power.cpu().numpy())
+    sep, one = out[0], out[3]
+    L = [(5 * (n if lens is None else lens[i]) + 7) // 8 for i in range(b)]
+    for i in range(b):
+        assert np.array_equal(sep["y"][:, i, :L[i]], one["y"][:, i, :L[i]]), i        # 10 kHz signals: bit-identical
+    assert np.array_equal(sep["mask"], one["mask"]) and np.array_equal(sep["kept"], one["kept"])
+    assert np.array_equal(sep["pst"], one["pst"]) and np.array_equal(sep["sst"], one["sst"])
+    assert np.array_equal(sep["scores"][1:], one["scores"][1:], equal_nan=True)       # STOI, ESTOI
+    assert np.allclose(sep["power"], one["power"], rtol=2e-5, atol=0)                 # band power: chunk-grid noise only
+    d_pesq = np.abs(sep["scores"][0] - one["scores"][0])
+    # 20-frame items (the 5380-sample shape) are the most sensitive to where the chunk boundaries fall: 2.5e-5 there
+    assert np.nanmax(d_pesq) <= (5e-5 if n < 16000 else 1e-5), np.nanmax(d_pesq)
+    _report("first_pass_vs_separate_pesq_%dx%d%s" % (b, n, "_ragged" if ragged else ""), float(np.nanmax(d_pesq)))
+
+
 def test_stoi_errors(stoi_metrics, golden_stoi):
     metric = stoi_metrics(10000)
     assert int(golden_stoi["err_no_segments"]) == 1
