@@ -466,6 +466,23 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
     }
     if (!first_pass_done) {   // kernel A
         const bool vec4 = aligned16(in->clean) && aligned16(in->deg) && (in->stride % 4 == 0);
+#ifdef FSEM_FILTER_RING
+        if (vec4 && p.tiled) {   // A/B variant: the IIR pass on the cp.async tile ring of fsem_first_pass.cuh
+            const int64_t units = 2 * ceil_div(in->batch, 32) * p.nchunks;
+            const unsigned grid = (unsigned)ceil_div(units, kFpWarps);
+            StoiWindowArg nowin{};
+            Resample85Taps notaps{};
+            { ProfScope prof_(K_PESQ_FILTER, stream);
+              if (in->lengths)
+                  pesq_stoi_first_pass_kernel<true, false><<<grid, kFpWarps * 32, kFpIirDynSmem, stream>>>(
+                      in->clean, in->deg, in->lengths, order, in->batch, in->n, in->stride, p.chunk, p.nchunks,
+                      ctx->warm, ctx->coef, notaps, nowin, z, p.zstride, partial, nullptr, 0, nullptr, 0);
+              else
+                  pesq_stoi_first_pass_kernel<false, false><<<grid, kFpWarps * 32, kFpIirDynSmem, stream>>>(
+                      in->clean, in->deg, nullptr, nullptr, in->batch, in->n, in->stride, p.chunk, p.nchunks,
+                      ctx->warm, ctx->coef, notaps, nowin, z, p.zstride, partial, nullptr, 0, nullptr, 0); }
+        } else
+#endif
         if (vec4 && p.tiled) {
             const int64_t units = 2 * ceil_div(in->batch, 32) * p.nchunks;
             const unsigned grid = (unsigned)ceil_div(units, kFiltWarps);

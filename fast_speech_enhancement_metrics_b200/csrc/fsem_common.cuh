@@ -77,6 +77,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // order earlier generic-proxy shared-memory accesses before later async-proxy (bulk copy) writes
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// 16-byte read-only load that asks L2 to fetch the whole 256-byte block around the address: for row-strided tile
+// walks (128 bytes per row and step) every other step then hits L2 and each DRAM page is opened half as often
+__device__ __forceinline__ float4 ldg_f4_l2_256(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L2::256B.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
 __device__ __forceinline__ int item_length(const int32_t* lengths, int64_t item, int64_t n) {
     if (lengths == nullptr) return (int)n;
     int l = lengths[item];

@@ -29,10 +29,11 @@ constexpr int kFpOutPitch = 22;      // floats per staged output row: 20 outputs
 constexpr int kFpQuantum = 1024;     // chunk granularity in input samples (5 hops of 128 outputs)
 constexpr int kFpWarpFloats = 32 * kFpRingPitch + 32 * kFpOutPitch;
 constexpr size_t kFpDynSmem = sizeof(float) * kFpWarps * kFpWarpFloats;
+constexpr size_t kFpIirDynSmem = sizeof(float) * kFpWarps * 32 * kFpRingPitch;   // kResample = false: no output staging
 
 // 16-byte asynchronous global -> shared copy (LDGSTS); bytes beyond `src_bytes` are zero-filled
 __device__ __forceinline__ void cp_async16(float* dst, const float* src, int src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+    asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int kPending>
@@ -44,7 +45,9 @@ struct StoiWindowArg { float w[FSEM_STOI_WIN]; };
 #ifndef FSEM_FP_MINBLOCKS
 #define FSEM_FP_MINBLOCKS 7
 #endif
-template <bool kHasLengths>
+// kResample = false: the same tile ring and IIR code without the STOI half (no FIR, no y, no hop energies) -- the
+// IIR pass on its own with the cp.async prefetch (the raw tile lands two iterations before the IIRs reach it).
+template <bool kHasLengths, bool kResample = true>
 __global__ void __launch_bounds__(kFpWarps * 32, FSEM_FP_MINBLOCKS)
 pesq_stoi_first_pass_kernel(const float* __restrict__ clean, const float* __restrict__ deg,
                             const int32_t* __restrict__ lengths, const int32_t* __restrict__ order, int64_t batch,
@@ -56,7 +59,7 @@ pesq_stoi_first_pass_kernel(const float* __restrict__ clean, const float* __rest
     extern __shared__ __align__(16) float s_dyn[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    float* ring = s_dyn + warp * kFpWarpFloats;
+    float* ring = s_dyn + warp * (kResample ? kFpWarpFloats : 32 * kFpRingPitch);
     float* stage = ring + 32 * kFpRingPitch;
 
     const int64_t groups = ceil_div(batch, 32);
@@ -157,11 +160,17 @@ pesq_stoi_first_pass_kernel(const float* __restrict__ clean, const float* __rest
     for (int i = i_first; i <= i_end; ++i) {
         const int t = i * 32;
         // ---- (a) tile i + 1 goes into the slot drained in the previous iteration; wait for tile i
-        if (i < i_end) { issue_tile(t + 32, sn); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
+        if (kResample) {                                     // the FIR needs tile i now
+            if (i < i_end) { issue_tile(t + 32, sn); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+        } else {                                             // IIR only: tile i - 1 is needed, tiles i and i + 1 may be in flight
+            if (i + 1 < i_end) { issue_tile(t + 32, sn); cp_async_wait<2>(); }
+            else if (i < i_end) cp_async_wait<1>();
+            else cp_async_wait<0>();
+        }
         __syncwarp();
         // ---- (b) resampler: blocks kb = 4i-2 .. 4i+1 (inputs [t-16, t+16)), outputs o = 20i-10 .. 20i+9
-        const bool rs_any = (t + 16 > t_acc) && (t - 16 < t_own_end);
+        const bool rs_any = kResample && (t + 16 > t_acc) && (t - 16 < t_own_end);
         if (rs_any) {
 #pragma unroll 1
             for (int bp = 0; bp < 2; ++bp) {
@@ -281,9 +290,10 @@ pesq_stoi_first_pass_kernel(const float* __restrict__ clean, const float* __rest
             float acc = 0.f;
             if (tp >= 16 && tp + 48 <= len) {
                 float acc2 = 0.f;
+                float4 q = *reinterpret_cast<const float4*>(prow);
 #pragma unroll 1
                 for (int g = 0; g < 8; ++g) {
-                    float4 q = *reinterpret_cast<const float4*>(prow + 4 * g);
+                    const float4 qn = *reinterpret_cast<const float4*>(prow + 4 * min(g + 1, 7));   // next group: hides the LDS latency
                     float y0 = bandpass_step(P, st, q.x); float z0 = preemph_step(P, st, q.x);
                     float y1 = bandpass_step(P, st, q.y); float z1 = preemph_step(P, st, q.y);
                     float y2 = bandpass_step(P, st, q.z); float z2 = preemph_step(P, st, q.z);
@@ -291,6 +301,7 @@ pesq_stoi_first_pass_kernel(const float* __restrict__ clean, const float* __rest
                     acc = fmaf(y0, y0, acc); acc2 = fmaf(y1, y1, acc2);
                     acc = fmaf(y2, y2, acc); acc2 = fmaf(y3, y3, acc2);
                     *reinterpret_cast<float4*>(prow + 4 * g) = make_float4(z0, z1, z2, z3);
+                    q = qn;
                 }
                 acc += acc2;
             } else if (tp < len) {

