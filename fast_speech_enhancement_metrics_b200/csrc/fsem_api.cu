@@ -181,15 +181,6 @@ int64_t host_chunk_items(int64_t batch, int64_t n) {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// host rows [cnt, n] (pitch `sstride` floats) -> device rows (pitch `dstride` floats); one flat copy when both are dense
-cudaError_t copy_rows_h2d(float* dst, int64_t dstride, const float* src, int64_t sstride, int64_t n, int64_t cnt,
-                          cudaStream_t stream) {
-    if (sstride == n && dstride == n)
-        return cudaMemcpyAsync(dst, src, sizeof(float) * n * cnt, cudaMemcpyHostToDevice, stream);
-    return cudaMemcpy2DAsync(dst, dstride * sizeof(float), src, sstride * sizeof(float), n * sizeof(float), cnt,
-                             cudaMemcpyHostToDevice, stream);
-}
-
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -362,6 +353,9 @@ extern "C" int fsem_pesq_create(fsem_pesq_ctx_t** out, const fsem_pesq_design_t*
     }
     e = cudaFuncSetAttribute(pesq_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpecDynSmem);
     if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(pesq_bark_kernel<kBarkThreadsWide, kBarkTileWide>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bark_dyn_smem(kBarkTileWide));
+    if (e == cudaSuccess)
         e = cudaFuncSetAttribute(pesq_stoi_first_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)kFpDynSmem);
     if (e == cudaSuccess)
@@ -525,9 +519,16 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
     }
     {   // kernel C
         { ProfScope prof_(K_PESQ_BARK, stream);
-          pesq_bark_kernel<<<(unsigned)in->batch, kBarkThreads, 0, stream>>>(bark, partial, p.nchunks, in->lengths, order,
-                                                                            in->batch, in->n, p.tmax, ctx->d_tab, dist,
-                                                                            mos_out, status_out, power); }
+          if (in->batch <= ctx->dev.sms)   // cannot fill the SMs anyway: one wide CTA per item, few serial tile rounds
+              pesq_bark_kernel<kBarkThreadsWide, kBarkTileWide>
+                  <<<(unsigned)in->batch, kBarkThreadsWide, bark_dyn_smem(kBarkTileWide), stream>>>(
+                      bark, partial, p.nchunks, in->lengths, order, in->batch, in->n, p.tmax, ctx->d_tab, dist, mos_out,
+                      status_out, power);
+          else
+              pesq_bark_kernel<kBarkThreads, kBarkTile>
+                  <<<(unsigned)in->batch, kBarkThreads, bark_dyn_smem(kBarkTile), stream>>>(
+                      bark, partial, p.nchunks, in->lengths, order, in->batch, in->n, p.tmax, ctx->d_tab, dist, mos_out,
+                      status_out, power); }
         FSEM_LAUNCHED();
     }
     return FSEM_OK;

@@ -278,12 +278,12 @@ pesq_filter_tiled_kernel(const float* __restrict__ clean, const float* __restric
     if (t < t_stop) fetch(t, pre);
     for (; t < t_stop; t += 32) {
         // fill the tile with the prefetched segment, then prefetch the next one
-#pragma unroll
 #ifndef FSEM_FILTER_DRAIN32
         const int cs = ((t >> 5) & 1) * 32;                  // slot of this tile
 #else
         constexpr int cs = 0;
 #endif
+#pragma unroll
         for (int i = 0; i < 8; ++i)
             *reinterpret_cast<float4*>(tile + ((lane >> 3) + 4 * i) * kFiltPitch + cs + col) = pre[i];
         __syncwarp();
@@ -588,9 +588,15 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
 
 // ------------------------------------------------------------------------------------------------
 // Kernel C: one CTA per item; Bark-domain model.
+// Two shapes of the same code: (128 threads, 64-frame tiles) for throughput -- 8 CTAs per SM hide each other's
+// barriers (128-frame tiles were slower) -- and (640 threads, 320-frame tiles) for batches that cannot fill the SMs
+// anyway, where the kernel's latency is the number of serial tile rounds (2 instead of 10 for a 10 s utterance).
+// Frame tiles live in dynamic shared memory: 2 x kTile x 49 Bark powers + the per-frame flags.
 constexpr int kBarkThreads = 128;
-constexpr int kBarkTile = 64;   // frames per shared-memory tile; two threads per frame (128 frames/tile was slower: fewer
-                                // resident CTAs to hide the barriers)
+constexpr int kBarkTile = 64;
+constexpr int kBarkThreadsWide = 640;
+constexpr int kBarkTileWide = 320;
+__host__ __device__ constexpr size_t bark_dyn_smem(int tile) { return tile <= 64 ? 0 : sizeof(float) * (size_t)tile * (2 * FSEM_PESQ_NBANDS + 2); }
 
 // x^y for x > 0 through the SFU (lg2.approx / ex2.approx): relative error ~1e-6 for the exponents used here
 // (|y * log2 x| < 10), three orders of magnitude inside the PESQ budget and ~20x cheaper than powf.
@@ -602,21 +608,32 @@ __device__ __forceinline__ float zwicker_loudness(float p, float thr, float inv_
     return (p <= thr) ? 0.f : l;   // NaN p: comparison false -> l (NaN) propagates like the reference
 }
 
-__global__ void __launch_bounds__(kBarkThreads)
+template <int kThreads, int kTile>
+__global__ void __launch_bounds__(kThreads)
 pesq_bark_kernel(const float* __restrict__ bark, const double* __restrict__ partial, int nchunks,
                  const int32_t* __restrict__ lengths, const int32_t* __restrict__ order, int64_t batch, int64_t n, int tmax,
                  const PesqTables* __restrict__ tab, float* __restrict__ dist_ws /* [2][batch][tmax] */,
                  float* __restrict__ mos_out, int32_t* __restrict__ status_out,
                  double* __restrict__ power_out /* [2][batch] */) {
-    __shared__ float s_tile[2][kBarkTile][FSEM_PESQ_NBANDS];
+    static_assert(kThreads == 2 * kTile && kThreads % 32 == 0 && kThreads >= 2 * FSEM_PESQ_NBANDS, "two threads per frame of a tile");
+    // the throughput shape keeps its tiles in static arrays (the compiler schedules the unrolled band loops better
+    // around provably distinct arrays: 1.40 vs 1.85 ms at 8192 items); only the wide shape needs dynamic memory
+    constexpr bool kDyn = bark_dyn_smem(kTile) > 0;
+    extern __shared__ __align__(16) float s_bark_dyn[];
+    __shared__ float s_tile_st[kDyn ? 1 : 2][kDyn ? 1 : kTile][FSEM_PESQ_NBANDS];
+    __shared__ float s_silent_st[kDyn ? 1 : kTile];
+    __shared__ float s_fr_st[kDyn ? 1 : kTile];
+    float (*s_tile)[kTile][FSEM_PESQ_NBANDS] =
+        kDyn ? reinterpret_cast<float (*)[kTile][FSEM_PESQ_NBANDS]>(s_bark_dyn)
+             : reinterpret_cast<float (*)[kTile][FSEM_PESQ_NBANDS]>(&s_tile_st[0][0][0]);
+    float* s_silent = kDyn ? s_bark_dyn + 2 * kTile * FSEM_PESQ_NBANDS : s_silent_st;
+    float* s_fr = kDyn ? s_bark_dyn + 2 * kTile * FSEM_PESQ_NBANDS + kTile : s_fr_st;
     __shared__ float s_thr[FSEM_PESQ_NBANDS], s_ithr[FSEM_PESQ_NBANDS], s_exp[FSEM_PESQ_NBANDS],
         s_lsc[FSEM_PESQ_NBANDS], s_w[FSEM_PESQ_NBANDS], s_ratio[FSEM_PESQ_NBANDS];
-    __shared__ float s_silent[kBarkTile];
-    __shared__ float s_fr[kBarkTile];
     __shared__ float s_g2[2];
     __shared__ float s_carry;
     __shared__ double s_mean[2][FSEM_PESQ_NBANDS];
-    __shared__ float s_red[2][kBarkThreads / 32];
+    __shared__ float s_red[2][kThreads / 32];
 
     const int tid = threadIdx.x;
     // ragged batches: CTAs are scheduled in launch order, so the longest items go first (no long item left for the tail)
@@ -658,7 +675,7 @@ pesq_bark_kernel(const float* __restrict__ bark, const double* __restrict__ part
         const float* srcd = bd + (int64_t)f0 * FSEM_PESQ_NBANDS;
         float* dc = &s_tile[0][0][0];
         float* dd = &s_tile[1][0][0];
-        for (int i = tid; i < cnt; i += kBarkThreads) {
+        for (int i = tid; i < cnt; i += kThreads) {
             dc[i] = __ldg(srcc + i) * g2c;
             dd[i] = __ldg(srcd + i) * g2d;
         }
@@ -668,8 +685,8 @@ pesq_bark_kernel(const float* __restrict__ bark, const double* __restrict__ part
     double band_acc = 0.0;   // thread t < 98: signal t / 49, band t % 49
     const int my_sig = tid / FSEM_PESQ_NBANDS;
     const int my_band = tid - my_sig * FSEM_PESQ_NBANDS;
-    for (int f0 = 0; f0 < T; f0 += kBarkTile) {
-        const int nf = min(kBarkTile, T - f0);
+    for (int f0 = 0; f0 < T; f0 += kTile) {
+        const int nf = min(kTile, T - f0);
         __syncthreads();
         load_tile(f0, nf);
         __syncthreads();
@@ -710,8 +727,8 @@ pesq_bark_kernel(const float* __restrict__ bark, const double* __restrict__ part
     float* __restrict__ dasym = dist_ws + (batch + item) * (int64_t)tmax;
 
     // ---- phase 2: frame equalisation, loudness, disturbances (PESQ.py:149-224)
-    for (int f0 = 0; f0 < T; f0 += kBarkTile) {
-        const int nf = min(kBarkTile, T - f0);
+    for (int f0 = 0; f0 < T; f0 += kTile) {
+        const int nf = min(kTile, T - f0);
         __syncthreads();
         load_tile(f0, nf);
         __syncthreads();
@@ -781,7 +798,7 @@ pesq_bark_kernel(const float* __restrict__ bark, const double* __restrict__ part
     // ---- phase 3: L6 over 20-frame windows (hop 10), L2 across windows, MOS (PESQ.py:168-172, 240-243)
     const int W = (T - 20) / 10 + 1;
     float acc_s = 0.f, acc_a = 0.f;
-    for (int w = tid; w < W; w += kBarkThreads) {
+    for (int w = tid; w < W; w += kThreads) {
         float s6 = 0.f, a6 = 0.f;
 #pragma unroll 4
         for (int j = 0; j < 20; ++j) {
@@ -800,7 +817,7 @@ pesq_bark_kernel(const float* __restrict__ bark, const double* __restrict__ part
     __syncthreads();
     if (tid == 0) {
         float ts = 0.f, ta = 0.f;
-        for (int i = 0; i < kBarkThreads / 32; ++i) { ts += s_red[0][i]; ta += s_red[1][i]; }
+        for (int i = 0; i < kThreads / 32; ++i) { ts += s_red[0][i]; ta += s_red[1][i]; }
         float d_sym = sqrtf(ts / (float)W), d_asym = sqrtf(ta / (float)W);
         float mos = 4.5f - 0.1f * d_sym - 0.0309f * d_asym;
         mos = 0.999f + 4.f / (1.f + expf(-1.3669f * mos + 3.8224f));
