@@ -16,8 +16,15 @@ one STOI call over the whole (sharded) batch = 81 920 audio-seconds.
   roofline: dominant kernel (largest device time in the step, measured live with CUDA events around
            every launch): algorithmic bytes of its metric call (8 B per sample pair = 128 000 B per
            audio-second) / its average duration, against MEASURED_PEAKS.json's hbm_gbs.
-  cpu_baseline / --impl reference: the numpy oracle port (oracle/) of the reference's CPU path on the
-           host cores (one process per core), on a bounded sample of the same workload.
+  roofline_call: the same per metric CALL (all kernels of the PESQ call / of the STOI call against the bytes
+           the call must read), roofline_step for the whole step -- the dominant kernel's fraction is not the path's.
+  parity : outside the timed region, a seeded sample of the SAME device tensors (>= 32 items per rank, spread over
+           the shard) is scored by the float64 oracle port and, when oracle/_ref is staged, by the unmodified
+           reference; reports max |dPESQ|, |dSTOI|, |dESTOI|, K equality, the smallest silent-frame decision margin
+           of the whole batch and, for N > 1, that the all-gathered rows equal rank-local scoring bit for bit.
+  cpu_baseline / --impl reference: the reference's own CPU path (oracle/_ref: the unmodified reference modules,
+           `PESQ(16000, use_gpu=False)` + `STOI(16000, use_gpu=False)` on 64-item chunks) on the host cores, on a
+           bounded sample of the same workload; the numpy port (oracle/) beside it / as fallback.
 """
 from __future__ import annotations
 
@@ -123,109 +130,128 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU baseline
-_CPU_DATA = None      # (clean[items, n], deg[items, n]) generated in the parent, inherited by the forked workers
+def workload_string(batch: int, seconds: float, gpus: int) -> str:
+    """config.workload: identical in the GPU arm and the reference arm."""
+    return ("PESQ + STOI/ESTOI, %d x %.0f s @16 kHz, batch-sharded over %d GPU(s) (BASELINE configs[4])"
+            % (batch, seconds, gpus))
 
 
-_CPU_LIMITER = None
-
-
-def _cpu_init():
-    # one scoring thread per worker process: keep BLAS / OpenMP pools from oversubscribing the cores
-    global _CPU_LIMITER
-    os.environ["OMP_NUM_THREADS"] = "1"
-    try:
-        from threadpoolctl import threadpool_limits
-        _CPU_LIMITER = threadpool_limits(limits=1)
-    except Exception:
-        pass
-    from oracle import pesq_oracle, stoi_oracle  # noqa: F401  (pay the imports outside the timed region)
-
-
-def _cpu_worker(i):
-    from oracle import pesq_oracle, stoi_oracle
-    clean, deg = _CPU_DATA
-    p = pesq_oracle.pesq_batch(clean[i:i + 1], deg[i:i + 1])
-    s, e, _ = stoi_oracle.stoi_batch(clean[i:i + 1], deg[i:i + 1], FS)
-    return float(p[0]), float(s[0]), float(e[0])
-
-
-class CpuOraclePool:
-    """The numpy oracle port of the reference's CPU path (PESQ + STOI per item), one worker process per
-    host core.  Inputs are generated once in the parent; the timed region is scoring only."""
-
-    def __init__(self, n: int, items: int, cores: int):
-        global _CPU_DATA
-        import multiprocessing as mp
-
-        from fast_speech_enhancement_metrics_b200.synth import synth_batch
-        clean, deg, _ = synth_batch(4242, items, n)
-        _CPU_DATA = (clean, deg)
-        self.items, self.n, self.cores = items, n, cores
-        self.pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init)
-        self.pool.map(_cpu_worker, [i % items for i in range(2 * cores)], chunksize=1)      # warm every worker
-
-    def step(self) -> float:
-        t0 = time.perf_counter()
-        self.pool.map(_cpu_worker, range(self.items), chunksize=1)
-        return time.perf_counter() - t0
-
-    def close(self):
-        self.pool.close()
-        self.pool.join()
-
-
-def cpu_baseline(n: int, items: int, cores: int, repeats: int = 2) -> dict:
-    pool = CpuOraclePool(n, items, cores)
-    best = min(pool.step() for _ in range(repeats))
-    pool.close()
-    audio_s = items * n / FS
-    return {"value": audio_s / best, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d items x %.0f s (PESQ+STOI per item, numpy oracle port of the reference CPU path, "
-                      "%d worker processes, best of %d, inputs pre-generated)" % (items, n / FS, cores, repeats),
-            "seconds": best}
-
-
-def host_cores() -> int:
-    try:
-        return max(1, len(os.sched_getaffinity(0)))
-    except AttributeError:
-        return max(1, os.cpu_count() or 1)
+def newest_traffic_file():
+    """profiles/rNN_dram_traffic.json of the latest round (written by tools/ncu_launches_summary.py from the ncu
+    launch list of THIS code), else None."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r[0-9][0-9]_dram_traffic.json")))
+    return files[-1] if files else None
 
 
 # ------------------------------------------------------------------------------------------ reference arm
 def run_reference(args, emit):
+    """The reference's own CPU implementation of the path on the host cores (oracle/_ref when staged, else the
+    numpy port), every step a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = host_cores()
+    from oracle import cpu_arm
+    cores = cpu_arm.host_cores()
     n = int(args.seconds * FS)
-    items = max(8 * cores, 64)
-    pool = CpuOraclePool(n, items, cores)
+    kind = cpu_arm.pick_kind()
+    procs, threads, items = cpu_arm.plan(kind, cores)
+    arm = cpu_arm.CpuArm(kind, n, procs, threads, items)
     times = []
     for step in range(args.warmup + args.steps):
-        dt = pool.step()
+        dt = arm.step()
         if step >= args.warmup:
             times.append(dt)
-    pool.close()
-    audio_s = items * n / FS
+    finite = arm.finite
+    arm.close()
+    audio_s = arm.audio_seconds_per_step
     total = sum(times)
     value = audio_s * len(times) / total
+    sample = ("%d worker processes x %d items x %.0f s per step; %s; inputs pre-generated"
+              % (procs, items, args.seconds, cpu_arm._describe(kind, threads)))
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-        "config": {"workload": "PESQ+STOI/ESTOI, %d x %.0f s @16 kHz (BASELINE configs[4]); each step a bounded "
-                               "sample of %d items" % (args.batch, args.seconds, items),
-                   "sample_items_per_step": items},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d items x %.0f s per step, numpy oracle port of the reference CPU path "
-                                   "(use_gpu=False), %d worker processes, inputs pre-generated"
-                                   % (items, args.seconds, cores)},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32" if kind == "reference" else "f64",
+        "data": "synthetic", "impl": "reference",
+        "config": {"workload": workload_string(args.batch, args.seconds, args.gpus),
+                   "batch_total": args.batch, "samples": n, "sample_rate": FS,
+                   "sample_items_per_step": procs * items,
+                   "note": "each step scores a bounded sample of the workload on the host cores"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "procs": procs,
+                         "threads_per_proc": threads, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "finite_score_fraction": finite,
     }
     emit(line)
     return 0
+
+
+# ------------------------------------------------------------------------------------------ parity at the workload
+def parity_block(pesq, stoi, clean, deg, gathered, lo, hi, world, device, items):
+    """Outside the timed region: the rank's shard is scored once more (same kernels, same chunk grid as the timed
+    steps), a seeded sample of `items` rows spread over the shard is checked against the float64 oracle port and --
+    when oracle/_ref is staged -- the unmodified reference, and the all-gathered table of the last timed step is
+    compared bit for bit with rank-local scoring.  Bars: 1e-3 / 1e-4 / exact."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from oracle import make_ref, pesq_oracle, stoi_oracle
+    local_b = clean.shape[0]
+    mos, _ = pesq.score_tensors(clean, deg)
+    sc, kept, _ = stoi.score_tensors(clean, deg)
+    margin = stoi.mask_margin()
+    local = torch.stack([mos, sc[0], sc[1]], dim=1)
+    torch.cuda.synchronize()
+    # bit-for-bit (NaN-safe): compare the raw words
+    gather_equal = bool(torch.equal(gathered[lo:hi].contiguous().view(torch.int32), local.contiguous().view(torch.int32)))
+    idx = np.unique(np.linspace(0, local_b - 1, min(items, local_b)).round().astype(np.int64))
+    tidx = torch.from_numpy(idx).to(device)
+    c = clean[tidx].cpu()
+    d = deg[tidx].cpu()
+    got = local[tidx].double().cpu().numpy()
+    k_got = kept[tidx].cpu().numpy()
+
+    def maxabs(a, b):
+        both_nan = np.isnan(a) & np.isnan(b)
+        diff = np.where(both_nan, 0.0, np.abs(a - b))
+        return float(np.max(np.where(np.isnan(diff), np.inf, diff))) if len(a) else 0.0
+
+    o_p = pesq_oracle.pesq_batch(c.numpy(), d.numpy())
+    o_s, o_e, o_k = stoi_oracle.stoi_batch(c.numpy(), d.numpy(), FS)
+    stats = [maxabs(got[:, 0], o_p), maxabs(got[:, 1], o_s), maxabs(got[:, 2], o_e)]
+    k_equal = bool(np.array_equal(k_got, o_k))
+    ref_stats = [-1.0, -1.0, -1.0]
+    if make_ref.available():
+        RP, RS = make_ref.load()
+        rp = RP(FS, use_gpu=False)(c, d)
+        rs = RS(FS, use_gpu=False)(c, d)
+        ref_stats = [maxabs(got[:, 0], np.array([r["PESQ"] for r in rp])),
+                     maxabs(got[:, 1], np.array([r["STOI"] for r in rs])),
+                     maxabs(got[:, 2], np.array([r["ESTOI"] for r in rs]))]
+    finite_margin = margin[torch.isfinite(margin)]
+    mmin = float(finite_margin.min()) if finite_margin.numel() else float("inf")
+    near = int((margin < 1e-4).sum())
+    red_max = torch.tensor(stats + ref_stats + [0.0 if k_equal else 1.0, 0.0 if gather_equal else 1.0, -mmin],
+                           dtype=torch.float64, device=device)
+    red_sum = torch.tensor([float(len(idx)), float(near)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(red_max, op=dist.ReduceOp.MAX)
+        dist.all_reduce(red_sum, op=dist.ReduceOp.SUM)
+    m = red_max.tolist()
+    out = {"pesq_max_abs": m[0], "stoi_max_abs": m[1], "estoi_max_abs": m[2], "k_equal": m[6] == 0.0,
+           "items": int(red_sum[0].item()), "vs": "float64 oracle port (oracle/), sample spread over every rank's shard",
+           "bars": {"pesq": 1e-3, "stoi": 1e-4, "estoi": 1e-4, "k": "exact"},
+           "mask_margin_min_db": -m[8], "items_with_margin_below_1e-4_db": int(red_sum[1].item()),
+           "gathered_rows_equal_rank_local_bitwise": m[7] == 0.0}
+    if m[3] >= 0.0:
+        out["vs_reference"] = {"pesq_max_abs": m[3], "stoi_max_abs": m[4], "estoi_max_abs": m[5],
+                               "vs": "oracle/_ref: unmodified reference, use_gpu=False, same sample"}
+    out["ok"] = bool(m[0] <= 1e-3 and m[1] <= 1e-4 and m[2] <= 1e-4 and out["k_equal"]
+                     and out["gathered_rows_equal_rank_local_bitwise"]
+                     and (m[3] < 0 or (m[3] <= 1e-3 and m[4] <= 1e-4 and m[5] <= 1e-4)))
+    return out
 
 
 # ------------------------------------------------------------------------------------------ main arm
@@ -238,11 +264,9 @@ def main():
     ap.add_argument("--batch", type=int, default=8192, help="total items over all ranks")
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--two-streams", action="store_true",
-                    help="experiment: run the PESQ and the STOI kernel chains on two CUDA streams")
-    ap.add_argument("--overlap", type=int, default=-1,
-                    help="experiment: fused device entry fsem_pesq_stoi_score_f32 with overlap mode 0/1/2/3 (3 = single-read first pass)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--parity-items", type=int, default=32, help="items per rank scored by the oracle (outside the timed region)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     # stdout carries exactly ONE JSON line (rank 0): anything libraries print there (e.g. NCCL's version banner) is
@@ -295,27 +319,9 @@ def main():
 
     gathered = torch.empty(args.batch, 3, dtype=torch.float32, device=device)
 
-    side = (torch.cuda.Stream(device), torch.cuda.Stream(device)) if args.two_streams else None
-
-    from fast_speech_enhancement_metrics_b200 import score_pesq_stoi_tensors
-
     def step_device():
-        if args.overlap >= 0:
-            sc3, _, _, _ = score_pesq_stoi_tensors(pesq, stoi, clean, deg, overlap=args.overlap)
-            return gather_scores(sc3.t().contiguous(), args.batch, world, out=gathered)
-        if side is None:
-            mos, _ = pesq.score_tensors(clean, deg)
-            sc, _, _ = stoi.score_tensors(clean, deg)
-        else:
-            cur = torch.cuda.current_stream(device)
-            side[0].wait_stream(cur)
-            side[1].wait_stream(cur)
-            with torch.cuda.stream(side[0]):
-                mos, _ = pesq.score_tensors(clean, deg)
-            with torch.cuda.stream(side[1]):
-                sc, _, _ = stoi.score_tensors(clean, deg)
-            cur.wait_stream(side[0])
-            cur.wait_stream(side[1])
+        mos, _ = pesq.score_tensors(clean, deg)
+        sc, _, _ = stoi.score_tensors(clean, deg)
         local = torch.stack([mos, sc[0], sc[1]], dim=1)
         return gather_scores(local, args.batch, world, out=gathered)
 
@@ -359,6 +365,11 @@ def main():
     value = audio_s_total / (ms_per_step * 1e-3)
     scores = out.cpu().numpy()
     finite = float(np.isfinite(scores).mean())
+
+    # ---- parity at this workload, on these tensors (outside the timed region)
+    parity = None
+    if not args.no_parity:
+        parity = parity_block(pesq, stoi, clean, deg, out, lo, hi, world, device, args.parity_items)
 
     # ---- e2e: public API with pinned host tensors (H2D + compute + D2H every step)
     e2e = None
@@ -439,17 +450,34 @@ def main():
     alg_bytes = BYTES_PER_AUDIO_SECOND_PER_METRIC * local_audio_s          # per launch (one launch per metric call)
     top_avg_ms = top_ms / max(top_cnt, 1)
     achieved = alg_bytes / (top_avg_ms * 1e-3) / 1e9
-    traffic_path = os.path.join(ROOT, "profiles", "dram_traffic.json")
-    traffic = None
-    if os.path.exists(traffic_path):
+    # DRAM traffic per launch: from the ncu launch list of THIS round's code (profiles/rNN_dram_traffic.json, written
+    # by tools/ncu_launches_summary.py); measured at tj["items"] items x 10 s, linear in the item count
+    traffic, traffic_src, tj = None, None, None
+    traffic_path = newest_traffic_file()
+    if traffic_path:
         tj = json.load(open(traffic_path))
         per_launch = tj.get("bytes_per_launch", {}).get(top_name)
-        if per_launch is not None:          # measured with ncu at tj["items"] items x 10 s; linear in the item count
+        if per_launch is not None:
             traffic = per_launch * (local_b * args.seconds) / (tj.get("items", 8192) * 10.0)
+            traffic_src = os.path.relpath(traffic_path, ROOT)
     roofline = {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": top_avg_ms,
-                "note": "FP32-issue-bound path (SURVEY 7.2): the HBM fraction is reported as the metric asks"}
+                "note": "dominant kernel only (one of the kernels of its metric call): see roofline_call / "
+                        "roofline_step for the path; the path is FP32-issue / shared-memory bound (SURVEY 7.2), the "
+                        "HBM fraction is reported because the metric asks for it"}
+    # per metric CALL: all kernels of the call against the bytes the call must read
+    roofline_call = {}
+    for call, prefix in (("PESQ", "pesq_"), ("STOI", "stoi_")):
+        call_ms = sum(v[0] for k, v in prof.items() if k.startswith(prefix)) / args.steps
+        if call_ms > 0:
+            tr = None
+            if tj is not None:
+                tr = sum(b for k, b in tj.get("bytes_per_launch", {}).items() if k.startswith(prefix))
+                tr = tr * (local_b * args.seconds) / (tj.get("items", 8192) * 10.0)
+            roofline_call[call] = {"ms": call_ms, "achieved": alg_bytes / (call_ms * 1e-3) / 1e9, "peak": peak,
+                                   "unit": "GB/s", "frac": alg_bytes / (call_ms * 1e-3) / 1e9 / peak,
+                                   "algorithmic_bytes": alg_bytes, "traffic": tr}
     step_bytes = 2 * BYTES_PER_AUDIO_SECOND_PER_METRIC * local_audio_s
     roofline_step = {"achieved": step_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
@@ -457,21 +485,25 @@ def main():
 
     cpu = None
     if not args.no_cpu and world == 1:
-        cores = host_cores()
-        cpu = cpu_baseline(n, max(64, 32 * cores), cores)      # ~20-30 CPU-seconds of scoring
+        from oracle import cpu_arm
+        cores = cpu_arm.host_cores()
+        kind = cpu_arm.pick_kind()
+        cpu = cpu_arm.measure(kind, n, cores)                  # 1 warm-up + best of 3 steps of 64-item chunks
+        if kind == "reference":                                # the numpy port beside it (round-1 baseline)
+            port = cpu_arm.measure("port", n, cores, repeats=2, single_process=False)
+            cpu["port"] = {k: port[k] for k in ("value", "unit", "procs", "seconds", "sample")}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "PESQ + STOI/ESTOI, %d x %.0f s @16 kHz, batch-sharded over %d GPU(s) "
-                               "(BASELINE configs[4])" % (args.batch, args.seconds, world),
+        "config": {"workload": workload_string(args.batch, args.seconds, world),
                    "batch_total": args.batch, "batch_per_gpu": local_b, "samples": n, "sample_rate": FS,
                    "l2": "inputs (%.1f GB per GPU) exceed L2; no flush" % (2 * local_b * n * 4 / 1e9),
                    "collective": "all_gather of [batch/N, 3] fp32 scores (NCCL)" if world > 1 else "none"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "roofline_step": roofline_step, "kernels": kernels, "cpu_baseline": cpu,
-        "finite_score_fraction": finite,
+        "roofline": roofline, "roofline_call": roofline_call, "roofline_step": roofline_step, "kernels": kernels,
+        "cpu_baseline": cpu, "parity": parity, "finite_score_fraction": finite,
     }
     emit(line)
     if world > 1:

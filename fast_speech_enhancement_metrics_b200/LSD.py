@@ -17,8 +17,7 @@ class LSD(BaseMetric):
 
     def __init__(self, sample_rate: int = 16000, use_gpu: bool = False):
         super().__init__(sample_rate, use_gpu)
-        if self.sample_rate != self.EXPECTED_SAMPLING_RATE:
-            raise NotImplementedError("LSD resample-on-ingest is not built: pass 16 kHz audio")
+        self._make_resampler()                                              # base.py:13 (None at 16 kHz)
         self.nfft, self.hop = 512, 256                                      # LSD.py:12-13
         window = torch.hann_window(self.nfft, dtype=torch.float32)          # LSD.py:16
         self._window = (C.c_float * 512)(*window.tolist())
@@ -35,11 +34,15 @@ class LSD(BaseMetric):
             except Exception:
                 pass
             self._ctx = None
+        self._free_resampler()
 
     def score_tensors(self, clean: torch.Tensor, deg: torch.Tensor, lengths=None) -> torch.Tensor:
         """[B, n] float32 CUDA tensors -> lsd[B] CUDA tensor, stream-ordered, no host synchronisation."""
+        clean, deg = self._on_device(clean), self._on_device(deg)
         b, n = clean.shape
         lens = self._lengths_tensor(lengths, b, n, clean.device)
+        clean, deg, lens = self._resample_pair(clean, deg, lens)            # base.py:19-20
+        b, n = clean.shape
         out = torch.empty(b, dtype=torch.float32, device=clean.device)
         with torch.cuda.device(clean.device):
             ws = self._get_workspace(self._lib.fsem_lsd_workspace_bytes(self._ctx, b, n))
@@ -53,9 +56,6 @@ class LSD(BaseMetric):
 
     def compute_metric(self, clean_speech, denoised_speech, lengths=None) -> list[dict[str, float]]:
         assert clean_speech is not None                                     # LSD.py:36
-        if not clean_speech.is_cuda:                                        # host tensors: plain upload (base.py:18)
-            clean_speech = clean_speech.to(self.device, non_blocking=True)
-            denoised_speech = denoised_speech.to(self.device, non_blocking=True)
-            if clean_speech.dtype != torch.float32:                             # int16 / float16 ingest: widen after the upload
-                clean_speech, denoised_speech = self.prepare_audio(clean_speech), self.prepare_audio(denoised_speech)
+        if not clean_speech.is_cuda:                                        # host tensors (base.py:18)
+            clean_speech, denoised_speech = self._upload(clean_speech, denoised_speech)
         return [{"LSD": v} for v in self.score_tensors(clean_speech, denoised_speech, lengths).cpu().tolist()]

@@ -41,6 +41,7 @@ class PESQ(BaseMetric):
     def score_tensors(self, clean: torch.Tensor, deg: torch.Tensor, lengths=None):
         """Device-resident scoring: returns (mos[B] f32, status[B] i32) CUDA tensors, stream-ordered,
         no host synchronisation.  `clean`/`deg` are [B, n] float32 CUDA tensors."""
+        clean, deg = self._on_device(clean), self._on_device(deg)
         b, n = clean.shape
         lens = self._lengths_tensor(lengths, b, n, clean.device)
         mos = torch.empty(b, dtype=torch.float32, device=clean.device)

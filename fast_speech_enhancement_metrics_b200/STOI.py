@@ -42,6 +42,7 @@ class STOI(BaseMetric):
     def score_tensors(self, clean: torch.Tensor, deg: torch.Tensor, lengths=None):
         """Device-resident scoring: returns (scores[2, B] f32 = STOI row 0 / ESTOI row 1, kept[B] i32,
         status[B] i32) CUDA tensors, stream-ordered, no host synchronisation."""
+        clean, deg = self._on_device(clean), self._on_device(deg)
         b, n = clean.shape
         lens = self._lengths_tensor(lengths, b, n, clean.device)
         scores = torch.empty(2, b, dtype=torch.float32, device=clean.device)
@@ -59,7 +60,22 @@ class STOI(BaseMetric):
                 status.data_ptr(), ws.data_ptr(), ws.numel(),
                 C.c_void_p(torch.cuda.current_stream(clean.device).cuda_stream)))
         self._last_shape = (b, n)
+        self._last_lengths = lens
         return scores, kept, status
+
+    def mask_margin(self) -> torch.Tensor:
+        """After a device-resident score call: margin[B] (CUDA, dB) = min over the item's analysis frames of
+        |(max E - 40) - E_t|, i.e. how far the closest frame was from flipping the keep/drop decision of
+        STOI.py:98-102.  The mask is bit-exact against any fp32 evaluation of the frame norm whenever the
+        margin exceeds the norm's rounding noise (~1e-6 dB); ties are reported by this margin, not hidden."""
+        b, n = self._last_shape
+        lens = getattr(self, "_last_lengths", None)
+        out = torch.empty(b, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.fsem_stoi_mask_margin(
+                self._ctx, b, n, lens.data_ptr() if lens is not None else None, self._workspace.data_ptr(),
+                out.data_ptr(), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return out
 
     def score_host(self, clean: torch.Tensor, deg: torch.Tensor, lengths=None):
         """Host-resident scoring: CPU [B, n] float32 / int16 / float16 tensors in, CPU tensors out."""

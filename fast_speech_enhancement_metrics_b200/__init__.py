@@ -15,4 +15,4 @@ from .SDR import SDR
 from .fused import score_pesq_stoi, score_pesq_stoi_tensors
 
 __all__ = ["BaseMetric", "PESQ", "STOI", "LSD", "SDR", "score_pesq_stoi", "score_pesq_stoi_tensors"]
-__version__ = "0.1.0"
+__version__ = "0.2.0"

@@ -54,8 +54,18 @@ class BaseMetric(ABC):
         code = _lib.dtype_code(audio.dtype)           # raises for float64 & co like the reference
         if audio.stride(1) != 1 or (audio.shape[0] > 1 and audio.stride(0) < audio.shape[1]):
             audio = audio.contiguous()
+        audio = self._on_device(audio)
         if code != _lib.DTYPE_F32 and audio.is_cuda:
             audio = self._ingest(audio, code)
+        return audio
+
+    def _on_device(self, audio: torch.Tensor) -> torch.Tensor:
+        """The context tables, resampler taps and workspace of a metric live on the device that was current at
+        construction (self.device).  A CUDA tensor on ANOTHER device is moved there, as the reference's
+        prepare_audio does with `.to(self.device)` (base.py:18); CPU tensors stay on the host for the library's
+        overlapped upload."""
+        if audio.is_cuda and audio.device != self.device:
+            audio = audio.to(self.device)
         return audio
 
     def _ingest(self, audio: torch.Tensor, code: int) -> torch.Tensor:
@@ -88,6 +98,61 @@ class BaseMetric(ABC):
     def __call__(self, clean_speech, denoised_speech, lengths=None) -> list[dict[str, float]]:
         clean_speech, denoised_speech = self.prepare_inputs(clean_speech, denoised_speech)
         return self.compute_metric(clean_speech, denoised_speech, lengths)
+
+    # ------------------------------------------------------------------ resample-on-ingest (base.py:13,19-20)
+    def _make_resampler(self):
+        """For metrics that do not fuse the resampling into their own first kernel (LSD, SDR): a library
+        resampler context holding torchaudio's sinc-Hann kernel for sample_rate -> EXPECTED_SAMPLING_RATE."""
+        from .design import sinc_hann_kernel
+        self._resampler = None
+        if self.sample_rate == self.EXPECTED_SAMPLING_RATE:
+            return
+        taps, width, o, nw = sinc_hann_kernel(self.sample_rate, self.EXPECTED_SAMPLING_RATE)
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.fsem_resampler_create(C.byref(handle), o, nw, width, taps.shape[1],
+                                                       taps.ctypes.data_as(C.POINTER(C.c_float))))
+        self._resampler = handle
+
+    def _free_resampler(self):
+        r = getattr(self, "_resampler", None)
+        if r is not None and r.value:
+            try:
+                self._lib.fsem_resampler_destroy(r)
+            except Exception:
+                pass
+        self._resampler = None
+
+    def _resample_pair(self, clean: torch.Tensor, deg: torch.Tensor, lens):
+        """[B, n] float32 CUDA rows at sample_rate -> ([B, L] clean, [B, L] deg, lengths or None) at the expected
+        rate, one kernel launch for both signals (fsem_resample_f32)."""
+        if getattr(self, "_resampler", None) is None:
+            return clean, deg, lens
+        b, n = clean.shape
+        L = int(self._lib.fsem_resampled_len(self._resampler, n))
+        pitch = (L + 3) // 4 * 4
+        out = torch.empty(2, b, pitch, dtype=torch.float32, device=self.device)
+        new_lens = torch.empty(b, dtype=torch.int32, device=self.device) if lens is not None else None
+        with torch.cuda.device(self.device):
+            if deg.stride(0) != clean.stride(0) and b > 1:
+                deg = deg.contiguous(); clean = clean.contiguous()
+            batch = _lib.Batch(clean.data_ptr(), deg.data_ptr(), lens.data_ptr() if lens is not None else None,
+                               b, n, clean.stride(0) if b > 1 else max(n, clean.stride(0)))
+            _lib.check(self._lib.fsem_resample_f32(
+                self._resampler, C.byref(batch), out.data_ptr(), pitch,
+                new_lens.data_ptr() if new_lens is not None else None,
+                C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return out[0, :, :L], out[1, :, :L], new_lens
+
+    def _upload(self, clean: torch.Tensor, deg: torch.Tensor):
+        """Host rows -> device rows for the metrics without a chunked host pipeline in the library (LSD, SDR):
+        both copies on the current stream, non-blocking when the host tensors are pinned; 2-byte dtypes cross
+        PCIe as they are and are widened on the device."""
+        clean = clean.to(self.device, non_blocking=True)
+        deg = deg.to(self.device, non_blocking=True)
+        if clean.dtype != torch.float32:
+            clean, deg = self.prepare_audio(clean), self.prepare_audio(deg)
+        return clean, deg
 
     # ------------------------------------------------------------------ helpers
     def _get_workspace(self, nbytes: int) -> torch.Tensor:

@@ -13,7 +13,6 @@
 #include "fsem_lsd.cuh"
 #include "fsem_sdr.cuh"
 #include "fsem_ingest.cuh"
-#include "fsem_first_pass.cuh"
 
 using namespace fsem;
 
@@ -21,18 +20,6 @@ using namespace fsem;
 namespace {
 
 thread_local char g_err[512] = "";
-// set by fsem_pesq_stoi_score_f32 around its call of fsem_pesq_score_f32: event to record right after the IIR pass,
-// and a cap on the spectrum kernel's CTAs per SM so that the other metric's kernels can co-reside
-// first_pass_done: the single-read first pass (fsem_first_pass.cuh) has already produced z / partials (PESQ side,
-// together with the length order and frame prefix) and y / hop energies (STOI side) in the workspaces, with IIR chunks
-// of `chunk_quantum` granularity: the two score functions skip their own first kernels
-struct OverlapHook {
-    cudaEvent_t after_filter = nullptr;
-    int spec_ctas_per_sm = 0;
-    bool first_pass_done = false;
-    int chunk_quantum = 0;
-};
-thread_local OverlapHook g_hook;
 std::atomic<int64_t> g_launches{0};
 
 int fail(int code, const char* fmt, ...) {
@@ -62,11 +49,11 @@ inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 // ---- optional per-kernel timing with CUDA events on the launching stream (bench.py only; not thread-safe)
 enum KernelId {
     K_PESQ_FILTER = 0, K_PESQ_SPECTRUM, K_PESQ_BARK, K_STOI_RESAMPLE, K_STOI_ENERGY, K_STOI_COMPACT,
-    K_STOI_TOB, K_STOI_SEGMENT, K_STOI_FINALIZE, K_PESQ_RESAMPLE, K_LSD_FRAMES, K_SDR_CORR, K_SDR_SOLVE, K_INGEST, K_FIRST_PASS, K_COUNT
+    K_STOI_TOB, K_STOI_SEGMENT, K_STOI_FINALIZE, K_PESQ_RESAMPLE, K_LSD_FRAMES, K_SDR_CORR, K_SDR_SOLVE, K_INGEST, K_STOI_MARGIN, K_COUNT
 };
 const char* const kKernelNames[K_COUNT] = {
     "pesq_filter_kernel", "pesq_spectrum_kernel", "pesq_bark_kernel", "stoi_resample_kernel", "stoi_energy_kernel",
-    "stoi_compact_kernel", "stoi_tob_kernel", "stoi_segment_kernel", "stoi_finalize_kernel", "pesq_resample_kernel", "lsd_frames_kernel", "sdr_corr_kernel", "sdr_solve_kernel", "ingest_kernel", "first_pass_kernel"};
+    "stoi_compact_kernel", "stoi_tob_kernel", "stoi_segment_kernel", "stoi_finalize_kernel", "pesq_resample_kernel", "lsd_frames_kernel", "sdr_corr_kernel", "sdr_solve_kernel", "ingest_kernel", "stoi_margin_kernel"};
 bool g_profile = false;
 struct ProfRecord { int id; cudaEvent_t start, stop; };
 std::vector<ProfRecord> g_prof_pending;
@@ -214,10 +201,7 @@ struct fsem_pesq_ctx {
     float* d_rs_taps = nullptr;
     int spec_ctas_per_sm = 2;
     int filt_ctas_per_sm = 4;
-    int fp_ctas_per_sm = 7;                         // single-read first pass (fsem_first_pass.cuh)
     HostPipe pipe;
-    cudaStream_t side = nullptr;                    // second stream of the overlapped two-metric device entry
-    cudaEvent_t ev_fork = nullptr, ev_filter = nullptr, ev_join = nullptr;
 };
 
 namespace {
@@ -231,7 +215,8 @@ struct PesqPlan {
     size_t off_rs, off_rslen, off_z, off_partial, off_bark, off_dist, off_power, off_order, off_fprefix, total;
 };
 
-PesqPlan pesq_plan(const fsem_pesq_ctx* ctx, int64_t batch, int64_t n_in, int quantum = 64) {
+PesqPlan pesq_plan(const fsem_pesq_ctx* ctx, int64_t batch, int64_t n_in) {
+    constexpr int quantum = 64;                        // chunk granularity: owned tiles start on an even 32-sample slot
     PesqPlan p{};
     p.batch = batch;
     p.n_in = n_in;
@@ -239,7 +224,9 @@ PesqPlan pesq_plan(const fsem_pesq_ctx* ctx, int64_t batch, int64_t n_in, int qu
     const int64_t n = stoi_resampled_len(n_in, ctx->rs_orig, ctx->rs_neu);
     p.rstride = round_up(n > 0 ? n : 1, 4);
     p.n = n;
-    p.zstride = round_up(n > 0 ? n : 1, 4);
+    // the spectrum kernel fetches whole 1 KB half-frames with bulk copies: the last frame ends at most 255 samples
+    // (the n % 256 zero padding, PESQ.py:128-130) beyond n, so a pitch of n + 256 keeps every copy inside its own row
+    p.zstride = round_up((n > 0 ? n : 1) + FSEM_PESQ_HOP, 4);
     p.tmax = pesq_num_frames(n);
     if (p.tmax < 1) p.tmax = 1;
     // Chunking of the serial IIR pass.  A warp-unit = (32 signals, one chunk) and costs chunk + warm-up sample steps;
@@ -247,9 +234,7 @@ PesqPlan pesq_plan(const fsem_pesq_ctx* ctx, int64_t batch, int64_t n_in, int qu
     // waves x (chunk + warm-up): enough units to fill the chip, no half-empty last wave, little redundant warm-up.
     const int64_t nn = n > 0 ? n : 1;
     const int64_t groups = 2 * ceil_div(batch > 0 ? batch : 1, 32);
-    // resident warps of the kernel that walks the chunks: the IIR pass, or (coarse grid) the single-read first pass
-    const int64_t slots = quantum == kFpQuantum ? (int64_t)ctx->dev.sms * ctx->fp_ctas_per_sm * kFpWarps
-                                                : (int64_t)ctx->dev.sms * ctx->filt_ctas_per_sm * kFiltWarps;
+    const int64_t slots = (int64_t)ctx->dev.sms * ctx->filt_ctas_per_sm * kFiltWarps;   // resident warps of the IIR pass
     const int64_t max_ch = ceil_div(nn, 256) < 1024 ? ceil_div(nn, 256) : 1024;     // chunks of at least 256 samples
     int64_t nch = 1, chunk = round_up(nn, quantum);
     double best = 1e300;
@@ -278,7 +263,6 @@ PesqPlan pesq_plan(const fsem_pesq_ctx* ctx, int64_t batch, int64_t n_in, int qu
     p.off_power = off;   off = align256(off + sizeof(double) * 2 * batch);
     p.off_order = off;   off = align256(off + sizeof(int32_t) * batch);              // variable-length batches only
     p.off_fprefix = off; off = align256(off + sizeof(int64_t) * (batch + 1));
-    // last, so that no other offset depends on the chunk count (the two-metric entry point plans a coarser chunk grid)
     p.off_partial = off; off = align256(off + sizeof(double) * 2 * batch * p.nchunks);
     p.total = off;
     return p;
@@ -355,12 +339,6 @@ extern "C" int fsem_pesq_create(fsem_pesq_ctx_t** out, const fsem_pesq_design_t*
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(pesq_bark_kernel<kBarkThreadsWide, kBarkTileWide>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bark_dyn_smem(kBarkTileWide));
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(pesq_stoi_first_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)kFpDynSmem);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(pesq_stoi_first_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)kFpDynSmem);
     if (e != cudaSuccess) {
         cudaFree(ctx->d_tab);
         if (ctx->d_rs_taps) cudaFree(ctx->d_rs_taps);
@@ -373,9 +351,6 @@ extern "C" int fsem_pesq_create(fsem_pesq_ctx_t** out, const fsem_pesq_design_t*
     occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pesq_filter_tiled_kernel<false>, kFiltWarps * 32, 0) == cudaSuccess && occ > 0)
         ctx->filt_ctas_per_sm = occ;
-    occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pesq_stoi_first_pass_kernel<false>, kFpWarps * 32, kFpDynSmem) == cudaSuccess && occ > 0)
-        ctx->fp_ctas_per_sm = occ;
     *out = ctx;
     return FSEM_OK;
 }
@@ -383,10 +358,6 @@ extern "C" int fsem_pesq_create(fsem_pesq_ctx_t** out, const fsem_pesq_design_t*
 extern "C" int fsem_pesq_destroy(fsem_pesq_ctx_t* ctx) {
     if (!ctx) return FSEM_OK;
     ctx->pipe.destroy();
-    if (ctx->side) cudaStreamDestroy(ctx->side);
-    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-    if (ctx->ev_filter) cudaEventDestroy(ctx->ev_filter);
-    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->d_tab) cudaFree(ctx->d_tab);
     if (ctx->d_rs_taps) cudaFree(ctx->d_rs_taps);
     delete ctx;
@@ -395,9 +366,7 @@ extern "C" int fsem_pesq_destroy(fsem_pesq_ctx_t* ctx) {
 
 extern "C" size_t fsem_pesq_workspace_bytes(const fsem_pesq_ctx_t* ctx, int64_t batch, int64_t n) {
     if (!ctx || batch <= 0 || n <= 0) return 0;
-    // the single-read first pass of the two-metric entry point plans its IIR chunks on a coarser grid
-    const size_t a = pesq_plan(ctx, batch, n).total, b = pesq_plan(ctx, batch, n, kFpQuantum).total;
-    return a > b ? a : b;
+    return pesq_plan(ctx, batch, n).total;
 }
 
 extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in, float* mos_out,
@@ -410,8 +379,7 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
     if (in->batch == 0) return FSEM_OK;
     if (!in->clean || !in->deg) return fail(FSEM_E_INVALID, "fsem_pesq_score_f32: null input");
     if (in->n >= (int64_t(1) << 30)) return fail(FSEM_E_INVALID, "fsem_pesq_score_f32: n too large");
-    const bool first_pass_done = g_hook.first_pass_done;
-    const PesqPlan p = pesq_plan(ctx, in->batch, in->n, first_pass_done ? g_hook.chunk_quantum : 64);
+    const PesqPlan p = pesq_plan(ctx, in->batch, in->n);
     // without per-item lengths every item has n samples: fewer than 20 frames is the reference's
     // RuntimeError from unfold (PESQ.py:169)
     if (!in->lengths && pesq_num_frames(p.n) < 20)
@@ -431,11 +399,13 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
     if (p.resample) {   // resample-on-ingest to 16 kHz (base.py:19-20), then the pipeline runs on the workspace copy
         float* y = reinterpret_cast<float*>(ws + p.off_rs);
         int32_t* rslen = reinterpret_cast<int32_t*>(ws + p.off_rslen);
-        dim3 grid((unsigned)ceil_div(p.n, 256), (unsigned)(2 * in->batch));
+        const int64_t bps = ceil_div(p.n, 256);
+        if (bps * 2 * in->batch >= (int64_t(1) << 31))
+            return fail(FSEM_E_INVALID, "fsem_pesq_score_f32: batch x samples too large for one launch; split the batch");
         { ProfScope prof_(K_PESQ_RESAMPLE, stream);
-          stoi_resample_kernel<<<grid, 256, 0, stream>>>(in->clean, in->deg, in->lengths, in->batch, in->n, in->stride,
-                                                        ctx->d_rs_taps, ctx->rs_orig, ctx->rs_neu, ctx->rs_width,
-                                                        ctx->rs_ntaps, y, p.rstride); }
+          stoi_resample_kernel<<<(unsigned)(bps * 2 * in->batch), 256, 0, stream>>>(
+              in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, ctx->d_rs_taps, ctx->rs_orig, ctx->rs_neu,
+              ctx->rs_width, ctx->rs_ntaps, y, p.rstride, (int)bps); }
         FSEM_LAUNCHED();
         if (in->lengths) {
             resampled_lengths_kernel<<<(unsigned)ceil_div(in->batch, 256), 256, 0, stream>>>(
@@ -453,30 +423,11 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
     if (in->lengths) {
         order = reinterpret_cast<int32_t*>(ws + p.off_order);
         fprefix = reinterpret_cast<int64_t*>(ws + p.off_fprefix);
-        if (!first_pass_done) {
-            pesq_order_kernel<<<1, kOrderThreads, 0, stream>>>(in->lengths, in->batch, in->n, order, fprefix);
-            FSEM_LAUNCHED();
-        }
+        pesq_order_kernel<<<1, kOrderThreads, 0, stream>>>(in->lengths, in->batch, in->n, order, fprefix);
+        FSEM_LAUNCHED();
     }
-    if (!first_pass_done) {   // kernel A
+    {   // kernel A
         const bool vec4 = aligned16(in->clean) && aligned16(in->deg) && (in->stride % 4 == 0);
-#ifdef FSEM_FILTER_RING
-        if (vec4 && p.tiled) {   // A/B variant: the IIR pass on the cp.async tile ring of fsem_first_pass.cuh
-            const int64_t units = 2 * ceil_div(in->batch, 32) * p.nchunks;
-            const unsigned grid = (unsigned)ceil_div(units, kFpWarps);
-            StoiWindowArg nowin{};
-            Resample85Taps notaps{};
-            { ProfScope prof_(K_PESQ_FILTER, stream);
-              if (in->lengths)
-                  pesq_stoi_first_pass_kernel<true, false><<<grid, kFpWarps * 32, kFpIirDynSmem, stream>>>(
-                      in->clean, in->deg, in->lengths, order, in->batch, in->n, in->stride, p.chunk, p.nchunks,
-                      ctx->warm, ctx->coef, notaps, nowin, z, p.zstride, partial, nullptr, 0, nullptr, 0);
-              else
-                  pesq_stoi_first_pass_kernel<false, false><<<grid, kFpWarps * 32, kFpIirDynSmem, stream>>>(
-                      in->clean, in->deg, nullptr, nullptr, in->batch, in->n, in->stride, p.chunk, p.nchunks,
-                      ctx->warm, ctx->coef, notaps, nowin, z, p.zstride, partial, nullptr, 0, nullptr, 0); }
-        } else
-#endif
         if (vec4 && p.tiled) {
             const int64_t units = 2 * ceil_div(in->batch, 32) * p.nchunks;
             const unsigned grid = (unsigned)ceil_div(units, kFiltWarps);
@@ -503,14 +454,11 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
                       ctx->coef, z, p.zstride, partial); }
         }
         FSEM_LAUNCHED();
-        if (g_hook.after_filter) FSEM_CUDA(cudaEventRecord(g_hook.after_filter, stream));
     }
     {   // kernel B
         const int64_t units = in->batch * (int64_t)p.tmax;
         int64_t grid = ceil_div(units, kSpecWarps);
-        const int per_sm = (g_hook.spec_ctas_per_sm > 0 && g_hook.spec_ctas_per_sm < ctx->spec_ctas_per_sm)
-                               ? g_hook.spec_ctas_per_sm : ctx->spec_ctas_per_sm;
-        const int64_t cap = (int64_t)ctx->dev.sms * per_sm;
+        const int64_t cap = (int64_t)ctx->dev.sms * ctx->spec_ctas_per_sm;
         if (grid > cap) grid = cap;
         { ProfScope prof_(K_PESQ_SPECTRUM, stream);
           pesq_spectrum_kernel<<<(unsigned)grid, kSpecWarps * 32, kSpecDynSmem, stream>>>(
@@ -559,7 +507,6 @@ struct fsem_stoi_ctx {
     float* d_taps = nullptr;
     bool fast85 = false;        // taps fit the specialised 8:5 kernel
     Resample85Taps taps85;
-    StoiWindowArg win_arg;      // analysis window as a kernel argument of the single-read first pass
     StoiTables* d_tab = nullptr;
     float clip = 0.f, dyn_range = 40.f;
     int tob_ctas_per_sm = 2;
@@ -628,7 +575,6 @@ extern "C" int fsem_stoi_create(fsem_stoi_ctx_t** out, const fsem_stoi_design_t*
     ctx->clip = d->clip; ctx->dyn_range = d->dyn_range;
     StoiTables h{};
     memcpy(h.window, d->window, sizeof(h.window));
-    memcpy(ctx->win_arg.w, d->window, sizeof(ctx->win_arg.w));
     for (int b = 0; b < FSEM_STOI_NBANDS; ++b) { h.band_lo[b] = d->band_lo[b]; h.band_hi[b] = d->band_hi[b]; }
     h.clip = d->clip; h.dyn_range = d->dyn_range;
     cudaError_t e = cudaMalloc(&ctx->d_tab, sizeof(StoiTables));
@@ -681,6 +627,7 @@ extern "C" int fsem_stoi_score_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t* in,
         return fail(FSEM_E_INVALID, "fsem_stoi_score_f32: bad shape batch=%lld n=%lld stride=%lld",
                     (long long)in->batch, (long long)in->n, (long long)in->stride);
     if (in->batch == 0) return FSEM_OK;
+    if (in->n == 0) return fail(FSEM_E_INVALID, "fsem_stoi_score_f32: n = 0 (empty signals)");
     if (!in->clean || !in->deg) return fail(FSEM_E_INVALID, "fsem_stoi_score_f32: null input");
     if (in->n >= (int64_t(1) << 30)) return fail(FSEM_E_INVALID, "fsem_stoi_score_f32: n too large");
     const StoiPlan p = stoi_plan(ctx, in->batch, in->n);
@@ -703,29 +650,28 @@ extern "C" int fsem_stoi_score_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t* in,
     const float* c10 = in->clean;
     const float* d10 = in->deg;
     int64_t sstride = in->stride;
-    if (p.resample && g_hook.first_pass_done) {                  // y and the hop energies are already in the workspace
-        c10 = y;
-        d10 = y + in->batch * p.ystride;
-        sstride = p.ystride;
-    } else if (p.resample) {
+    if (p.resample) {
         if (ctx->fast85) {
-            dim3 grid((unsigned)ceil_div(p.lmax, (int64_t)kRs85TileOut * kRs85TilesPerCta), (unsigned)(2 * in->batch));
+            const int64_t bps = ceil_div(p.lmax, (int64_t)kRs85TileOut * kRs85TilesPerCta);
+            const unsigned grid = (unsigned)(bps * 2 * in->batch);       // < 2^31: batch x frames is checked above
             const bool vec4 = aligned16(in->clean) && aligned16(in->deg) && (in->stride % 4 == 0);
             { ProfScope prof_(K_STOI_RESAMPLE, stream);
               if (vec4)
                   stoi_resample85_kernel<true><<<grid, kRs85Threads, 0, stream>>>(
                       in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, ctx->taps85, ctx->d_tab, y,
-                      p.ystride, hops, p.hops_max);
+                      p.ystride, hops, p.hops_max, (int)bps);
               else
                   stoi_resample85_kernel<false><<<grid, kRs85Threads, 0, stream>>>(
                       in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, ctx->taps85, ctx->d_tab, y,
-                      p.ystride, hops, p.hops_max); }
+                      p.ystride, hops, p.hops_max, (int)bps); }
         } else {
-            dim3 grid((unsigned)ceil_div(p.lmax, 256), (unsigned)(2 * in->batch));
+            const int64_t bps = ceil_div(p.lmax, 256);
+            if (bps * 2 * in->batch >= (int64_t(1) << 31))
+                return fail(FSEM_E_INVALID, "fsem_stoi_score_f32: batch x samples too large for one launch; split the batch");
             { ProfScope prof_(K_STOI_RESAMPLE, stream);
-              stoi_resample_kernel<<<grid, 256, 0, stream>>>(in->clean, in->deg, in->lengths, in->batch, in->n,
-                                                            in->stride, ctx->d_taps, ctx->orig, ctx->neu, ctx->width,
-                                                            ctx->ntaps, y, p.ystride); }
+              stoi_resample_kernel<<<(unsigned)(bps * 2 * in->batch), 256, 0, stream>>>(
+                  in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, ctx->d_taps, ctx->orig, ctx->neu,
+                  ctx->width, ctx->ntaps, y, p.ystride, (int)bps); }
         }
         FSEM_LAUNCHED();
         c10 = y;
@@ -799,6 +745,20 @@ extern "C" int fsem_stoi_debug_taps(fsem_stoi_ctx_t* ctx, int64_t batch, int64_t
     if (resampled_out && p.resample)
         FSEM_CUDA(cudaMemcpyAsync(resampled_out, ws + p.off_y, sizeof(float) * 2 * batch * p.ystride,
                                   cudaMemcpyDeviceToDevice, stream));
+    return FSEM_OK;
+}
+
+extern "C" int fsem_stoi_mask_margin(fsem_stoi_ctx_t* ctx, int64_t batch, int64_t n, const int32_t* lengths,
+                                     const void* workspace, float* margin_out, void* stream_v) {
+    if (!ctx || !workspace || !margin_out) return fail(FSEM_E_INVALID, "fsem_stoi_mask_margin: null argument");
+    if (batch <= 0 || n <= 0) return fail(FSEM_E_INVALID, "fsem_stoi_mask_margin: bad shape");
+    const StoiPlan p = stoi_plan(ctx, batch, n);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    const float* energy = reinterpret_cast<const float*>(static_cast<const char*>(workspace) + p.off_energy);
+    { ProfScope prof_(K_STOI_MARGIN, stream);
+      stoi_margin_kernel<<<(unsigned)ceil_div(batch * 32, 128), 128, 0, stream>>>(
+          energy, lengths, batch, n, ctx->orig, ctx->neu, p.t0max, ctx->dyn_range, margin_out); }
+    FSEM_LAUNCHED();
     return FSEM_OK;
 }
 
@@ -880,6 +840,10 @@ int score_host_any(const char* who, fsem_pesq_ctx* pctx, fsem_stoi_ctx* sctx, co
             return cudaMemcpyAsync(dst, src, es * n * cnt, cudaMemcpyHostToDevice, P.copy);
         return cudaMemcpy2DAsync(dst, rstride * es, src, stride * es, n * es, cnt, cudaMemcpyHostToDevice, P.copy);
     };
+    // Everything that touches the caller's host buffers or the staging slots runs inside `run`; whatever it returns,
+    // both streams are drained before this function does, so that no async copy still references memory the caller
+    // may free or reuse after an error return.
+    auto run = [&]() -> int {
     int64_t done_chunks = 0;
     for (int64_t i0 = 0; i0 < batch; i0 += per, ++done_chunks) {
         const int slot = (int)(done_chunks & 1);
@@ -909,7 +873,7 @@ int score_host_any(const char* who, fsem_pesq_ctx* pctx, fsem_stoi_ctx* sctx, co
                                           reinterpret_cast<float*>(ob + 3 * col) + i0,
                                           reinterpret_cast<int32_t*>(ob + 4 * col) + i0,
                                           reinterpret_cast<int32_t*>(ob + 5 * col) + i0, wsb + 2 * conv_sig, ws_pesq,
-                                          wsb + 2 * conv_sig + ws_pesq, ws_stoi, P.compute, 0);
+                                          wsb + 2 * conv_sig + ws_pesq, ws_stoi, P.compute);
         else if (rc == FSEM_OK && pctx)
             rc = fsem_pesq_score_f32(pctx, &dev, reinterpret_cast<float*>(ob) + i0,
                                      reinterpret_cast<int32_t*>(ob + col) + i0, wsb + 2 * conv_sig, ws_pesq, P.compute);
@@ -919,7 +883,7 @@ int score_host_any(const char* who, fsem_pesq_ctx* pctx, fsem_stoi_ctx* sctx, co
                                      reinterpret_cast<int32_t*>(ob + 4 * col) + i0,
                                      reinterpret_cast<int32_t*>(ob + 5 * col) + i0, wsb + 2 * conv_sig + ws_pesq, ws_stoi,
                                      P.compute);
-        if (rc != FSEM_OK) { cudaStreamSynchronize(P.copy); cudaStreamSynchronize(P.compute); return rc; }
+        if (rc != FSEM_OK) return rc;
         FSEM_CUDA(cudaEventRecord(P.done[slot], P.compute));
     }
     // one read-back of the score columns (a per-chunk copy into pageable memory would stall the pipeline)
@@ -937,8 +901,14 @@ int score_host_any(const char* who, fsem_pesq_ctx* pctx, fsem_stoi_ctx* sctx, co
         FSEM_CUDA(readback(kept_frames_out, 4));
         FSEM_CUDA(readback(stoi_status_out, 5));
     }
-    FSEM_CUDA(cudaStreamSynchronize(P.copy));
-    FSEM_CUDA(cudaStreamSynchronize(P.compute));
+    return FSEM_OK;
+    };
+    rc = run();
+    const cudaError_t e_copy = cudaStreamSynchronize(P.copy);
+    const cudaError_t e_comp = cudaStreamSynchronize(P.compute);
+    if (rc != FSEM_OK) return rc;                                    // g_err already holds the first failure
+    if (e_copy != cudaSuccess || e_comp != cudaSuccess)
+        return fail(FSEM_E_CUDA, "%s: %s", who, cudaGetErrorString(e_copy != cudaSuccess ? e_copy : e_comp));
     return FSEM_OK;
 }
 
@@ -982,6 +952,76 @@ extern "C" int fsem_pesq_stoi_score_host_f32(fsem_pesq_ctx_t* pctx, fsem_stoi_ct
     return score_host_any("fsem_pesq_stoi_score_host_f32", pctx, sctx, in->clean, in->deg, FSEM_DTYPE_F32, in->lengths,
                           in->batch, in->n, in->stride, mos_out, pesq_status_out, stoi_out, estoi_out, kept_frames_out,
                           stoi_status_out);
+}
+
+// ================================================================================================
+// Resample-on-ingest as a building block (BaseMetric.prepare_audio, fast_se_metrics/base.py:13,19-20): the
+// general polyphase kernel behind a small context that owns the device copy of the taps.  PESQ and STOI run the
+// same kernel inside their own chains; LSD and SDR call this first.
+// ================================================================================================
+struct fsem_resampler {
+    int orig = 1, neu = 1, width = 0, ntaps = 0;
+    float* d_taps = nullptr;
+};
+
+extern "C" int fsem_resampler_create(fsem_resampler_t** out, int32_t orig, int32_t neu, int32_t width, int32_t ntaps,
+                                     const float* taps) {
+    if (!out) return fail(FSEM_E_INVALID, "fsem_resampler_create: null argument");
+    *out = nullptr;
+    if (orig <= 0 || neu <= 0 || width < 0 || !taps || ntaps != 2 * width + orig)
+        return fail(FSEM_E_INVALID, "fsem_resampler_create: bad resampling kernel (ntaps must be 2*width+orig)");
+    fsem_resampler* r = new (std::nothrow) fsem_resampler();
+    if (!r) return fail(FSEM_E_INVALID, "out of host memory");
+    r->orig = orig; r->neu = neu; r->width = width; r->ntaps = ntaps;
+    cudaError_t e = cudaMalloc(&r->d_taps, sizeof(float) * neu * ntaps);
+    if (e == cudaSuccess) e = cudaMemcpy(r->d_taps, taps, sizeof(float) * neu * ntaps, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (r->d_taps) cudaFree(r->d_taps);
+        delete r;
+        return fail(FSEM_E_CUDA, "fsem_resampler_create: %s", cudaGetErrorString(e));
+    }
+    *out = r;
+    return FSEM_OK;
+}
+
+extern "C" int fsem_resampler_destroy(fsem_resampler_t* r) {
+    if (!r) return FSEM_OK;
+    if (r->d_taps) cudaFree(r->d_taps);
+    delete r;
+    return FSEM_OK;
+}
+
+extern "C" int64_t fsem_resampled_len(const fsem_resampler_t* r, int64_t n) {
+    if (!r || n < 0) return 0;
+    return stoi_resampled_len(n, r->orig, r->neu);
+}
+
+extern "C" int fsem_resample_f32(fsem_resampler_t* r, const fsem_batch_t* in, float* out, int64_t out_stride,
+                                 int32_t* lengths_out, void* stream_v) {
+    if (!r || !in || !out) return fail(FSEM_E_INVALID, "fsem_resample_f32: null argument");
+    if (in->batch < 0 || in->n <= 0 || in->stride < in->n || in->n >= (int64_t(1) << 30))
+        return fail(FSEM_E_INVALID, "fsem_resample_f32: bad shape");
+    if (in->batch == 0) return FSEM_OK;
+    if (!in->clean || !in->deg) return fail(FSEM_E_INVALID, "fsem_resample_f32: null input");
+    const int64_t L = stoi_resampled_len(in->n, r->orig, r->neu);
+    if (out_stride < L) return fail(FSEM_E_INVALID, "fsem_resample_f32: out_stride %lld < resampled length %lld",
+                                    (long long)out_stride, (long long)L);
+    if (in->lengths && !lengths_out) return fail(FSEM_E_INVALID, "fsem_resample_f32: lengths given but lengths_out is null");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    const int64_t bps = ceil_div(L, 256);
+    if (bps * 2 * in->batch >= (int64_t(1) << 31))
+        return fail(FSEM_E_INVALID, "fsem_resample_f32: batch x samples too large for one launch; split the batch");
+    { ProfScope prof_(K_PESQ_RESAMPLE, stream);
+      stoi_resample_kernel<<<(unsigned)(bps * 2 * in->batch), 256, 0, stream>>>(
+          in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, r->d_taps, r->orig, r->neu, r->width,
+          r->ntaps, out, out_stride, (int)bps); }
+    FSEM_LAUNCHED();
+    if (in->lengths) {
+        resampled_lengths_kernel<<<(unsigned)ceil_div(in->batch, 256), 256, 0, stream>>>(
+            in->lengths, in->batch, in->n, r->orig, r->neu, lengths_out);
+        FSEM_LAUNCHED();
+    }
+    return FSEM_OK;
 }
 
 // ================================================================================================
@@ -1071,91 +1111,18 @@ extern "C" int fsem_lsd_score_f32(fsem_lsd_ctx_t* ctx, const fsem_batch_t* in, f
 }
 
 // ------------------------------------------------------------------------------------------------
-// Device entry point for BOTH metrics with kernel overlap: the PESQ chain runs on `stream`, the STOI chain on an
-// internal second stream that starts once PESQ's IIR pass is done, so that STOI's HBM-bound resampler runs in the
-// shadow of PESQ's shared-memory-bound spectrum kernel (and STOI's FFT kernel next to PESQ's Bark kernel).
-// `overlap` = 0 runs the two chains back to back on `stream` (identical results either way).
+// Device entry point for BOTH metrics: the two kernel chains back to back on `stream`, each reading the input itself
+// (SURVEY.md 8f rank 1 is delivered as "single upload": the host pipeline copies every chunk once and calls this).
 extern "C" int fsem_pesq_stoi_score_f32(fsem_pesq_ctx_t* pctx, fsem_stoi_ctx_t* sctx, const fsem_batch_t* in,
                                         float* mos_out, int32_t* pesq_status_out, float* stoi_out, float* estoi_out,
                                         int32_t* kept_frames_out, int32_t* stoi_status_out, void* ws_pesq,
-                                        size_t ws_pesq_bytes, void* ws_stoi, size_t ws_stoi_bytes, void* stream_v,
-                                        int overlap) {
+                                        size_t ws_pesq_bytes, void* ws_stoi, size_t ws_stoi_bytes, void* stream) {
     if (!pctx || !sctx) return fail(FSEM_E_INVALID, "fsem_pesq_stoi_score_f32: null context");
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-    if (overlap <= 0 || overlap == 3) {
-        // overlap = 3: single-read first pass (fsem_first_pass.cuh) -- needs 16 kHz input for PESQ, the 8:5 resampler for
-        // STOI, 16-byte aligned rows and enough items to fill the 32 signal lanes of a warp; otherwise, and with
-        // overlap = 0, the two kernel chains run back to back, each reading the input itself.  Measured on B200
-        // (8192 x 10 s): 9.5 ms for the single-read kernel against 4.4 + 3.7 ms for the two separate first kernels
-        // (it saves 9 GB of HBM traffic but is issue-bound, not HBM-bound), so it is not the default.
-        bool fuse = overlap == 3 && in && in->clean && in->deg && in->batch >= 16 && in->n > 0 && in->stride >= in->n &&
-                    in->n < (int64_t(1) << 30) && pctx->rs_orig == pctx->rs_neu && sctx->fast85 && sctx->orig == 8 &&
-                    sctx->neu == 5 && aligned16(in->clean) && aligned16(in->deg) && in->stride % 4 == 0 && ws_pesq &&
-                    ws_stoi;
-        if (fuse) {
-            const PesqPlan pp = pesq_plan(pctx, in->batch, in->n, kFpQuantum);
-            const StoiPlan sp = stoi_plan(sctx, in->batch, in->n);
-            fuse = pp.tiled && ws_pesq_bytes >= pp.total && ws_stoi_bytes >= sp.total &&
-                   (in->lengths || pesq_num_frames(pp.n) >= 20);
-            if (fuse) {
-                char* wp = static_cast<char*>(ws_pesq);
-                char* wsb = static_cast<char*>(ws_stoi);
-                int32_t* order = nullptr;
-                if (in->lengths) {
-                    order = reinterpret_cast<int32_t*>(wp + pp.off_order);
-                    pesq_order_kernel<<<1, kOrderThreads, 0, stream>>>(in->lengths, in->batch, in->n, order,
-                                                                       reinterpret_cast<int64_t*>(wp + pp.off_fprefix));
-                    FSEM_LAUNCHED();
-                }
-                const int64_t units = 2 * ceil_div(in->batch, 32) * pp.nchunks;
-                const unsigned grid = (unsigned)ceil_div(units, kFpWarps);
-                float* z = reinterpret_cast<float*>(wp + pp.off_z);
-                double* partial = reinterpret_cast<double*>(wp + pp.off_partial);
-                float* y = reinterpret_cast<float*>(wsb + sp.off_y);
-                double2* hops = reinterpret_cast<double2*>(wsb + sp.off_hops);
-                { ProfScope prof_(K_FIRST_PASS, stream);
-                  if (in->lengths)
-                      pesq_stoi_first_pass_kernel<true><<<grid, kFpWarps * 32, kFpDynSmem, stream>>>(
-                          in->clean, in->deg, in->lengths, order, in->batch, in->n, in->stride, pp.chunk, pp.nchunks,
-                          pctx->warm, pctx->coef, sctx->taps85, sctx->win_arg, z, pp.zstride, partial, y, sp.ystride, hops,
-                          sp.hops_max);
-                  else
-                      pesq_stoi_first_pass_kernel<false><<<grid, kFpWarps * 32, kFpDynSmem, stream>>>(
-                          in->clean, in->deg, nullptr, nullptr, in->batch, in->n, in->stride, pp.chunk, pp.nchunks,
-                          pctx->warm, pctx->coef, sctx->taps85, sctx->win_arg, z, pp.zstride, partial, y, sp.ystride, hops,
-                          sp.hops_max); }
-                FSEM_LAUNCHED();
-                g_hook.first_pass_done = true;
-                g_hook.chunk_quantum = kFpQuantum;
-            }
-        }
-        int rc = fsem_pesq_score_f32(pctx, in, mos_out, pesq_status_out, ws_pesq, ws_pesq_bytes, stream);
-        if (rc == FSEM_OK)
-            rc = fsem_stoi_score_f32(sctx, in, stoi_out, estoi_out, kept_frames_out, stoi_status_out, ws_stoi,
-                                     ws_stoi_bytes, stream);
-        g_hook = OverlapHook{};
-        return rc;
-    }
-    if (!pctx->side) {
-        FSEM_CUDA(cudaStreamCreateWithFlags(&pctx->side, cudaStreamNonBlocking));
-        FSEM_CUDA(cudaEventCreateWithFlags(&pctx->ev_fork, cudaEventDisableTiming));
-        FSEM_CUDA(cudaEventCreateWithFlags(&pctx->ev_filter, cudaEventDisableTiming));
-        FSEM_CUDA(cudaEventCreateWithFlags(&pctx->ev_join, cudaEventDisableTiming));
-    }
-    FSEM_CUDA(cudaEventRecord(pctx->ev_fork, stream));
-    g_hook.after_filter = pctx->ev_filter;
-    g_hook.spec_ctas_per_sm = overlap > 1 ? 1 : 0;             // overlap = 2: leave half of every SM to the STOI chain
     int rc = fsem_pesq_score_f32(pctx, in, mos_out, pesq_status_out, ws_pesq, ws_pesq_bytes, stream);
-    g_hook = OverlapHook{};
-    if (rc != FSEM_OK) return rc;
-    FSEM_CUDA(cudaStreamWaitEvent(pctx->side, pctx->ev_fork, 0));
-    FSEM_CUDA(cudaStreamWaitEvent(pctx->side, pctx->ev_filter, 0));
-    rc = fsem_stoi_score_f32(sctx, in, stoi_out, estoi_out, kept_frames_out, stoi_status_out, ws_stoi, ws_stoi_bytes,
-                             pctx->side);
-    if (rc != FSEM_OK) { cudaStreamSynchronize(pctx->side); return rc; }
-    FSEM_CUDA(cudaEventRecord(pctx->ev_join, pctx->side));
-    FSEM_CUDA(cudaStreamWaitEvent(stream, pctx->ev_join, 0));
-    return FSEM_OK;
+    if (rc == FSEM_OK)
+        rc = fsem_stoi_score_f32(sctx, in, stoi_out, estoi_out, kept_frames_out, stoi_status_out, ws_stoi,
+                                 ws_stoi_bytes, stream);
+    return rc;
 }
 
 // ================================================================================================

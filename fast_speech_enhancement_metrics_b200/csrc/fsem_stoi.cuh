@@ -26,17 +26,19 @@ struct StoiTables {
 
 // ------------------------------------------------------------------------------------------------
 // General polyphase resampler: y[neu*k + p] = sum_j taps[p][j] * xpad[orig*k + j],
-// xpad = `width` zeros | x | zeros.  One thread per output sample; grid.y = signal.
+// xpad = `width` zeros | x | zeros.  One thread per output sample; 1-D grid of blocks_per_sig blocks per signal
+// (no 65535 cap of grid.y on the batch).
 __global__ void __launch_bounds__(256)
 stoi_resample_kernel(const float* __restrict__ clean, const float* __restrict__ deg,
                      const int32_t* __restrict__ lengths, int64_t batch, int64_t n, int64_t stride,
                      const float* __restrict__ taps, int orig, int neu, int width, int ntaps,
-                     float* __restrict__ y, int64_t ystride) {
-    const int64_t sig = blockIdx.y;
+                     float* __restrict__ y, int64_t ystride, int blocks_per_sig) {
+    const int64_t sig = blockIdx.x / blocks_per_sig;
+    const int bx = blockIdx.x - (int)sig * blocks_per_sig;
     const int64_t item = sig < batch ? sig : sig - batch;
     const int len = item_length(lengths, item, n);
     const int64_t L = stoi_resampled_len(len, orig, neu);
-    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t m = (int64_t)bx * blockDim.x + threadIdx.x;
     if (m >= L) return;
     const float* __restrict__ x = (sig < batch ? clean : deg) + item * stride;
     const int64_t k = m / neu;
@@ -103,17 +105,19 @@ __global__ void __launch_bounds__(kRs85Threads)
 stoi_resample85_kernel(const float* __restrict__ clean, const float* __restrict__ deg,
                        const int32_t* __restrict__ lengths, int64_t batch, int64_t n, int64_t stride,
                        const __grid_constant__ Resample85Taps taps, const StoiTables* __restrict__ tab,
-                       float* __restrict__ y, int64_t ystride, double2* __restrict__ hop_energy, int hops_max) {
+                       float* __restrict__ y, int64_t ystride, double2* __restrict__ hop_energy, int hops_max,
+                       int blocks_per_sig) {
     __shared__ float4 s_in[kRs85SmemQuads];
     __shared__ __align__(16) float s_out[kRs85TileOut];
     __shared__ __align__(16) float s_win[FSEM_STOI_WIN];
     const int tid = threadIdx.x;
-    const int64_t sig = blockIdx.y;
+    const int64_t sig = blockIdx.x / blocks_per_sig;                 // 1-D grid: no 65535 cap of grid.y on the batch
+    const int bx = blockIdx.x - (int)sig * blocks_per_sig;
     const bool is_clean = sig < batch;
     const int64_t item = is_clean ? sig : sig - batch;
     const int len = item_length(lengths, item, n);
     const int64_t L = stoi_resampled_len(len, 8, 5);
-    const int64_t tile0 = (int64_t)blockIdx.x * kRs85TilesPerCta;
+    const int64_t tile0 = (int64_t)bx * kRs85TilesPerCta;
     if (tile0 * kRs85TileOut >= L) return;
     const float* __restrict__ x = (is_clean ? clean : deg) + item * stride;
     float* __restrict__ yrow = y + sig * ystride;
@@ -303,6 +307,28 @@ stoi_compact_kernel(const float* __restrict__ energy, const int32_t* __restrict_
         count += __popc(bal);
     }
     if (lane == 0) kept_count[item] = count;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Diagnostics: how close the silent-frame decisions of an item came to flipping.  One warp per item:
+// margin = min_t |(max E - dyn_range) - E_t| over the item's frames, in dB (same fp32 ops as the decision above).
+__global__ void __launch_bounds__(128)
+stoi_margin_kernel(const float* __restrict__ energy, const int32_t* __restrict__ lengths, int64_t batch, int64_t n,
+                   int orig, int neu, int t0max, float dyn_range, float* __restrict__ margin_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (item >= batch) return;
+    const int64_t L = stoi_resampled_len(item_length(lengths, item, n), orig, neu);
+    const int T0 = stoi_num_frames(L);
+    const float* __restrict__ e = energy + item * t0max;
+    float mx = -INFINITY;
+    for (int t = lane; t < T0; t += 32) mx = fmaxf(mx, e[t]);
+    mx = warp_max(mx);
+    const float thr = __fsub_rn(mx, dyn_range);
+    float mg = INFINITY;
+    for (int t = lane; t < T0; t += 32) mg = fminf(mg, fabsf(__fsub_rn(thr, e[t])));
+    mg = -warp_max(-mg);
+    if (lane == 0) margin_out[item] = mg;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -4,9 +4,8 @@ Callers of the reference always score both metrics on the same pair of tensors
 (README.md:29-30, benchmark_metrics.py:22,24).  With host tensors the PCIe copy dominates the
 end-to-end time, so `score_pesq_stoi` hands the pair to the library once: every chunk is copied
 once and both kernel pipelines run on it.  Results are identical to
-calling the two metric objects separately.  (A single-READ first-pass kernel exists as well --
-`score_pesq_stoi_tensors(..., overlap=3)` -- but it is slower than the two separate first kernels on
-B200, see include/fsem.h.)
+calling the two metric objects separately.  (Round 1's single-READ first-pass kernel and two-stream
+overlap modes measured slower than the two separate first kernels on B200 and were removed; DESIGN.md.)
 """
 from __future__ import annotations
 
@@ -20,13 +19,13 @@ from .PESQ import PESQ
 from .STOI import STOI
 
 
-def score_pesq_stoi_tensors(pesq: PESQ, stoi: STOI, clean: torch.Tensor, deg: torch.Tensor, lengths=None,
-                            overlap: int = 0):
+def score_pesq_stoi_tensors(pesq: PESQ, stoi: STOI, clean: torch.Tensor, deg: torch.Tensor, lengths=None):
     """Device-resident scoring of both metrics: [B, n] float32 CUDA tensors -> (scores[3, B] f32 = PESQ / STOI /
-    ESTOI rows, pesq_status[B], kept_frames[B], stoi_status[B]) CUDA tensors; stream-ordered, no host sync.
-    overlap = 0 (default): the two kernel chains back to back; 1 / 2: the STOI chain on a second stream next to
-    PESQ's spectrum kernel (measured on B200: no gain); 3: single-read first pass (one kernel feeds both metrics
-    from one read of the input; measured slower).  See include/fsem.h (fsem_pesq_stoi_score_f32)."""
+    ESTOI rows, pesq_status[B], kept_frames[B], stoi_status[B]) CUDA tensors; stream-ordered, no host sync
+    (C ABI fsem_pesq_stoi_score_f32: the two kernel chains back to back on the current stream)."""
+    clean, deg = pesq._on_device(clean), pesq._on_device(deg)
+    if stoi.device != pesq.device:
+        raise Exception("both metrics must live on the same CUDA device")
     b, n = clean.shape
     lens = pesq._lengths_tensor(lengths, b, n, clean.device)
     scores = torch.empty(3, b, dtype=torch.float32, device=clean.device)
@@ -43,9 +42,10 @@ def score_pesq_stoi_tensors(pesq: PESQ, stoi: STOI, clean: torch.Tensor, deg: to
         PESQ._check_score(pesq._lib.fsem_pesq_stoi_score_f32(
             pesq._ctx, stoi._ctx, C.byref(batch), scores[0].data_ptr(), pst.data_ptr(), scores[1].data_ptr(),
             scores[2].data_ptr(), kept.data_ptr(), sst.data_ptr(), wp.data_ptr(), wp.numel(), wsb.data_ptr(),
-            wsb.numel(), C.c_void_p(torch.cuda.current_stream(clean.device).cuda_stream), int(overlap)))
+            wsb.numel(), C.c_void_p(torch.cuda.current_stream(clean.device).cuda_stream)))
     pesq._last_shape = (b, n)
     stoi._last_shape = (b, n)
+    stoi._last_lengths = lens
     return scores, pst, kept, sst
 
 

@@ -43,7 +43,7 @@ extern "C" {
 #define FSEM_API
 #endif
 
-#define FSEM_VERSION 100 /* 0.1.0 */
+#define FSEM_VERSION 200 /* 0.2.0 */
 
 #define FSEM_OK 0
 #define FSEM_E_INVALID (-1) /* bad argument (null pointer, negative size, ...) */
@@ -124,6 +124,7 @@ typedef struct fsem_stoi_design {
 typedef struct fsem_pesq_ctx fsem_pesq_ctx_t;
 typedef struct fsem_stoi_ctx fsem_stoi_ctx_t;
 typedef struct fsem_lsd_ctx fsem_lsd_ctx_t;
+typedef struct fsem_resampler fsem_resampler_t;
 
 FSEM_API int fsem_version(void);
 FSEM_API const char* fsem_last_error(void);
@@ -175,6 +176,13 @@ FSEM_API int fsem_stoi_score_host_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t* 
 FSEM_API int fsem_stoi_debug_taps(fsem_stoi_ctx_t* ctx, int64_t batch, int64_t n, const void* workspace,
                          uint32_t* mask_out, float* tob_out, float* resampled_out,
                          int64_t* dims_out, void* stream);
+/* Silent-frame decision margins (device pointers, after a score call on the same workspace and batch):
+ * margin_out[batch] fp32 = min over the item's analysis frames of |(max_t E_t - dyn_range) - E_t| in dB, i.e. how
+ * far the closest frame of the item is from flipping the bit-exact keep/drop decision of STOI.py:98-102
+ * (+inf for an item without frames).  A batch whose smallest margin is above ~1e-4 dB cannot have been decided
+ * differently by any fp32 evaluation order of the frame norm.  `lengths` as passed to the score call (or NULL). */
+FSEM_API int fsem_stoi_mask_margin(fsem_stoi_ctx_t* ctx, int64_t batch, int64_t n, const int32_t* lengths,
+                          const void* workspace, float* margin_out, void* stream);
 
 /* ------------------------------------------------------------------ PESQ + STOI, one upload
  * Host entry point scoring BOTH metrics while copying every chunk of the batch host->device once
@@ -186,22 +194,15 @@ FSEM_API int fsem_pesq_stoi_score_host_f32(fsem_pesq_ctx_t* pesq, fsem_stoi_ctx_
                                   int32_t* kept_frames_out, int32_t* stoi_status_out);
 
 /* Device entry point for both metrics (device pointers, separate workspaces sized by the two
- * *_workspace_bytes functions).
- *   overlap = 0 (default): the two complete kernel chains back to back on `stream`, each reading the input itself;
- *   overlap = 1: the STOI chain runs on an internal second stream that starts after PESQ's IIR pass;
- *   overlap = 2: as 1, with the spectrum kernel capped at one CTA per SM;
- *   overlap = 3: single-read first pass -- ONE kernel reads every input sample once and produces both PESQ's
- *     filtered signal + band power and STOI's 10 kHz signal + hop energies (16 kHz input, 16-byte aligned rows,
- *     batch >= 16; otherwise it behaves like 0), then the remaining kernels of both chains run back to back.
- *     Saves 9 GB of HBM traffic per 8192 x 10 s but is issue-bound and measured slower than mode 0 on B200
- *     (9.5 ms against 4.4 + 3.7 ms for the two separate first kernels), hence not the default.
- * `stream` is joined with the second stream before returning (stream-ordered, no host synchronisation).
- * STOI/ESTOI, the silent-frame masks and K are identical in all modes; PESQ of overlap = 3 differs from the other
- * modes by the IIR chunk-grid noise (<= 1e-5; 2.5e-5 on 20-frame items: the same effect as changing the batch size). */
+ * *_workspace_bytes functions): the two complete kernel chains back to back on `stream`, each reading the
+ * input itself; stream-ordered, no host synchronisation.  Results are identical to the two separate calls.
+ * (Round 1 also carried a single-READ first-pass kernel and two-stream overlap modes behind an `overlap`
+ * argument; both measured slower than this on B200 -- 9.5 ms against 4.0 + 3.5 ms for the two separate first
+ * kernels, issue-bound rather than HBM-bound -- and were removed in 0.2.0.  DESIGN.md section 5.) */
 FSEM_API int fsem_pesq_stoi_score_f32(fsem_pesq_ctx_t* pesq, fsem_stoi_ctx_t* stoi, const fsem_batch_t* in,
                              float* mos_out, int32_t* pesq_status_out, float* stoi_out, float* estoi_out,
                              int32_t* kept_frames_out, int32_t* stoi_status_out, void* ws_pesq, size_t ws_pesq_bytes,
-                             void* ws_stoi, size_t ws_stoi_bytes, void* stream, int overlap);
+                             void* ws_stoi, size_t ws_stoi_bytes, void* stream);
 
 /* ------------------------------------------------------------------ ingest formats
  * The reference's boundary is float32 (base.py:16-21).  These entry points also take int16 PCM and fp16 sample
@@ -227,10 +228,24 @@ FSEM_API int fsem_score_host(fsem_pesq_ctx_t* pesq, fsem_stoi_ctx_t* stoi, const
                     int32_t* pesq_status_out, float* stoi_out, float* estoi_out, int32_t* kept_frames_out,
                     int32_t* stoi_status_out);
 
+/* ------------------------------------------------------------------ resample-on-ingest (building block)
+ * Replaces the torchaudio Resample of BaseMetric.prepare_audio (fast_se_metrics/base.py:13,19-20) for the metrics
+ * that do not fuse it into their own first kernel (LSD, SDR): y[neu*k + p] = sum_j taps[p][j] * xpad[orig*k + j],
+ * xpad = `width` zeros | x | zeros, output length ceil(neu * len / orig) per item.  `taps` is the HOST kernel
+ * [neu][ntaps] torchaudio builds (design.sinc_hann_kernel), orig/neu the rates divided by their gcd.
+ * fsem_resample_f32: `in` holds DEVICE rows; `out` is a DEVICE buffer [2, batch, out_stride] fp32 (clean rows, then
+ * degraded rows); lengths_out[batch] (device int32) receives the per-item output lengths when in->lengths is given. */
+FSEM_API int fsem_resampler_create(fsem_resampler_t** out, int32_t orig, int32_t neu, int32_t width, int32_t ntaps,
+                          const float* taps);
+FSEM_API int fsem_resampler_destroy(fsem_resampler_t* r);
+FSEM_API int64_t fsem_resampled_len(const fsem_resampler_t* r, int64_t n);
+FSEM_API int fsem_resample_f32(fsem_resampler_t* r, const fsem_batch_t* in, float* out, int64_t out_stride,
+                      int32_t* lengths_out, void* stream);
+
 /* ------------------------------------------------------------------ LSD (adjacent metric on the same FFT)
  * Replaces LSD.compute_metric (fast_se_metrics/LSD.py:33-52): scale-matched log-spectral distance on a
  * centred Hann-512/256 STFT.  `hann512` is the HOST window torch.hann_window(512) (LSD.py:16).
- * lsd_out[batch] fp32 and all batch pointers are DEVICE pointers; 16 kHz input only. */
+ * lsd_out[batch] fp32 and all batch pointers are DEVICE pointers; 16 kHz rows (other rates: fsem_resample_f32 first). */
 FSEM_API int fsem_lsd_create(fsem_lsd_ctx_t** out, const float* hann512);
 FSEM_API int fsem_lsd_destroy(fsem_lsd_ctx_t* ctx);
 FSEM_API size_t fsem_lsd_workspace_bytes(const fsem_lsd_ctx_t* ctx, int64_t batch, int64_t n);

@@ -24,10 +24,12 @@ def lsd_item(clean: np.ndarray, deg: np.ndarray) -> float:
     return float(np.mean(np.sqrt(np.mean(lsd, axis=1))))                              # LSD.py:50
 
 
-def lsd_batch(clean: np.ndarray, deg: np.ndarray, lengths=None) -> np.ndarray:
+def lsd_batch(clean: np.ndarray, deg: np.ndarray, lengths=None, sample_rate: int = 16000) -> np.ndarray:
+    """sample_rate != 16000: resample-on-ingest first (base.py:19-20, torchaudio sinc-Hann kernel)."""
+    from .stoi_oracle import resample
     clean, deg = np.atleast_2d(clean), np.atleast_2d(deg)
     out = np.empty(clean.shape[0])
     for i in range(clean.shape[0]):
         n = clean.shape[1] if lengths is None else int(lengths[i])
-        out[i] = lsd_item(clean[i, :n], deg[i, :n])
+        out[i] = lsd_item(resample(clean[i, :n], sample_rate, 16000), resample(deg[i, :n], sample_rate, 16000))
     return out

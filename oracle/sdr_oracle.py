@@ -25,10 +25,12 @@ def sdr_item(clean: np.ndarray, deg: np.ndarray) -> float:
     return float(10.0 * np.log10(max(ratio, 1e-8)))            # SDR.py:91-95
 
 
-def sdr_batch(clean: np.ndarray, deg: np.ndarray, lengths=None) -> np.ndarray:
+def sdr_batch(clean: np.ndarray, deg: np.ndarray, lengths=None, sample_rate: int = 16000) -> np.ndarray:
+    """sample_rate != 16000: resample-on-ingest first (base.py:19-20, torchaudio sinc-Hann kernel)."""
+    from .stoi_oracle import resample
     clean, deg = np.atleast_2d(clean), np.atleast_2d(deg)
     out = np.empty(clean.shape[0])
     for i in range(clean.shape[0]):
         n = clean.shape[1] if lengths is None else int(lengths[i])
-        out[i] = sdr_item(clean[i, :n], deg[i, :n])
+        out[i] = sdr_item(resample(clean[i, :n], sample_rate, 16000), resample(deg[i, :n], sample_rate, 16000))
     return out

@@ -72,6 +72,29 @@ def lsd_cases():
     return cases
 
 
+def lsd_rate_cases():
+    """LSD with resample-on-ingest to 16 kHz (base.py:13,19-20): (clean, degraded, lengths, sample_rate)."""
+    cases = {}
+    c, d, _ = synth_batch(311, 3, 16000, fs=8000)
+    cases["speech8k_2s"] = (c, d, None, 8000)
+    c, d, _ = synth_batch(312, 3, 96000, fs=48000)
+    cases["ragged48k"] = (c, d, [96000, 60001, 24000], 48000)
+    return cases
+
+
+def sdr_rate_cases():
+    """SDR with resample-on-ingest to 16 kHz (base.py:13,19-20): (clean, degraded, lengths, sample_rate).
+    Down-sampling rates only: an up-sampled (band-limited) signal makes the 512 x 512 autocorrelation matrix
+    numerically singular -- the reference's own float32 Cholesky fails on 8 kHz input and its fallback
+    `torch.linalg.solve` dies inside MKL (SLASWP parameter error), so there is no reference value to pin."""
+    cases = {}
+    c, d, _ = synth_batch(411, 3, 64000, fs=32000)
+    cases["speech32k_2s"] = (c, d, None, 32000)
+    c, d, _ = synth_batch(412, 3, 96000, fs=48000)
+    cases["ragged48k"] = (c, d, [96000, 60001, 24000], 48000)
+    return cases
+
+
 def sdr_cases():
     """SDR (fast_se_metrics/SDR.py): (clean, degraded, lengths)."""
     cases = {}

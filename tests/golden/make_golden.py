@@ -37,6 +37,7 @@ _cases = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(_cases)   # (the reference ships its own `tests` package, so import by path)
 pesq_cases, stoi_cases, pesq_rate_cases, lsd_cases, sdr_cases = (
     _cases.pesq_cases, _cases.stoi_cases, _cases.pesq_rate_cases, _cases.lsd_cases, _cases.sdr_cases)
+lsd_rate_cases, sdr_rate_cases = _cases.lsd_rate_cases, _cases.sdr_rate_cases
 
 
 def run_pesq():
@@ -159,6 +160,15 @@ def run_lsd():
             res = [metric(c[i:i + 1, :n], d[i:i + 1, :n])[0]["LSD"] for i, n in enumerate(lengths)]
         out[name] = np.asarray(res, np.float64)
         print("LSD", name, out[name])
+    for name, (clean, deg, lengths, fs) in lsd_rate_cases().items():      # resample-on-ingest (base.py:19-20)
+        m = LSD(fs, use_gpu=False)
+        c, d = torch.from_numpy(clean), torch.from_numpy(deg)
+        if lengths is None:
+            res = [r["LSD"] for r in m(c, d)]
+        else:
+            res = [m(c[i:i + 1, :n], d[i:i + 1, :n])[0]["LSD"] for i, n in enumerate(lengths)]
+        out["rate/" + name] = np.asarray(res, np.float64)
+        print("LSD rate", name, out["rate/" + name])
     np.savez_compressed(os.path.join(HERE, "golden_lsd.npz"), **out)
 
 
@@ -174,12 +184,20 @@ def run_sdr():
             res = [metric(c[i:i + 1, :n], d[i:i + 1, :n])[0]["SDR"] for i, n in enumerate(lengths)]
         out[name] = np.asarray(res, np.float64)
         print("SDR", name, out[name])
+    for name, (clean, deg, lengths, fs) in sdr_rate_cases().items():      # resample-on-ingest (base.py:19-20)
+        m = SDR(fs, use_gpu=False)
+        c, d = torch.from_numpy(clean), torch.from_numpy(deg)
+        if lengths is None:
+            res = [r["SDR"] for r in m(c, d)]
+        else:
+            res = [m(c[i:i + 1, :n], d[i:i + 1, :n])[0]["SDR"] for i, n in enumerate(lengths)]
+        out["rate/" + name] = np.asarray(res, np.float64)
+        print("SDR rate", name, out["rate/" + name])
     np.savez_compressed(os.path.join(HERE, "golden_sdr.npz"), **out)
 
 
 if __name__ == "__main__":
-    run_pesq()
-    run_stoi()
-    run_lsd()
-    run_sdr()
+    which = sys.argv[1:] or ["pesq", "stoi", "lsd", "sdr"]      # e.g. `make_golden.py lsd sdr` regenerates two files
+    for name in which:
+        {"pesq": run_pesq, "stoi": run_stoi, "lsd": run_lsd, "sdr": run_sdr}[name]()
     print("golden fixtures written to", HERE)

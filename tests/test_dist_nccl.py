@@ -1,0 +1,89 @@
+"""NCCL test (-m gpu, needs >= 2 GPUs; skipped otherwise): the batch-sharded scoring path of bench.py / dist.py over
+real NCCL with an UNEVEN batch (8191 items over 2 ranks: shards of 4096 and 4095, padded for the collective).
+
+Every rank scores its own shard with the CUDA kernels, the score rows are all-gathered, and every rank checks the
+gathered [8191, 3] table bit for bit against its own scoring of BOTH shards (identical GPUs, deterministic kernels),
+plus a sample of rows against the float64 oracle."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BATCH = 8191
+N = 8000
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _make_batch(device):
+    from fast_speech_enhancement_metrics_b200.synth import synth_batch
+    clean, deg, _ = synth_batch(909, 32, N)
+    reps = -(-BATCH // 32)
+    c = torch.from_numpy(clean).to(device).repeat(reps, 1)[:BATCH]
+    d = torch.from_numpy(deg).to(device).repeat(reps, 1)[:BATCH]
+    gains = torch.linspace(0.25, 2.0, BATCH, device=device)[:, None]
+    return (c * gains).contiguous(), (d * gains).contiguous(), clean, deg
+
+
+def _worker(rank, world, port, q):
+    try:
+        import torch.distributed as dist
+
+        from fast_speech_enhancement_metrics_b200 import PESQ, STOI
+        from fast_speech_enhancement_metrics_b200.dist import gather_scores, shard_ranges
+        from oracle import pesq_oracle, stoi_oracle
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        torch.cuda.set_device(rank)
+        device = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
+        pesq, stoi = PESQ(16000, use_gpu=True), STOI(16000, use_gpu=True)
+        c, d, _, _ = _make_batch(device)
+        ranges = shard_ranges(BATCH, world)
+
+        def score(lo, hi):
+            mos, _ = pesq.score_tensors(c[lo:hi], d[lo:hi])
+            sc, _, _ = stoi.score_tensors(c[lo:hi], d[lo:hi])
+            return torch.stack([mos, sc[0], sc[1]], dim=1)
+
+        lo, hi = ranges[rank]
+        full = gather_scores(score(lo, hi), BATCH, world)
+        want = torch.cat([score(a, b) for a, b in ranges])
+        ok_shape = tuple(full.shape) == (BATCH, 3)
+        ok_bits = bool(torch.equal(full.contiguous().view(torch.int32), want.contiguous().view(torch.int32)))
+        pick = [0, 31, 4095, 4096, BATCH - 1]
+        cs, ds = c[pick].cpu().numpy(), d[pick].cpu().numpy()
+        got = full[pick].double().cpu().numpy()
+        dp = float(np.max(np.abs(got[:, 0] - pesq_oracle.pesq_batch(cs, ds))))
+        ws, we, _ = stoi_oracle.stoi_batch(cs, ds, 16000)
+        dsd = float(max(np.max(np.abs(got[:, 1] - ws)), np.max(np.abs(got[:, 2] - we))))
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, ok_shape, ok_bits, dp, dsd))
+    except Exception as exc:   # report instead of hanging the parent
+        q.put((rank, False, False, repr(exc), 0.0))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (NCCL)")
+def test_sharded_scores_over_nccl_uneven_batch():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=120)
+    for rank, ok_shape, ok_bits, dp, dsd in res:
+        assert ok_shape and ok_bits, (rank, dp)
+        assert dp <= 2e-4 and dsd <= 1e-4, (rank, dp, dsd)

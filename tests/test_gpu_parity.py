@@ -220,14 +220,10 @@ def test_fused_upload_equals_separate_calls(pesq, stoi_metrics):
     assert np.array_equal(np.array([r["STOI"] for r in both]), np.array([r["STOI"] for r in sep_s]), equal_nan=True)
 
 
-@pytest.mark.parametrize("shape", [(64, 48000, False), (33, 40004, False), (40, 64000, True), (16, 17000, True),
-                                   (150, 5380, False)])
-def test_single_read_first_pass_matches_the_two_separate_kernels(shape, pesq, stoi_metrics):
-    """fsem_pesq_stoi_score_f32 with overlap = 3 runs ONE first-pass kernel that reads every sample once and
-    produces PESQ's filtered signal + band power and STOI's 10 kHz signal + hop energies; overlap = 0 runs the two
-    separate first kernels.  The 10 kHz signals must be bit-identical, the silent-frame masks and K equal,
-    STOI/ESTOI equal; PESQ agrees to the chunk-grid noise (the single-read pass cuts the IIR time axis on a
-    1024-sample grid instead of a 64-sample one: the same effect as changing the batch size)."""
+@pytest.mark.parametrize("shape", [(64, 48000, False), (33, 40004, False), (40, 64000, True), (150, 5380, False)])
+def test_fused_device_entry_against_oracle(shape, pesq, stoi_metrics):
+    """fsem_pesq_stoi_score_f32 (both kernel chains, one call) against the float64 ORACLE on the same seeded inputs --
+    not against the CUDA path itself: PESQ <= 2e-4, STOI/ESTOI <= 1e-4, K exact (sample of items for the big shapes)."""
     from fast_speech_enhancement_metrics_b200 import score_pesq_stoi_tensors
     from fast_speech_enhancement_metrics_b200.synth import synth_batch
     b, n, ragged = shape
@@ -239,26 +235,93 @@ def test_single_read_first_pass_matches_the_two_separate_kernels(shape, pesq, st
         lens[0], lens[-1] = n, 5400
         lens = lens.tolist()
     st = stoi_metrics(16000)
-    out = {}
-    for mode in (0, 3):
-        scores, pst, kept, sst = score_pesq_stoi_tensors(pesq, st, c, d, lens, overlap=mode)
-        taps = st.debug_taps()
-        bark, power = pesq.debug_taps()
-        out[mode] = dict(scores=scores.cpu().numpy(), pst=pst.cpu().numpy(), kept=kept.cpu().numpy(), sst=sst.cpu().numpy(),
-                         y=taps["resampled"].cpu().numpy(), mask=taps["mask"].cpu().numpy(), tob=taps["tob"].cpu().numpy(),
-                         power=power.cpu().numpy())
-    sep, one = out[0], out[3]
-    L = [(5 * (n if lens is None else lens[i]) + 7) // 8 for i in range(b)]
-    for i in range(b):
-        assert np.array_equal(sep["y"][:, i, :L[i]], one["y"][:, i, :L[i]]), i        # 10 kHz signals: bit-identical
-    assert np.array_equal(sep["mask"], one["mask"]) and np.array_equal(sep["kept"], one["kept"])
-    assert np.array_equal(sep["pst"], one["pst"]) and np.array_equal(sep["sst"], one["sst"])
-    assert np.array_equal(sep["scores"][1:], one["scores"][1:], equal_nan=True)       # STOI, ESTOI
-    assert np.allclose(sep["power"], one["power"], rtol=2e-5, atol=0)                 # band power: chunk-grid noise only
-    d_pesq = np.abs(sep["scores"][0] - one["scores"][0])
-    # 20-frame items (the 5380-sample shape) are the most sensitive to where the chunk boundaries fall: 2.5e-5 there
-    assert np.nanmax(d_pesq) <= (5e-5 if n < 16000 else 1e-5), np.nanmax(d_pesq)
-    _report("first_pass_vs_separate_pesq_%dx%d%s" % (b, n, "_ragged" if ragged else ""), float(np.nanmax(d_pesq)))
+    scores, pst, kept, sst = score_pesq_stoi_tensors(pesq, st, c, d, lens)
+    scores, kept = scores.cpu().numpy().astype(np.float64), kept.cpu().numpy()
+    pick = sorted(set(np.linspace(0, b - 1, 12).round().astype(int).tolist()))
+    pl = None if lens is None else [lens[i] for i in pick]
+    want_p = po.pesq_batch(clean[pick], deg[pick], pl)
+    ws, we, wk = so.stoi_batch(clean[pick], deg[pick], 16000, pl)
+    dp = _maxdiff(scores[0][pick], want_p)
+    assert dp <= 2e-4, dp
+    assert _maxdiff(scores[1][pick], ws) <= 1e-4 and _maxdiff(scores[2][pick], we) <= 1e-4
+    assert np.array_equal(kept[pick], wk)
+    _report("fused_vs_oracle_pesq_%dx%d%s" % (b, n, "_ragged" if ragged else ""), dp)
+
+
+def test_mask_margin_reports_how_close_the_silent_frame_decisions_were(stoi_metrics, golden_stoi):
+    """STOI.mask_margin(): min_t |(max E - 40) - E_t| per item (dB), against the oracle's float64 energies; the mask of
+    every fixture case is bit-exact AND its smallest margin is reported (ties are reported by margin)."""
+    for name in ("speech10k_3s", "speech16k_3s", "ragged10k"):
+        clean, deg, lengths, fs = STOI_CASES[name]
+        metric = stoi_metrics(fs)
+        c, d = torch.from_numpy(clean).cuda(), torch.from_numpy(deg).cuda()
+        metric.score_tensors(c, d, lengths)
+        got = metric.mask_margin().cpu().numpy()
+        win = so.window32().astype(np.float64)
+        for i in range(clean.shape[0]):
+            n = clean.shape[1] if lengths is None else lengths[i]
+            x = so.resample(clean[i, :n], fs, 10000).astype(np.float64)
+            if len(x) < 256:
+                assert np.isinf(got[i])
+                continue
+            t0 = (len(x) - 256) // 128 + 1
+            fr = np.stack([x[128 * t:128 * t + 256] * win for t in range(t0)])
+            e = 20 * np.log10(np.linalg.norm(fr, axis=1) + 1e-9)
+            want = np.min(np.abs(e.max() - 40 - e))
+            assert abs(got[i] - want) <= 2e-4 + 1e-3 * want, (name, i, got[i], want)
+        _report("mask_margin_min_db_" + name, float(np.min(got[np.isfinite(got)])))
+
+
+def test_headline_workload_sample_against_oracle(pesq, stoi_metrics):
+    """BASELINE configs[4] at FULL size (8192 x 10 s on one GPU, the tensors bench.py times): every item scored, a
+    sample of 32 items spread over the batch checked against the oracle (and the staged reference, if present) through
+    bench.py's own parity block."""
+    import bench
+    free, _ = torch.cuda.mem_get_info()
+    batch = 8192 if free > 60e9 else 1024
+    device = torch.device("cuda", torch.cuda.current_device())
+    clean, deg = bench.make_shard(batch, 160000, 1000, device)
+    st = stoi_metrics(16000)
+    mos, _ = pesq.score_tensors(clean, deg)
+    sc, _, _ = st.score_tensors(clean, deg)
+    table = torch.stack([mos, sc[0], sc[1]], dim=1)
+    par = bench.parity_block(pesq, st, clean, deg, table, 0, batch, 1, device, 32)
+    _report("headline_%dx10s" % batch, par)
+    assert par["ok"], par
+    assert par["items"] >= 32 and par["k_equal"]
+    del clean, deg
+    pesq._workspace = None
+    st._workspace = None
+    torch.cuda.empty_cache()
+
+
+def test_batches_beyond_the_grid_y_limit(stoi_metrics):
+    """More than 32767 items per call (2 x batch used to sit in gridDim.y, capped at 65535)."""
+    from fast_speech_enhancement_metrics_b200.synth import synth_batch
+    clean, deg, _ = synth_batch(77, 8, 8000)
+    b = 33000
+    c = torch.from_numpy(clean).cuda().repeat(b // 8, 1).contiguous()
+    d = torch.from_numpy(deg).cuda().repeat(b // 8, 1).contiguous()
+    st = stoi_metrics(16000)
+    scores, kept, _ = st.score_tensors(c, d)
+    scores = scores.cpu().numpy()
+    assert np.array_equal(scores[:, :8], scores[:, -8:], equal_nan=True)
+    ws, we, wk = so.stoi_batch(clean, deg, 16000)
+    assert _maxdiff(scores[0, :8], ws) <= 1e-4 and _maxdiff(scores[1, :8], we) <= 1e-4
+    st._workspace = None
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_tensors_on_another_device_are_moved_like_the_reference_does(pesq, stoi_metrics):
+    """A metric lives on the device that was current at construction; CUDA tensors on another device are moved there
+    (base.py:18 `.to(self.device)`) instead of being dereferenced from the wrong GPU."""
+    clean, deg, _ = PESQ_CASES["speech2s"]
+    c0, d0 = torch.from_numpy(clean).cuda(0), torch.from_numpy(deg).cuda(0)
+    c1, d1 = c0.to("cuda:1"), d0.to("cuda:1")
+    assert pesq(c1, d1) == pesq(c0, d0)
+    st = stoi_metrics(16000)
+    assert st(c1, d1) == st(c0, d0)
 
 
 def test_stoi_errors(stoi_metrics, golden_stoi):

@@ -17,7 +17,7 @@ from tests.conftest import ROOT
 
 def test_library_loads_and_exports_every_declared_symbol():
     lib = _lib.load()
-    assert lib.fsem_version() == 100
+    assert lib.fsem_version() == 200
     header = open(os.path.join(ROOT, "include", "fsem.h")).read()
     declared = set(re.findall(r"FSEM_API [^;(]*?\b(fsem_[a-z0-9_]+)\(", header))
     assert declared == set(_lib.EXPORTS)

@@ -10,9 +10,10 @@ import pytest
 
 from oracle import sdr_oracle as sd
 from tests.conftest import GOLDEN_DIR
-from tests.golden.cases import sdr_cases
+from tests.golden.cases import sdr_cases, sdr_rate_cases
 
 CASES = sdr_cases()
+RATE_CASES = sdr_rate_cases()
 
 
 @pytest.fixture(scope="module")
@@ -39,4 +40,27 @@ def test_sdr_matches_reference_and_oracle(name, golden_sdr):
     host = np.array([r["SDR"] for r in metric(torch.from_numpy(clean), torch.from_numpy(deg), lengths=lengths)])
     assert np.max(np.abs(got - golden_sdr[name])) <= 5e-2
     assert np.max(np.abs(got - sd.sdr_batch(clean, deg, lengths))) <= 2e-2
+    assert np.array_equal(got, host)
+
+
+@pytest.mark.parametrize("name", sorted(RATE_CASES))
+def test_sdr_oracle_resample_on_ingest_matches_reference(name, golden_sdr):
+    clean, deg, lengths, fs = RATE_CASES[name]
+    got = sd.sdr_batch(clean, deg, lengths, sample_rate=fs)
+    assert np.max(np.abs(got - golden_sdr["rate/" + name])) <= 2e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(RATE_CASES))
+def test_sdr_resample_on_ingest(name, golden_sdr):
+    """SDR(sample_rate != 16000): resample-on-ingest through the library's polyphase kernel (base.py:13,19-20)."""
+    import torch
+
+    from fast_speech_enhancement_metrics_b200 import SDR
+    clean, deg, lengths, fs = RATE_CASES[name]
+    metric = SDR(fs, use_gpu=True)
+    got = np.array([r["SDR"] for r in metric(torch.from_numpy(clean).cuda(), torch.from_numpy(deg).cuda(), lengths=lengths)])
+    host = np.array([r["SDR"] for r in metric(torch.from_numpy(clean), torch.from_numpy(deg), lengths=lengths)])
+    assert np.max(np.abs(got - golden_sdr["rate/" + name])) <= 5e-2
+    assert np.max(np.abs(got - sd.sdr_batch(clean, deg, lengths, sample_rate=fs))) <= 2e-2
     assert np.array_equal(got, host)

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from fast_speech_enhancement_metrics_b200 import PESQ, STOI, _lib  # noqa: E402
+from fast_speech_enhancement_metrics_b200 import LSD, PESQ, SDR, STOI, _lib  # noqa: E402
 from fast_speech_enhancement_metrics_b200.synth import synth_batch  # noqa: E402
 
 
@@ -79,6 +79,29 @@ def main():
         rows.append(row)
         print("%-42s PESQ %9.3f ms  STOI %9.3f ms  both %12.0f audio-s/s" % (name, row["PESQ"]["ms"], row["STOI"]["ms"],
                                                                             row["PESQ+STOI"]["audio_s_per_s"]), flush=True)
+        del c, d
+        torch.cuda.empty_cache()
+    # adjacent metrics at the headline shape, with their HBM roofline line: one call must read both
+    # fp32 signals once = 128 000 B per audio-second
+    peak = 6555.8
+    try:
+        peak = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                 "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    lsd, sdr = LSD(16000, use_gpu=True), SDR(16000, use_gpu=True)
+    for name, b, n in (("LSD/SDR 8192 x 10 s", 8192, 160000), ("LSD/SDR 256 x 10 s", 256, 160000)):
+        c, d = make(b, n, 3000 + b)
+        audio_s = b * n / 16000.0
+        row = {"shape": name, "batch": b, "samples": n, "audio_s": audio_s}
+        for label, metric in (("LSD", lsd), ("SDR", sdr)):
+            ms, prof = timed(lambda: metric.score_tensors(c, d), max(2, args.steps // 3))
+            gbs = 128000.0 * audio_s / (ms * 1e-3) / 1e9
+            row[label] = {"ms": round(ms, 4), "audio_s_per_s": round(audio_s / (ms * 1e-3), 1), "kernels_ms": prof,
+                          "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s",
+                                       "frac": round(gbs / peak, 4)}}
+        rows.append(row)
+        print("%-42s LSD  %9.3f ms  SDR  %9.3f ms" % (name, row["LSD"]["ms"], row["SDR"]["ms"]), flush=True)
         del c, d
         torch.cuda.empty_cache()
     os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)

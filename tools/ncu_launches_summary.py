@@ -1,13 +1,15 @@
 #!/usr/bin/env python
-"""Summarise an `ncu --csv` launch list of one bench step into profiles/*.md and profiles/dram_traffic.json.
+"""Summarise an `ncu --csv` launch list of one bench step into profiles/*.md and profiles/rNN_dram_traffic.json.
 
     ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
         -k regex:"pesq_|stoi_" -s 30 -c 10 --csv --log-file gpurun_out/launches.csv \
         python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu
-    python tools/ncu_launches_summary.py gpurun_out/launches.csv profiles/r01_ncu_launches_final
+    python tools/ncu_launches_summary.py gpurun_out/launches.csv profiles/r02_ncu_launches
 
-Writes <out>.csv (the input, ncu banner lines dropped), <out>.md (time share and DRAM bytes per launch) and refreshes
-profiles/dram_traffic.json, which bench.py reads for `roofline.traffic` (keys = the library's profiler names).
+Writes <out>.csv (the input, ncu banner lines dropped), <out>.md (time share and DRAM bytes per launch) and
+profiles/rNN_dram_traffic.json (NN = the round prefix of <out>), which bench.py reads -- newest round first -- for
+`roofline.traffic` (keys = the library's profiler names), so the traffic figure comes from a launch list of the same
+round's code.
 """
 from __future__ import annotations
 
@@ -49,7 +51,7 @@ def main():
     md = ["# ncu launch list of one step (8192 x 10 s, one B200): `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,"
           "dram__bytes_write.sum --clock-control none -k regex:\"pesq_|stoi_\" -s 30 -c 10 python bench.py --steps 1 "
           "--warmup 3 --no-e2e --no-cpu`", "",
-          "Cold-cache, serialised launches: compare SHARES with the live CUDA-event times in r01_bench_final_1gpu.json "
+          "Cold-cache, serialised launches: compare SHARES with the live CUDA-event times in the same round's bench JSON "
           "(`kernels`).", "", "| kernel | time (us) | share | DRAM read (GB) | DRAM write (GB) |", "|---|---|---|---|---|"]
     traffic = {}
     for short, us, rd, wr in table:
@@ -60,7 +62,10 @@ def main():
     md.append("| **total** | %.1f | | %.1f (read+write) | |" % (total_us, sum(traffic.values()) / 1e9))
     with open(out + ".md", "w") as f:
         f.write("\n".join(md) + "\n")
-    with open(os.path.join(ROOT, "profiles", "dram_traffic.json"), "w") as f:
+    import re
+    m = re.match(r"(r\d\d)_", os.path.basename(out))
+    rnd = m.group(1) if m else "r00"
+    with open(os.path.join(ROOT, "profiles", rnd + "_dram_traffic.json"), "w") as f:
         json.dump({"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch from %s.csv (ncu, 8192 x 10 s on one "
                                "B200); bench.py scales by items per GPU" % os.path.relpath(out, ROOT),
                    "items": 8192, "bytes_per_launch": traffic}, f, indent=1)
