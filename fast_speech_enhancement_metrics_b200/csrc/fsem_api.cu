@@ -303,6 +303,13 @@ extern "C" int fsem_pesq_create(fsem_pesq_ctx_t** out, const fsem_pesq_design_t*
             delete ctx;
             return fail(FSEM_E_INVALID, "fsem_pesq_create: Bark bands must tile bins 0..255 contiguously, at most 32 bins each (band %d)", b);
         }
+        {   // the spectrum kernel gathers a band from at most 1 (bands 0..31) / 4 (bands 32..48) earlier 8-bin groups
+            const int span = ((h.band_first[b] + h.band_count[b] - 1) >> 3) - (h.band_first[b] >> 3);
+            if (span > (b < 32 ? kBarkPiecesLow : kBarkPiecesHigh)) {
+                delete ctx;
+                return fail(FSEM_E_INVALID, "fsem_pesq_create: Bark band %d spans %d groups of 8 bins (unsupported layout)", b, span + 1);
+            }
+        }
         h.pow_dens[b] = d->pow_dens[b];
         h.thresh[b] = d->thresh[b];
         h.zw_exp[b] = d->zwicker_exp[b];
@@ -564,6 +571,8 @@ extern "C" int fsem_stoi_create(fsem_stoi_ctx_t** out, const fsem_stoi_design_t*
     for (int b = 0; b < FSEM_STOI_NBANDS; ++b)
         if (d->band_lo[b] < 0 || d->band_hi[b] < d->band_lo[b] || d->band_hi[b] > 256)
             return fail(FSEM_E_INVALID, "fsem_stoi_create: band %d outside bins 0..255", b);
+    if (d->band_hi[FSEM_STOI_NBANDS - 1] - d->band_lo[FSEM_STOI_NBANDS - 1] > 48)
+        return fail(FSEM_E_INVALID, "fsem_stoi_create: third-octave bands must be at most 48 bins wide");
     for (int b = 0; b + 1 < FSEM_STOI_NBANDS; ++b)
         if (d->band_hi[b] != d->band_lo[b + 1] || d->band_hi[b] - d->band_lo[b] > 48)
             return fail(FSEM_E_INVALID, "fsem_stoi_create: third-octave bands must be contiguous and at most 48 bins wide");
@@ -599,7 +608,7 @@ extern "C" int fsem_stoi_create(fsem_stoi_ctx_t** out, const fsem_stoi_design_t*
             }
     }
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stoi_tob_kernel, kTobWarps * 32, 0) == cudaSuccess && occ > 0)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stoi_tob_kernel<true>, kTobWarps * 32, 0) == cudaSuccess && occ > 0)
         ctx->tob_ctas_per_sm = occ;
     *out = ctx;
     return FSEM_OK;
@@ -706,9 +715,15 @@ extern "C" int fsem_stoi_score_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t* in,
         int64_t grid = ceil_div(units, kTobWarps);
         const int64_t cap = (int64_t)ctx->dev.sms * ctx->tob_ctas_per_sm;
         if (grid > cap) grid = cap;
+        const bool vec2 = (reinterpret_cast<uintptr_t>(c10) & 7u) == 0 && (reinterpret_cast<uintptr_t>(d10) & 7u) == 0 &&
+                          sstride % 2 == 0;
         { ProfScope prof_(K_STOI_TOB, stream);
-          stoi_tob_kernel<<<(unsigned)grid, kTobWarps * 32, 0, stream>>>(c10, d10, sstride, in->batch, p.t0max, p.umax,
-                                                                      p.ustride, kept_idx, frame_prefix, ctx->d_tab, tob); }
+          if (vec2)
+              stoi_tob_kernel<true><<<(unsigned)grid, kTobWarps * 32, 0, stream>>>(
+                  c10, d10, sstride, in->batch, p.t0max, p.umax, p.ustride, kept_idx, frame_prefix, ctx->d_tab, tob);
+          else
+              stoi_tob_kernel<false><<<(unsigned)grid, kTobWarps * 32, 0, stream>>>(
+                  c10, d10, sstride, in->batch, p.t0max, p.umax, p.ustride, kept_idx, frame_prefix, ctx->d_tab, tob); }
         FSEM_LAUNCHED();
     }
     {

@@ -54,9 +54,11 @@ lsd_frames_kernel(const float* __restrict__ clean, const float* __restrict__ deg
     float2* buf = s_buf[warp];
     FftTwiddles tw;
     tw.init(lane);
-    float win[16];
+    float win[16];                                               // win[8h + j] = hann[2*lane + h + 64 j]
 #pragma unroll
-    for (int m = 0; m < 16; ++m) win[m] = hann[lane + 32 * m];
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) win[8 * h + j] = hann[fft_in_index(lane, h, j)];
 
     const int64_t units = batch * (int64_t)tmax;
     const int64_t nwarps = (int64_t)gridDim.x * kLsdWarps;
@@ -72,24 +74,26 @@ lsd_frames_kernel(const float* __restrict__ clean, const float* __restrict__ deg
         if (f < T) {
             const float* __restrict__ c = clean + item * stride;
             const float* __restrict__ d = deg + item * stride;
-            const int first = f * 256 - 256 + lane;              // centred frames, zero ("constant") padding
+            const int first = f * 256 - 256;                     // centred frames, zero ("constant") padding
             float re[16], im[16];
 #pragma unroll
-            for (int m = 0; m < 16; ++m) {
-                const int i = first + 32 * m;
-                const bool ok = i >= 0 && i < len;
-                re[m] = ok ? __ldg(c + i) * win[m] : 0.f;
-                im[m] = ok ? __ldg(d + i) * win[m] : 0.f;
-            }
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int i = first + fft_in_index(lane, h, j);
+                    const bool ok = i >= 0 && i < len;
+                    re[8 * h + j] = ok ? __ldg(c + i) * win[8 * h + j] : 0.f;
+                    im[8 * h + j] = ok ? __ldg(d + i) * win[8 * h + j] : 0.f;
+                }
             warp_fft512<false>(re, im, buf, tw, lane);
             float pc[8], pd[8];
-            packed_power8(buf, lane, pc, pd);
+            packed_power8(buf, lane, pc, pd);                    // 4x the power spectra
             const float a = fabsf(alpha[item]);
             float acc = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float den = fmaf(a, sqrtf(pd[j]), kLsdEps);
-                const float l = logf(pc[j] / (den * den) + kLsdEps);
+                const float den = fmaf(a, sqrtf(pd[j] * kPackedPowerScale), kLsdEps);
+                const float l = logf(pc[j] * kPackedPowerScale / (den * den) + kLsdEps);
                 acc = fmaf(l, l, acc);
             }
             if (lane == 0) {                                     // Nyquist bin 256: C = Re Z[256], D = Im Z[256]

@@ -438,13 +438,17 @@ constexpr int kSpecWarps = FSEM_FFT_WARPS;
 // copies: frame f needs halves f and f+1, half f+2 is in flight while frame f is transformed, so the global-load
 // latency is off the critical path and every sample is fetched from L2/HBM once (frames overlap by 50 %).
 struct SpecWarpSmem {
-    float2 fft[kFftBufElems];          // 5120 B
+    float2 fft[kFftBufElems];          // 5120 B; after the power spectrum has been read it holds the band scan rows S
     float half_c[3][FSEM_PESQ_HOP];    // 3072 B
     float half_d[3][FSEM_PESQ_HOP];    // 3072 B
-    float bands[2][64];                //  512 B
     unsigned long long bar[3];         //   24 B (+8 pad)
     unsigned long long pad_;
 };
+static_assert(kBandSFloats <= 2 * kFftBufElems, "band scan rows alias the FFT exchange buffer");
+// extra lanes a Bark band may reach back into: bands 0..31 (<= 4 bins at 16 kHz) at most one, bands 32..48 at most four
+// (fsem_pesq_create checks the design against these bounds)
+constexpr int kBarkPiecesLow = 1;
+constexpr int kBarkPiecesHigh = 4;
 constexpr size_t kSpecDynSmem = sizeof(SpecWarpSmem) * kSpecWarps;
 static_assert(sizeof(SpecWarpSmem) % 16 == 0, "per-warp shared block must keep 16-byte alignment");
 
@@ -457,8 +461,7 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
     const int warp = threadIdx.x >> 5;
     SpecWarpSmem& sm = reinterpret_cast<SpecWarpSmem*>(s_raw)[warp];
     float2* buf = sm.fft;
-    float* bands_c = sm.bands[0];
-    float* bands_d = sm.bands[1];
+    float* S = reinterpret_cast<float*>(sm.fft);
     const uint32_t bar0 = smem_u32(&sm.bar[0]);
     const uint32_t hc0 = smem_u32(&sm.half_c[0][0]), hd0 = smem_u32(&sm.half_d[0][0]);
     constexpr uint32_t kHalfBytes = FSEM_PESQ_HOP * sizeof(float);
@@ -470,14 +473,26 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
 
     FftTwiddles tw;
     tw.init(lane);
-    float win[16];
+    float win[16];                                               // win[8h + j] = hann[2*lane + h + 64 j]
 #pragma unroll
-    for (int m = 0; m < 16; ++m) win[m] = tab->hann[lane + 32 * m];
-    BandPlan plan;
-    plan.init(tab->band_first, FSEM_PESQ_NBANDS, lane);
-    // power-density correction * Sp of the two bands this lane stores (bark.py:132, 204)
-    const float scale0 = tab->pow_dens[lane];
-    const float scale1 = (lane + 32 < FSEM_PESQ_NBANDS) ? tab->pow_dens[lane + 32] : 0.f;
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) win[8 * h + j] = tab->hann[fft_in_index(lane, h, j)];
+    BandScan scan;
+    scan.init(tab->band_first, FSEM_PESQ_NBANDS, lane);
+    // this lane gathers Bark bands `lane` and `lane + 32`
+    BandGather<kBarkPiecesLow> g_lo;
+    BandGather<kBarkPiecesHigh> g_hi;
+    g_lo.init(tab->band_first[lane], tab->band_first[lane] + tab->band_count[lane], true);
+    {
+        const bool has_hi = lane + 32 < FSEM_PESQ_NBANDS;
+        const int bh = has_hi ? lane + 32 : 0;
+        g_hi.init(tab->band_first[bh], tab->band_first[bh] + tab->band_count[bh], has_hi);
+    }
+    // power-density correction * Sp of the two bands this lane stores (bark.py:132, 204), times the 1/4 of the packed
+    // power spectrum (exact: a power of two)
+    const float scale0 = tab->pow_dens[lane] * kPackedPowerScale;
+    const float scale1 = (lane + 32 < FSEM_PESQ_NBANDS) ? tab->pow_dens[lane + 32] * kPackedPowerScale : 0.f;
 
     // Work units = VALID (item, frame) pairs in item-major order; frame_prefix[i] = number of units before item i
     // (nullptr: every item has tmax frames).  Every warp owns a contiguous, equally long range of them, so ragged
@@ -544,40 +559,44 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
         // wait for the two halves of the current frame
         mbar_wait(bar0 + 8 * sa, (par >> sa) & 1u);
         mbar_wait(bar0 + 8 * sb, (par >> sb) & 1u);
-        const float* ac = sm.half_c[sa] + lane;
-        const float* ad = sm.half_d[sa] + lane;
-        const float* bc = sm.half_c[sb] + lane;
-        const float* bd = sm.half_d[sb] + lane;
+        // lane L owns samples 2L + h + 64 j of the frame: pairs (h = 0, 1) are one LDS.64; j < 4 lie in the first half
+        const float2* ac = reinterpret_cast<const float2*>(sm.half_c[sa]) + lane;
+        const float2* ad = reinterpret_cast<const float2*>(sm.half_d[sa]) + lane;
+        const float2* bc = reinterpret_cast<const float2*>(sm.half_c[sb]) + lane;
+        const float2* bd = reinterpret_cast<const float2*>(sm.half_d[sb]) + lane;
         float re[16], im[16];
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            re[m] = ac[32 * m] * win[m];
-            im[m] = ad[32 * m] * win[m];
-            re[m + 8] = bc[32 * m] * win[m + 8];
-            im[m + 8] = bd[32 * m] * win[m + 8];
+        for (int j = 0; j < 4; ++j) {
+            const float2 c0 = ac[32 * j], d0 = ad[32 * j], c1 = bc[32 * j], d1 = bd[32 * j];
+            re[j] = c0.x * win[j];             re[8 + j] = c0.y * win[8 + j];
+            im[j] = d0.x * win[j];             im[8 + j] = d0.y * win[8 + j];
+            re[4 + j] = c1.x * win[4 + j];     re[12 + j] = c1.y * win[12 + j];
+            im[4 + j] = d1.x * win[4 + j];     im[12 + j] = d1.y * win[12 + j];
         }
         if (f * FSEM_PESQ_HOP + FSEM_PESQ_NFFT > len) {          // warp-uniform, last frame(s) only:
-            const int room = len - (f * FSEM_PESQ_HOP + lane);   // zero padding beyond the signal (PESQ.py:128-130)
+            const int room = len - f * FSEM_PESQ_HOP;            // zero padding beyond the signal (PESQ.py:128-130)
 #pragma unroll
-            for (int m = 0; m < 16; ++m)
-                if (32 * m >= room) { re[m] = 0.f; im[m] = 0.f; }
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (fft_in_index(lane, h, j) >= room) { re[8 * h + j] = 0.f; im[8 * h + j] = 0.f; }
         }
         warp_fft512<false>(re, im, buf, tw, lane);
         float pc[8], pd[8];
         packed_power8(buf, lane, pc, pd);
         if (lane == 0) { pc[0] = 0.f; pd[0] = 0.f; }             // "we won't use energy feature" (PESQ.py:136)
-        band_sums8<4>(pc, pd, plan, lane, [&](int band, float sc, float sd) {
-            bands_c[band] = sc;
-            bands_d[band] = sd;
-        });
+        __syncwarp();                                            // every lane has read the spectrum: S may overwrite it
+        scan.scan_store(pc, pd, S, lane);
         __syncwarp();
         float* __restrict__ out_c = bark + (item * tmax + f) * FSEM_PESQ_NBANDS;
         float* __restrict__ out_d = bark + ((batch + item) * tmax + f) * FSEM_PESQ_NBANDS;
-        out_c[lane] = bands_c[lane] * scale0;
-        out_d[lane] = bands_d[lane] * scale0;
+        const float lo_c = g_lo.sum(S), lo_d = g_lo.sum(S + kBandSStride);
+        const float hi_c = g_hi.sum(S), hi_d = g_hi.sum(S + kBandSStride);     // all lanes: no divergence around the loads
+        out_c[lane] = lo_c * scale0;
+        out_d[lane] = lo_d * scale0;
         if (lane + 32 < FSEM_PESQ_NBANDS) {
-            out_c[lane + 32] = bands_c[lane + 32] * scale1;
-            out_d[lane + 32] = bands_d[lane + 32] * scale1;
+            out_c[lane + 32] = hi_c * scale1;
+            out_d[lane + 32] = hi_d * scale1;
         }
         if (!has_next) break;
         --remaining;

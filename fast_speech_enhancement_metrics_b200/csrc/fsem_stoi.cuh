@@ -387,6 +387,13 @@ stoi_prefix_kernel(const int32_t* __restrict__ kept_count, int64_t batch, int32_
 #endif
 constexpr int kTobWarps = FSEM_FFT_WARPS;
 
+// a third-octave band (at most 48 bins, checked by fsem_stoi_create) reaches back into at most 6 earlier lanes
+constexpr int kTobPieces = 6;
+static_assert(kBandSFloats <= 2 * kFftBufElems, "band scan rows alias the FFT exchange buffer");
+
+// kVec2: the 10 kHz rows are 8-byte aligned with an even pitch (always true for the workspace copy the resampler
+// writes), so a lane fetches its sample pairs (2L, 2L + 1) with one 64-bit load
+template <bool kVec2>
 __global__ void __launch_bounds__(kTobWarps * 32, FSEM_FFT_MINBLOCKS)
 stoi_tob_kernel(const float* __restrict__ clean10k, const float* __restrict__ deg10k, int64_t sstride,
                 int64_t batch, int t0max, int umax,
@@ -394,11 +401,10 @@ stoi_tob_kernel(const float* __restrict__ clean10k, const float* __restrict__ de
                 const StoiTables* __restrict__ tab, float* __restrict__ tob /* [2][batch][15][ustride] */) {
     __shared__ __align__(16) float2 s_buf[kTobWarps][kFftBufElems];
     __shared__ int32_t s_starts[FSEM_STOI_NBANDS + 2];
-    __shared__ float s_band[kTobWarps][64];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     float2* buf = s_buf[warp];
-    float* bands = s_band[warp];
+    float* S = reinterpret_cast<float*>(buf);
     // pseudo-bands: 0 = bins below the first band, 1..15 = the third-octave bands (contiguous), 16 = bins above
     if (threadIdx.x == 0) s_starts[0] = 0;
     if (threadIdx.x < FSEM_STOI_NBANDS) s_starts[1 + threadIdx.x] = tab->band_lo[threadIdx.x];
@@ -407,11 +413,19 @@ stoi_tob_kernel(const float* __restrict__ clean10k, const float* __restrict__ de
 
     FftTwiddles tw;
     tw.init(lane);
-    float win[8];
+    float win[8];                                            // win[4h + j] = w[2*lane + h + 64 j], j = 0..3
 #pragma unroll
-    for (int m = 0; m < 8; ++m) win[m] = tab->window[lane + 32 * m];
-    BandPlan plan;
-    plan.init(s_starts, FSEM_STOI_NBANDS + 2, lane);
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) win[4 * h + j] = tab->window[fft_in_index(lane, h, j)];
+    BandScan scan;
+    scan.init(s_starts, FSEM_STOI_NBANDS + 2, lane);
+    // lanes 0..14 gather the clean bands, lanes 16..30 the degraded ones
+    const int my_band = lane & 15;
+    const bool has_band = my_band < FSEM_STOI_NBANDS;
+    BandGather<kTobPieces> gather;
+    gather.init(s_starts[1 + (has_band ? my_band : 0)], s_starts[2 + (has_band ? my_band : 0)], has_band);
+    const float* Srow = S + (lane >> 4) * kBandSStride;
 
     // work = the REAL STFT frames of all items in (item, u) order; every warp takes an equal contiguous share
     const int64_t total = frame_prefix[batch];
@@ -434,35 +448,40 @@ stoi_tob_kernel(const float* __restrict__ clean10k, const float* __restrict__ de
         {
             const int32_t* idx = kept_idx + item * t0max + u;
             const int ta = idx[0] * FSEM_STOI_HOP, tb = idx[1] * FSEM_STOI_HOP, tc = idx[2] * FSEM_STOI_HOP;
-            const float* __restrict__ xc = clean10k + item * sstride + lane;
-            const float* __restrict__ xd = deg10k + item * sstride + lane;
+            const float* __restrict__ xc = clean10k + item * sstride + 2 * lane;
+            const float* __restrict__ xd = deg10k + item * sstride + 2 * lane;
+            auto pair = [&](const float* p) -> float2 {
+                if (kVec2) return __ldg(reinterpret_cast<const float2*>(p));
+                return make_float2(__ldg(p), __ldg(p + 1));
+            };
             float re[16], im[16];
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const int q = 32 * m;
+            for (int j = 0; j < 4; ++j) {
+                const int q = 64 * j;                        // this lane's samples q + 2L, q + 2L + 1 of the chunk
                 // neighbour frame: first half of the chunk overlaps the tail of frame u, second half the head of frame u+2
-                const int nb = (m < 4) ? (ta + q + 128) : (tc + q - 128);
-                const float wn = (m < 4) ? win[m + 4] : win[m - 4];
-                float c = __fadd_rn(__fmul_rn(win[m], __ldg(xc + tb + q)), __fmul_rn(wn, __ldg(xc + nb)));
-                float d = __fadd_rn(__fmul_rn(win[m], __ldg(xd + tb + q)), __fmul_rn(wn, __ldg(xd + nb)));
-                re[m] = __fmul_rn(win[m], c);
-                im[m] = __fmul_rn(win[m], d);
+                const int nb = (j < 2) ? (ta + q + 128) : (tc + q - 128);
+                const int jn = (j < 2) ? j + 2 : j - 2;      // window index of the neighbour's sample
+                const float2 c0 = pair(xc + tb + q), c1 = pair(xc + nb);
+                const float2 d0 = pair(xd + tb + q), d1 = pair(xd + nb);
+                const float w0f = win[j], w1f = win[4 + j], n0f = win[jn], n1f = win[4 + jn];
+                re[j] = __fmul_rn(w0f, __fadd_rn(__fmul_rn(w0f, c0.x), __fmul_rn(n0f, c1.x)));
+                re[8 + j] = __fmul_rn(w1f, __fadd_rn(__fmul_rn(w1f, c0.y), __fmul_rn(n1f, c1.y)));
+                im[j] = __fmul_rn(w0f, __fadd_rn(__fmul_rn(w0f, d0.x), __fmul_rn(n0f, d1.x)));
+                im[8 + j] = __fmul_rn(w1f, __fadd_rn(__fmul_rn(w1f, d0.y), __fmul_rn(n1f, d1.y)));
             }
 #pragma unroll
-            for (int m = 8; m < 16; ++m) { re[m] = 0.f; im[m] = 0.f; }
+            for (int j = 4; j < 8; ++j) { re[j] = 0.f; im[j] = 0.f; re[8 + j] = 0.f; im[8 + j] = 0.f; }
             warp_fft512<true>(re, im, buf, tw, lane);
             float pc[8], pd[8];
             packed_power8(buf, lane, pc, pd);
-            band_sums8<6>(pc, pd, plan, lane, [&](int pseudo, float sc, float sd) {
-                bands[pseudo] = sc;
-                bands[32 + pseudo] = sd;
-            });
+            __syncwarp();                                    // every lane has read the spectrum: S may overwrite it
+            scan.scan_store(pc, pd, S, lane);
             __syncwarp();
-            // lanes 0..14 store the clean bands, lanes 16..30 the degraded ones (pseudo-band = band + 1)
-            if ((lane & 15) < FSEM_STOI_NBANDS) {
+            const float band = gather.sum(Srow);
+            if (has_band) {
                 const int64_t sig = (lane >> 4) ? (batch + item) : item;
-                tob[(sig * FSEM_STOI_NBANDS + (lane & 15)) * (int64_t)ustride + u] =
-                    sqrtf(bands[(lane & 16) * 2 + (lane & 15) + 1]);     // STOI.py:123-125
+                // sqrt(sum / 4) = sqrt(sum) / 2 exactly (STOI.py:123-125; the packed power spectrum carries a factor 4)
+                tob[(sig * FSEM_STOI_NBANDS + my_band) * (int64_t)ustride + u] = 0.5f * sqrtf(band);
             }
             __syncwarp();
         }
