@@ -85,9 +85,10 @@ lsd_frames_kernel(const float* __restrict__ clean, const float* __restrict__ deg
                     re[8 * h + j] = ok ? __ldg(c + i) * win[8 * h + j] : 0.f;
                     im[8 * h + j] = ok ? __ldg(d + i) * win[8 * h + j] : 0.f;
                 }
-            warp_fft512<false>(re, im, buf, tw, lane);
+            float ar[8], ai[8], br[8], bi[8];
+            warp_fft512<false>(re, im, buf, tw, lane, ar, ai, br, bi);
             float pc[8], pd[8];
-            packed_power8(buf, lane, pc, pd);                    // 4x the power spectra
+            packed_power_regs(ar, ai, br, bi, lane, pc, pd);     // 4x the power of this lane's 8 bins below 256
             const float a = fabsf(alpha[item]);
             float acc = 0.f;
 #pragma unroll
@@ -96,10 +97,9 @@ lsd_frames_kernel(const float* __restrict__ clean, const float* __restrict__ deg
                 const float l = logf(pc[j] * kPackedPowerScale / (den * den) + kLsdEps);
                 acc = fmaf(l, l, acc);
             }
-            if (lane == 0) {                                     // Nyquist bin 256: C = Re Z[256], D = Im Z[256]
-                const float2 zn = buf[fft_out_index(256)];
-                const float den = fmaf(a, fabsf(zn.y), kLsdEps);
-                const float l = logf(zn.x * zn.x / (den * den) + kLsdEps);
+            if (lane == 0) {                                     // Nyquist bin 256 = A[4] of lane 0: C = Re Z, D = Im Z
+                const float den = fmaf(a, fabsf(ai[4]), kLsdEps);
+                const float l = logf(ar[4] * ar[4] / (den * den) + kLsdEps);
                 acc = fmaf(l, l, acc);
             }
             acc = warp_sum(acc);

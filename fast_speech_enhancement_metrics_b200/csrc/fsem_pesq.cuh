@@ -438,13 +438,13 @@ constexpr int kSpecWarps = FSEM_FFT_WARPS;
 // copies: frame f needs halves f and f+1, half f+2 is in flight while frame f is transformed, so the global-load
 // latency is off the critical path and every sample is fetched from L2/HBM once (frames overlap by 50 %).
 struct SpecWarpSmem {
-    float2 fft[kFftBufElems];          // 5120 B; after the power spectrum has been read it holds the band scan rows S
+    float2 fft[kFftBufElems];          // 6016 B: FFT exchanges, then the band stage's P and S rows
     float half_c[3][FSEM_PESQ_HOP];    // 3072 B
     float half_d[3][FSEM_PESQ_HOP];    // 3072 B
     unsigned long long bar[3];         //   24 B (+8 pad)
     unsigned long long pad_;
 };
-static_assert(kBandSFloats <= 2 * kFftBufElems, "band scan rows alias the FFT exchange buffer");
+static_assert(kBandBufFloats <= 2 * kFftBufElems, "band rows alias the FFT exchange buffer");
 // extra lanes a Bark band may reach back into: bands 0..31 (<= 4 bins at 16 kHz) at most one, bands 32..48 at most four
 // (fsem_pesq_create checks the design against these bounds)
 constexpr int kBarkPiecesLow = 1;
@@ -461,7 +461,8 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
     const int warp = threadIdx.x >> 5;
     SpecWarpSmem& sm = reinterpret_cast<SpecWarpSmem*>(s_raw)[warp];
     float2* buf = sm.fft;
-    float* S = reinterpret_cast<float*>(sm.fft);
+    float* wbuf = reinterpret_cast<float*>(sm.fft);
+    const float* S = wbuf + kBandSOffset;
     const uint32_t bar0 = smem_u32(&sm.bar[0]);
     const uint32_t hc0 = smem_u32(&sm.half_c[0][0]), hd0 = smem_u32(&sm.half_d[0][0]);
     constexpr uint32_t kHalfBytes = FSEM_PESQ_HOP * sizeof(float);
@@ -473,13 +474,19 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
 
     FftTwiddles tw;
     tw.init(lane);
-    float win[16];                                               // win[8h + j] = hann[2*lane + h + 64 j]
+    // First half of the periodic Hann window only: win[4h + j] = hann[2*lane + h + 64 j], j < 4.  The second half is
+    // hann[n + 256] = 1 - hann[n] (0.5 -+ 0.5 cos), applied as y - y * hann[n] with one FMA: eight registers fewer in a
+    // kernel that sits at the 128-register occupancy limit.  torch's float32 table deviates from this identity by at
+    // most 1.8e-7 (its own cosine rounding), three orders of magnitude below the float32 FFT's round-off.
+    float win[8];
 #pragma unroll
     for (int h = 0; h < 2; ++h)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) win[8 * h + j] = tab->hann[fft_in_index(lane, h, j)];
+        for (int j = 0; j < 4; ++j) win[4 * h + j] = tab->hann[fft_in_index(lane, h, j)];
+    FftLaneBins bins;
+    bins.init(lane);
     BandScan scan;
-    scan.init(tab->band_first, FSEM_PESQ_NBANDS, lane);
+    scan.init(tab->band_first, FSEM_PESQ_NBANDS, lane, bins);
     // this lane gathers Bark bands `lane` and `lane + 32`
     BandGather<kBarkPiecesLow> g_lo;
     BandGather<kBarkPiecesHigh> g_hi;
@@ -501,7 +508,7 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
     const int64_t nwarps = (int64_t)gridDim.x * kSpecWarps;
     const int64_t per = (units + nwarps - 1) / nwarps;
     const int64_t v0 = ((int64_t)blockIdx.x * kSpecWarps + warp) * per;
-    int64_t remaining = min(units, v0 + per) - v0;
+    int remaining = (int)(min(units, v0 + per) - v0);            // per-warp share: far below 2^31
     if (remaining <= 0) return;
     int64_t item;
     int f;
@@ -568,10 +575,10 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float2 c0 = ac[32 * j], d0 = ad[32 * j], c1 = bc[32 * j], d1 = bd[32 * j];
-            re[j] = c0.x * win[j];             re[8 + j] = c0.y * win[8 + j];
-            im[j] = d0.x * win[j];             im[8 + j] = d0.y * win[8 + j];
-            re[4 + j] = c1.x * win[4 + j];     re[12 + j] = c1.y * win[12 + j];
-            im[4 + j] = d1.x * win[4 + j];     im[12 + j] = d1.y * win[12 + j];
+            re[j] = c0.x * win[j];                    re[8 + j] = c0.y * win[4 + j];
+            im[j] = d0.x * win[j];                    im[8 + j] = d0.y * win[4 + j];
+            re[4 + j] = fmaf(-win[j], c1.x, c1.x);    re[12 + j] = fmaf(-win[4 + j], c1.y, c1.y);
+            im[4 + j] = fmaf(-win[j], d1.x, d1.x);    im[12 + j] = fmaf(-win[4 + j], d1.y, d1.y);
         }
         if (f * FSEM_PESQ_HOP + FSEM_PESQ_NFFT > len) {          // warp-uniform, last frame(s) only:
             const int room = len - f * FSEM_PESQ_HOP;            // zero padding beyond the signal (PESQ.py:128-130)
@@ -581,13 +588,12 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
                 for (int j = 0; j < 8; ++j)
                     if (fft_in_index(lane, h, j) >= room) { re[8 * h + j] = 0.f; im[8 * h + j] = 0.f; }
         }
-        warp_fft512<false>(re, im, buf, tw, lane);
+        float ar[8], ai[8], br[8], bi[8];
+        warp_fft512<false>(re, im, buf, tw, lane, ar, ai, br, bi);
         float pc[8], pd[8];
-        packed_power8(buf, lane, pc, pd);
-        if (lane == 0) { pc[0] = 0.f; pd[0] = 0.f; }             // "we won't use energy feature" (PESQ.py:136)
-        __syncwarp();                                            // every lane has read the spectrum: S may overwrite it
-        scan.scan_store(pc, pd, S, lane);
-        __syncwarp();
+        packed_power_regs(ar, ai, br, bi, lane, pc, pd);
+        if (lane == 0) { pc[0] = 0.f; pd[0] = 0.f; }             // bin 0: "we won't use energy feature" (PESQ.py:136)
+        scan.scan_store(pc, pd, wbuf, lane);
         float* __restrict__ out_c = bark + (item * tmax + f) * FSEM_PESQ_NBANDS;
         float* __restrict__ out_d = bark + ((batch + item) * tmax + f) * FSEM_PESQ_NBANDS;
         const float lo_c = g_lo.sum(S), lo_d = g_lo.sum(S + kBandSStride);

@@ -389,7 +389,7 @@ constexpr int kTobWarps = FSEM_FFT_WARPS;
 
 // a third-octave band (at most 48 bins, checked by fsem_stoi_create) reaches back into at most 6 earlier lanes
 constexpr int kTobPieces = 6;
-static_assert(kBandSFloats <= 2 * kFftBufElems, "band scan rows alias the FFT exchange buffer");
+static_assert(kBandBufFloats <= 2 * kFftBufElems, "band rows alias the FFT exchange buffer");
 
 // kVec2: the 10 kHz rows are 8-byte aligned with an even pitch (always true for the workspace copy the resampler
 // writes), so a lane fetches its sample pairs (2L, 2L + 1) with one 64-bit load
@@ -404,7 +404,7 @@ stoi_tob_kernel(const float* __restrict__ clean10k, const float* __restrict__ de
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     float2* buf = s_buf[warp];
-    float* S = reinterpret_cast<float*>(buf);
+    float* wbuf = reinterpret_cast<float*>(buf);
     // pseudo-bands: 0 = bins below the first band, 1..15 = the third-octave bands (contiguous), 16 = bins above
     if (threadIdx.x == 0) s_starts[0] = 0;
     if (threadIdx.x < FSEM_STOI_NBANDS) s_starts[1 + threadIdx.x] = tab->band_lo[threadIdx.x];
@@ -418,14 +418,16 @@ stoi_tob_kernel(const float* __restrict__ clean10k, const float* __restrict__ de
     for (int h = 0; h < 2; ++h)
 #pragma unroll
         for (int j = 0; j < 4; ++j) win[4 * h + j] = tab->window[fft_in_index(lane, h, j)];
+    FftLaneBins bins;
+    bins.init(lane);
     BandScan scan;
-    scan.init(s_starts, FSEM_STOI_NBANDS + 2, lane);
+    scan.init(s_starts, FSEM_STOI_NBANDS + 2, lane, bins);
     // lanes 0..14 gather the clean bands, lanes 16..30 the degraded ones
     const int my_band = lane & 15;
     const bool has_band = my_band < FSEM_STOI_NBANDS;
     BandGather<kTobPieces> gather;
     gather.init(s_starts[1 + (has_band ? my_band : 0)], s_starts[2 + (has_band ? my_band : 0)], has_band);
-    const float* Srow = S + (lane >> 4) * kBandSStride;
+    const float* Srow = wbuf + kBandSOffset + (lane >> 4) * kBandSStride;
 
     // work = the REAL STFT frames of all items in (item, u) order; every warp takes an equal contiguous share
     const int64_t total = frame_prefix[batch];
@@ -471,12 +473,11 @@ stoi_tob_kernel(const float* __restrict__ clean10k, const float* __restrict__ de
             }
 #pragma unroll
             for (int j = 4; j < 8; ++j) { re[j] = 0.f; im[j] = 0.f; re[8 + j] = 0.f; im[8 + j] = 0.f; }
-            warp_fft512<true>(re, im, buf, tw, lane);
+            float ar[8], ai[8], br[8], bi[8];
+            warp_fft512<true>(re, im, buf, tw, lane, ar, ai, br, bi);
             float pc[8], pd[8];
-            packed_power8(buf, lane, pc, pd);
-            __syncwarp();                                    // every lane has read the spectrum: S may overwrite it
-            scan.scan_store(pc, pd, S, lane);
-            __syncwarp();
+            packed_power_regs(ar, ai, br, bi, lane, pc, pd);
+            scan.scan_store(pc, pd, wbuf, lane);
             const float band = gather.sum(Srow);
             if (has_band) {
                 const int64_t sig = (lane >> 4) ? (batch + item) : item;
