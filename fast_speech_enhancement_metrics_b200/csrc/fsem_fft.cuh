@@ -123,8 +123,8 @@ __device__ __forceinline__ int fft_in_index(int lane, int h, int j) { return 2 *
 // is (8 - k0, 7 - k1, 7 - k2) for k0 != 0 and (0, 8 - k1, 7 - k2) for k0 = 0, k1 != 0, so
 //   * pass 2 lane (n0 = lane & 7, j = lane >> 3) owns the k0 PAIR {j, 8 - j} (j = 0: {0, 4}),
 //   * pass 3 lane (r = lane & 7, j) owns the sequence pair (k0, k1) = (j, r), (8 - j, 7 - r); for j = 0 the pairs are
-//     (0, r), (0, 8 - r) [r = 1..3], (0, 0), (0, 4) [r = 0] and (4, r), (4, 7 - r) [r = 4..7] -- lanes 0..7 replace
-//     one element of every stored float4 with a select so that the stores are the same instruction for all lanes.
+//     (0, r), (0, 8 - r) [r = 1..3], (0, 0), (0, 4) [r = 0] and (4, 7 - r), (4, r) [r = 4..7] -- lanes 0..7 replace
+//     elements of the stored float4s with selects so that the stores are the same instruction for all lanes.
 // Exchange layouts (all accesses 128-bit, conflict-free per quarter-warp -- checked by emulation and with ncu):
 //   1: row n' = 2L + h at float4 9 L + 4 h; float4 q of a row = (a[n', k0 = q], a[n', k0 = (8 - q) or 4])
 //   2: float4 j * 72 + r * 9 + n0 = (b[n0; A-sequence of reader (r, j)], b[n0; B-sequence])
@@ -136,7 +136,7 @@ struct FftLaneBins {
         if (j >= 1) { base_a = j + 8 * r; base_b = (8 - j) + 8 * (7 - r); }
         else if (r == 0) { base_a = 0; base_b = 32; }
         else if (r < 4) { base_a = 8 * r; base_b = 8 * (8 - r); }
-        else { base_a = 4 + 8 * r; base_b = 4 + 8 * (7 - r); }
+        else { base_a = 4 + 8 * (7 - r); base_b = 4 + 8 * r; }
     }
 };
 
@@ -182,7 +182,7 @@ __device__ __forceinline__ void warp_fft512(float (&re)[16], float (&im)[16], fl
     {
         // r2[0][k1] = b[k1; k0 = j], r2[1][k1] = b[k1; k0 = 8 - j] (j = 0: k0 = 0 and 4).  Reader (r, j) wants
         // (b[r; j], b[7 - r; 8 - j]) = (r2[0][r], r2[1][7 - r]); group 0 pairs within one k0 (see above): one element of
-        // every float4 of lanes 0..7 is replaced with a select (16 selects).
+        // every float4 r < 4 and both of every float4 r >= 4 of lanes 0..7 are replaced with selects (24 selects).
         const bool g0 = jq == 0;
         float4* dst = buf4 + jq * 72 + lo3;
         // float4 r < 4: (b[r; j], mirror) -- group 0 takes the mirror (0, 8 - r) [r = 0: (0, 4)] from its own first sequence
@@ -190,10 +190,12 @@ __device__ __forceinline__ void warp_fft512(float (&re)[16], float (&im)[16], fl
         dst[9] = make_float4(r2[0][1], i2[0][1], g0 ? r2[0][7] : r2[1][6], g0 ? i2[0][7] : i2[1][6]);
         dst[18] = make_float4(r2[0][2], i2[0][2], g0 ? r2[0][6] : r2[1][5], g0 ? i2[0][6] : i2[1][5]);
         dst[27] = make_float4(r2[0][3], i2[0][3], g0 ? r2[0][5] : r2[1][4], g0 ? i2[0][5] : i2[1][4]);
-        // float4 r >= 4: (b[r; j], b[7 - r; 8 - j]) -- group 0 replaces the first by (4, r), the mirror of (4, 7 - r)
+        // float4 r >= 4: (b[r; j], b[7 - r; 8 - j]) -- group 0 stores ((4, 7 - r), (4, r)): this order keeps the scattered
+        // power stores of the band stage bank-conflict-free (bins 4 + 8 (7 - r) = 28, 20, 12, 4 in the A slot)
 #pragma unroll
         for (int r = 4; r < 8; ++r)
-            dst[9 * r] = make_float4(g0 ? r2[1][r] : r2[0][r], g0 ? i2[1][r] : i2[0][r], r2[1][7 - r], i2[1][7 - r]);
+            dst[9 * r] = make_float4(g0 ? r2[1][7 - r] : r2[0][r], g0 ? i2[1][7 - r] : i2[0][r],
+                                     g0 ? r2[1][r] : r2[1][7 - r], g0 ? i2[1][r] : i2[1][7 - r]);
     }
     __syncwarp();
     // ---- pass 3: radix-8 over n0 for the two sequences of reader (r = lane & 7, j)

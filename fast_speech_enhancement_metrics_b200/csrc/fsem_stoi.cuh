@@ -202,26 +202,66 @@ stoi_resample85_kernel(const float* __restrict__ clean, const float* __restrict_
             }
         }
         if (is_clean) {
-            // hop energies: warp w takes hops w, w+4, ... of this tile; lane handles 4 samples of the hop
+            // hop energies: warp w takes hops w, w + 4, w + 8 of this tile; a lane handles 4 samples of every hop and holds
+            // up to kV = 2 * 3 fp64 partial sums (A and B of three hops).  They are reduced over the 32 lanes by a
+            // reduce-scatter (every step halves the number of sums a lane is responsible for) instead of one butterfly
+            // per sum: 8 fp64 shuffles per warp instead of 30 -- shuffles share the LSU data pipe this kernel is bound by.
             const int lane = tid & 31, warp = tid >> 5;
             const float4 wa = *reinterpret_cast<const float4*>(s_win + 4 * lane);
             const float4 wb = *reinterpret_cast<const float4*>(s_win + 128 + 4 * lane);
-            for (int h = warp; h < kRs85Hops; h += kRs85Threads / 32) {
-                if ((int64_t)(h + 1) * FSEM_STOI_HOP > valid) break;               // only complete hops matter
-                const float4 v = *reinterpret_cast<const float4*>(s_out + h * FSEM_STOI_HOP + 4 * lane);
+            constexpr int kWarps = kRs85Threads / 32;
+            constexpr int kHopsPerWarp = (kRs85Hops + kWarps - 1) / kWarps;        // 3
+            static_assert(kHopsPerWarp == 3, "the reduce-scatter below is written for three hops (six sums) per warp");
+            double v[6];
+#pragma unroll
+            for (int i = 0; i < kHopsPerWarp; ++i) {
+                const int h = warp + kWarps * i;
                 double a = 0.0, b = 0.0;
-                float f;
-                f = __fmul_rn(v.x, wa.x); a = fma((double)f, (double)f, a);
-                f = __fmul_rn(v.y, wa.y); a = fma((double)f, (double)f, a);
-                f = __fmul_rn(v.z, wa.z); a = fma((double)f, (double)f, a);
-                f = __fmul_rn(v.w, wa.w); a = fma((double)f, (double)f, a);
-                f = __fmul_rn(v.x, wb.x); b = fma((double)f, (double)f, b);
-                f = __fmul_rn(v.y, wb.y); b = fma((double)f, (double)f, b);
-                f = __fmul_rn(v.z, wb.z); b = fma((double)f, (double)f, b);
-                f = __fmul_rn(v.w, wb.w); b = fma((double)f, (double)f, b);
-                a = warp_sum(a);
-                b = warp_sum(b);
-                if (lane == 0) hop_energy[item * hops_max + tile * kRs85Hops + h] = make_double2(a, b);
+                if (h < kRs85Hops && (int64_t)(h + 1) * FSEM_STOI_HOP <= valid) {      // only complete hops matter (warp-uniform)
+                    const float4 x = *reinterpret_cast<const float4*>(s_out + h * FSEM_STOI_HOP + 4 * lane);
+                    float f;
+                    f = __fmul_rn(x.x, wa.x); a = fma((double)f, (double)f, a);
+                    f = __fmul_rn(x.y, wa.y); a = fma((double)f, (double)f, a);
+                    f = __fmul_rn(x.z, wa.z); a = fma((double)f, (double)f, a);
+                    f = __fmul_rn(x.w, wa.w); a = fma((double)f, (double)f, a);
+                    f = __fmul_rn(x.x, wb.x); b = fma((double)f, (double)f, b);
+                    f = __fmul_rn(x.y, wb.y); b = fma((double)f, (double)f, b);
+                    f = __fmul_rn(x.z, wb.z); b = fma((double)f, (double)f, b);
+                    f = __fmul_rn(x.w, wb.w); b = fma((double)f, (double)f, b);
+                }
+                v[2 * i] = a; v[2 * i + 1] = b;
+            }
+            // step 16: lanes with bit 4 clear keep sums 0..2, the others 3..5
+            const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
+            double u[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const double send = b16 ? v[i] : v[3 + i], keep = b16 ? v[3 + i] : v[i];
+                u[i] = keep + __shfl_xor_sync(kFull, send, 16);
+            }
+            // step 8: bit 3 clear keeps u[0], u[1]; set keeps u[2] (and a zero)
+            double t2[2];
+            {
+                const double s0 = b8 ? u[0] : u[2], k0 = b8 ? u[2] : u[0];
+                const double s1 = b8 ? u[1] : 0.0, k1 = b8 ? 0.0 : u[1];
+                t2[0] = k0 + __shfl_xor_sync(kFull, s0, 8);
+                t2[1] = k1 + __shfl_xor_sync(kFull, s1, 8);
+            }
+            // step 4: bit 2 clear keeps t2[0], set keeps t2[1]
+            double one;
+            {
+                const double send = b4 ? t2[0] : t2[1], keep = b4 ? t2[1] : t2[0];
+                one = keep + __shfl_xor_sync(kFull, send, 4);
+            }
+            one += __shfl_xor_sync(kFull, one, 2);
+            one += __shfl_xor_sync(kFull, one, 1);
+            // lane (b16, b8, b4) now holds the total of sum index (b16 ? 3 : 0) + (b8 ? 2 : (b4 ? 1 : 0)); b8 && b4 is the zero
+            const int local = b8 ? 2 : (b4 ? 1 : 0);
+            const int sum_idx = (b16 ? 3 : 0) + local;
+            const int h = warp + kWarps * (sum_idx >> 1);
+            if ((lane & 3) == 0 && !(b8 && b4) && h < kRs85Hops && (int64_t)(h + 1) * FSEM_STOI_HOP <= valid) {
+                double* dst = reinterpret_cast<double*>(hop_energy + item * hops_max + tile * kRs85Hops + h);
+                dst[sum_idx & 1] = one;                                           // .x = A_h, .y = B_h
             }
         }
         __syncthreads();
