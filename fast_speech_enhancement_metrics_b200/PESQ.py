@@ -40,7 +40,8 @@ class PESQ(BaseMetric):
     # ------------------------------------------------------------------
     def score_tensors(self, clean: torch.Tensor, deg: torch.Tensor, lengths=None):
         """Device-resident scoring: returns (mos[B] f32, status[B] i32) CUDA tensors, stream-ordered,
-        no host synchronisation.  `clean`/`deg` are [B, n] float32 CUDA tensors."""
+        no host synchronisation.  `clean`/`deg` are [B, n] float32 / int16 / float16 CUDA tensors (the IIR pass reads
+        them in their own dtype: fsem_pesq_score)."""
         clean, deg = self._on_device(clean), self._on_device(deg)
         b, n = clean.shape
         lens = self._lengths_tensor(lengths, b, n, clean.device)
@@ -54,9 +55,9 @@ class PESQ(BaseMetric):
             if deg.stride(0) != clean.stride(0) and b > 1:
                 deg = deg.contiguous(); clean = clean.contiguous()
                 batch.clean, batch.deg, batch.stride = clean.data_ptr(), deg.data_ptr(), n
-            self._check_score(self._lib.fsem_pesq_score_f32(
-                self._ctx, C.byref(batch), mos.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(),
-                C.c_void_p(torch.cuda.current_stream(clean.device).cuda_stream)))
+            self._check_score(self._lib.fsem_pesq_score(
+                self._ctx, C.byref(batch), _lib.dtype_code(clean.dtype), mos.data_ptr(), status.data_ptr(), ws.data_ptr(),
+                ws.numel(), C.c_void_p(torch.cuda.current_stream(clean.device).cuda_stream)))
         self._last_shape = (b, n)
         return mos, status
 

@@ -25,7 +25,7 @@ class SDR(BaseMetric):
 
     def score_tensors(self, clean: torch.Tensor, deg: torch.Tensor, lengths=None) -> torch.Tensor:
         """[B, n] float32 CUDA tensors -> sdr[B] (dB) CUDA tensor, stream-ordered, no host synchronisation."""
-        clean, deg = self._on_device(clean), self._on_device(deg)
+        clean, deg = self._as_f32(self._on_device(clean)), self._as_f32(self._on_device(deg))
         b, n = clean.shape
         lens = self._lengths_tensor(lengths, b, n, clean.device)
         clean, deg, lens = self._resample_pair(clean, deg, lens)             # base.py:19-20

@@ -55,8 +55,8 @@ class STOI(BaseMetric):
                 deg = deg.contiguous(); clean = clean.contiguous()
             batch = _lib.Batch(clean.data_ptr(), deg.data_ptr(), lens.data_ptr() if lens is not None else None,
                                b, n, clean.stride(0) if b > 1 else max(n, clean.stride(0)))
-            _lib.check(self._lib.fsem_stoi_score_f32(
-                self._ctx, C.byref(batch), scores[0].data_ptr(), scores[1].data_ptr(), kept.data_ptr(),
+            _lib.check(self._lib.fsem_stoi_score(
+                self._ctx, C.byref(batch), _lib.dtype_code(clean.dtype), scores[0].data_ptr(), scores[1].data_ptr(), kept.data_ptr(),
                 status.data_ptr(), ws.data_ptr(), ws.numel(),
                 C.c_void_p(torch.cuda.current_stream(clean.device).cuda_stream)))
         self._last_shape = (b, n)

@@ -32,7 +32,7 @@ EXPORTS = [
     "fsem_pesq_stoi_score_f32", "fsem_lsd_create", "fsem_lsd_destroy", "fsem_lsd_workspace_bytes", "fsem_lsd_score_f32",
     "fsem_sdr_workspace_bytes", "fsem_sdr_score_f32", "fsem_ingest_f32", "fsem_score_host",
     "fsem_stoi_mask_margin", "fsem_resampler_create", "fsem_resampler_destroy", "fsem_resampled_len",
-    "fsem_resample_f32",
+    "fsem_resample_f32", "fsem_pesq_score", "fsem_stoi_score", "fsem_pesq_stoi_score",
 ]
 
 # ingest formats (include/fsem.h FSEM_DTYPE_*)
@@ -97,6 +97,10 @@ def load() -> C.CDLL:
     lib.fsem_pesq_stoi_score_host_f32.argtypes = [vp, vp, C.POINTER(Batch), fp, i32p, fp, fp, i32p, i32p]
     lib.fsem_pesq_stoi_score_f32.argtypes = [vp, vp, C.POINTER(Batch), fp, i32p, fp, fp, i32p, i32p, vp, C.c_size_t, vp,
                                              C.c_size_t, vp]
+    lib.fsem_pesq_score.argtypes = [vp, C.POINTER(Batch), C.c_int, fp, i32p, vp, C.c_size_t, vp]
+    lib.fsem_stoi_score.argtypes = [vp, C.POINTER(Batch), C.c_int, fp, fp, i32p, i32p, vp, C.c_size_t, vp]
+    lib.fsem_pesq_stoi_score.argtypes = [vp, vp, C.POINTER(Batch), C.c_int, fp, i32p, fp, fp, i32p, i32p, vp, C.c_size_t,
+                                         vp, C.c_size_t, vp]
     lib.fsem_stoi_mask_margin.argtypes = [vp, i64, i64, i32p, vp, fp, vp]
     lib.fsem_resampler_create.argtypes = [C.POINTER(vp), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           C.POINTER(C.c_float)]

@@ -45,19 +45,22 @@ class BaseMetric(ABC):
     # ------------------------------------------------------------------ reference API
     def prepare_audio(self, audio: torch.Tensor) -> torch.Tensor:
         """base.py:16-21: at least 2-D, unit stride along time.  The tensor stays where it is (no
-        implicit device move); inputs are never modified.  float32 is consumed in place; int16 / float16
-        CUDA tensors are widened to a float32 copy here (fsem_ingest_f32), CPU ones keep their dtype and
-        are widened by the library after the upload."""
+        implicit device move for CPU tensors); inputs are never modified and keep their dtype: float32, int16 PCM and
+        float16 rows are all consumed in place by the first kernel of the metric."""
         audio = torch.atleast_2d(audio)
         if audio.dim() != 2:
             raise Exception("expected a [batch, samples] tensor")
-        code = _lib.dtype_code(audio.dtype)           # raises for float64 & co like the reference
+        _lib.dtype_code(audio.dtype)                  # raises for float64 & co like the reference
         if audio.stride(1) != 1 or (audio.shape[0] > 1 and audio.stride(0) < audio.shape[1]):
             audio = audio.contiguous()
-        audio = self._on_device(audio)
-        if code != _lib.DTYPE_F32 and audio.is_cuda:
-            audio = self._ingest(audio, code)
-        return audio
+        return self._on_device(audio)
+
+    def _as_f32(self, audio: torch.Tensor) -> torch.Tensor:
+        """float32 CUDA rows for the kernels that only read float32 (LSD, SDR, the general resampler building block):
+        int16 / float16 CUDA tensors are widened with fsem_ingest_f32.  PESQ and STOI do not need this: their first
+        kernels read int16 / float16 rows directly (fsem_pesq_score / fsem_stoi_score)."""
+        code = _lib.dtype_code(audio.dtype)
+        return audio if code == _lib.DTYPE_F32 else self._ingest(audio, code)
 
     def _on_device(self, audio: torch.Tensor) -> torch.Tensor:
         """The context tables, resampler taps and workspace of a metric live on the device that was current at
@@ -150,9 +153,7 @@ class BaseMetric(ABC):
         PCIe as they are and are widened on the device."""
         clean = clean.to(self.device, non_blocking=True)
         deg = deg.to(self.device, non_blocking=True)
-        if clean.dtype != torch.float32:
-            clean, deg = self.prepare_audio(clean), self.prepare_audio(deg)
-        return clean, deg
+        return self._as_f32(clean), self._as_f32(deg)
 
     # ------------------------------------------------------------------ helpers
     def _get_workspace(self, nbytes: int) -> torch.Tensor:

@@ -167,6 +167,27 @@ int64_t host_chunk_items(int64_t batch, int64_t n) {
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+// rows of `es`-byte samples that the kernels may read four samples at a time
+bool rows_vec4(const void* a, const void* b, int64_t stride, size_t es) {
+    const uintptr_t m = 4 * es - 1;
+    return (reinterpret_cast<uintptr_t>(a) & m) == 0 && (reinterpret_cast<uintptr_t>(b) & m) == 0 && stride % 4 == 0;
+}
+size_t dtype_size(int dtype) {
+    return dtype == FSEM_DTYPE_F32 ? sizeof(float) : (dtype == FSEM_DTYPE_I16 || dtype == FSEM_DTYPE_F16) ? 2 : 0;
+}
+// run `fn(T{})` with T = the sample type of `dtype`
+int launch_ingest(const void* src, int dtype, int64_t rows, int64_t n, int64_t sstride, float* dst, int64_t dstride,
+                  cudaStream_t stream);
+
+template <typename F>
+int dispatch_dtype(int dtype, F&& fn) {
+    switch (dtype) {
+        case FSEM_DTYPE_F32: return fn(float{});
+        case FSEM_DTYPE_I16: return fn(int16_t{});
+        case FSEM_DTYPE_F16: return fn(__half{});
+        default: return FSEM_E_INVALID;
+    }
+}
 
 }  // namespace
 
@@ -356,7 +377,7 @@ extern "C" int fsem_pesq_create(fsem_pesq_ctx_t** out, const fsem_pesq_design_t*
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pesq_spectrum_kernel, kSpecWarps * 32, kSpecDynSmem) == cudaSuccess && occ > 0)
         ctx->spec_ctas_per_sm = occ;
     occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pesq_filter_tiled_kernel<false>, kFiltWarps * 32, 0) == cudaSuccess && occ > 0)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pesq_filter_tiled_kernel<false, float>, kFiltWarps * 32, 0) == cudaSuccess && occ > 0)
         ctx->filt_ctas_per_sm = occ;
     *out = ctx;
     return FSEM_OK;
@@ -379,7 +400,16 @@ extern "C" size_t fsem_pesq_workspace_bytes(const fsem_pesq_ctx_t* ctx, int64_t 
 extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in, float* mos_out,
                                    int32_t* status_out, void* workspace, size_t workspace_bytes,
                                    void* stream_v) {
+    return fsem_pesq_score(ctx, in, FSEM_DTYPE_F32, mos_out, status_out, workspace, workspace_bytes, stream_v);
+}
+
+// Any ingest dtype: the first kernel (IIR pass, or the resampler when the context resamples on ingest) reads the rows
+// as they are; `in->clean` / `in->deg` point at rows of `dtype`, `in->stride` counts elements.
+extern "C" int fsem_pesq_score(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in, int dtype, float* mos_out,
+                               int32_t* status_out, void* workspace, size_t workspace_bytes, void* stream_v) {
     if (!ctx || !in || !mos_out) return fail(FSEM_E_INVALID, "fsem_pesq_score_f32: null argument");
+    const size_t es = dtype_size(dtype);
+    if (es == 0) return fail(FSEM_E_INVALID, "fsem_pesq_score: unknown dtype %d", dtype);
     if (in->batch < 0 || in->n < 0 || in->stride < in->n)
         return fail(FSEM_E_INVALID, "fsem_pesq_score_f32: bad shape batch=%lld n=%lld stride=%lld",
                     (long long)in->batch, (long long)in->n, (long long)in->stride);
@@ -410,9 +440,13 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
         if (bps * 2 * in->batch >= (int64_t(1) << 31))
             return fail(FSEM_E_INVALID, "fsem_pesq_score_f32: batch x samples too large for one launch; split the batch");
         { ProfScope prof_(K_PESQ_RESAMPLE, stream);
-          stoi_resample_kernel<<<(unsigned)(bps * 2 * in->batch), 256, 0, stream>>>(
-              in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, ctx->d_rs_taps, ctx->rs_orig, ctx->rs_neu,
-              ctx->rs_width, ctx->rs_ntaps, y, p.rstride, (int)bps); }
+          dispatch_dtype(dtype, [&](auto tag) {
+              using T = decltype(tag);
+              stoi_resample_kernel<T><<<(unsigned)(bps * 2 * in->batch), 256, 0, stream>>>(
+                  reinterpret_cast<const T*>(in->clean), reinterpret_cast<const T*>(in->deg), in->lengths, in->batch, in->n,
+                  in->stride, ctx->d_rs_taps, ctx->rs_orig, ctx->rs_neu, ctx->rs_width, ctx->rs_ntaps, y, p.rstride, (int)bps);
+              return FSEM_OK;
+          }); }
         FSEM_LAUNCHED();
         if (in->lengths) {
             resampled_lengths_kernel<<<(unsigned)ceil_div(in->batch, 256), 256, 0, stream>>>(
@@ -421,6 +455,7 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
         }
         rs_batch = fsem_batch_t{y, y + in->batch * p.rstride, in->lengths ? rslen : nullptr, in->batch, p.n, p.rstride};
         in = &rs_batch;
+        dtype = FSEM_DTYPE_F32;                                   // the rest of the chain reads the resampled fp32 rows
     }
 
     // variable-length batches: length-sorted item order (IIR warps of similar signals, longest Bark CTAs first) and
@@ -433,35 +468,40 @@ extern "C" int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in,
         pesq_order_kernel<<<1, kOrderThreads, 0, stream>>>(in->lengths, in->batch, in->n, order, fprefix);
         FSEM_LAUNCHED();
     }
-    {   // kernel A
-        const bool vec4 = aligned16(in->clean) && aligned16(in->deg) && (in->stride % 4 == 0);
-        if (vec4 && p.tiled) {
-            const int64_t units = 2 * ceil_div(in->batch, 32) * p.nchunks;
-            const unsigned grid = (unsigned)ceil_div(units, kFiltWarps);
-            { ProfScope prof_(K_PESQ_FILTER, stream);
-              if (in->lengths)
-                  pesq_filter_tiled_kernel<true><<<grid, kFiltWarps * 32, 0, stream>>>(
-                      in->clean, in->deg, in->lengths, order, in->batch, in->n, in->stride, p.chunk, p.nchunks,
-                      ctx->warm, ctx->coef, z, p.zstride, partial);
-              else
-                  pesq_filter_tiled_kernel<false><<<grid, kFiltWarps * 32, 0, stream>>>(
-                      in->clean, in->deg, nullptr, nullptr, in->batch, in->n, in->stride, p.chunk, p.nchunks,
-                      ctx->warm, ctx->coef, z, p.zstride, partial); }
-        } else {
-            const int64_t threads = 2 * in->batch * p.nchunks;
-            const unsigned grid = (unsigned)ceil_div(threads, 128);
-            { ProfScope prof_(K_PESQ_FILTER, stream);
-              if (vec4)
-                  pesq_filter_kernel<true><<<grid, 128, 0, stream>>>(
-                      in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, p.chunk, p.nchunks, ctx->warm,
-                      ctx->coef, z, p.zstride, partial);
-              else
-                  pesq_filter_kernel<false><<<grid, 128, 0, stream>>>(
-                      in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, p.chunk, p.nchunks, ctx->warm,
-                      ctx->coef, z, p.zstride, partial); }
-        }
-        FSEM_LAUNCHED();
+    {   // kernel A: reads the rows in their own dtype (float32, int16 PCM, fp16)
+        const bool vec4 = rows_vec4(in->clean, in->deg, in->stride, dtype_size(dtype));
+        ProfScope prof_(K_PESQ_FILTER, stream);
+        dispatch_dtype(dtype, [&](auto tag) {
+            using T = decltype(tag);
+            const T* c = reinterpret_cast<const T*>(in->clean);
+            const T* d = reinterpret_cast<const T*>(in->deg);
+            if (vec4 && p.tiled) {
+                const int64_t units = 2 * ceil_div(in->batch, 32) * p.nchunks;
+                const unsigned grid = (unsigned)ceil_div(units, kFiltWarps);
+                if (in->lengths)
+                    pesq_filter_tiled_kernel<true, T><<<grid, kFiltWarps * 32, 0, stream>>>(
+                        c, d, in->lengths, order, in->batch, in->n, in->stride, p.chunk, p.nchunks, ctx->warm, ctx->coef, z,
+                        p.zstride, partial);
+                else
+                    pesq_filter_tiled_kernel<false, T><<<grid, kFiltWarps * 32, 0, stream>>>(
+                        c, d, nullptr, nullptr, in->batch, in->n, in->stride, p.chunk, p.nchunks, ctx->warm, ctx->coef, z,
+                        p.zstride, partial);
+            } else {
+                const int64_t threads = 2 * in->batch * p.nchunks;
+                const unsigned grid = (unsigned)ceil_div(threads, 128);
+                if (vec4)
+                    pesq_filter_kernel<true, T><<<grid, 128, 0, stream>>>(
+                        c, d, in->lengths, in->batch, in->n, in->stride, p.chunk, p.nchunks, ctx->warm, ctx->coef, z,
+                        p.zstride, partial);
+                else
+                    pesq_filter_kernel<false, T><<<grid, 128, 0, stream>>>(
+                        c, d, in->lengths, in->batch, in->n, in->stride, p.chunk, p.nchunks, ctx->warm, ctx->coef, z,
+                        p.zstride, partial);
+            }
+            return FSEM_OK;
+        });
     }
+    FSEM_LAUNCHED();
     {   // kernel B
         const int64_t units = in->batch * (int64_t)p.tmax;
         int64_t grid = ceil_div(units, kSpecWarps);
@@ -548,7 +588,8 @@ StoiPlan stoi_plan(const fsem_stoi_ctx* ctx, int64_t batch, int64_t n) {
     p.hops_max = (int)(ceil_div(p.lmax > 0 ? p.lmax : 1, kRs85TileOut) * kRs85Hops);
     size_t off = 0;
     p.off_hops = off;    off = align256(off + (p.fused_energy ? sizeof(double2) * batch * p.hops_max : 0));
-    p.off_y = off;       off = align256(off + (p.resample ? sizeof(float) * 2 * batch * p.ystride : 0));
+    // the 10 kHz float32 signals: written by the resampler, or by the widening copy of 10 kHz int16 / fp16 input
+    p.off_y = off;       off = align256(off + sizeof(float) * 2 * batch * p.ystride);
     p.off_energy = off;  off = align256(off + sizeof(float) * batch * p.t0max);
     p.off_idx = off;     off = align256(off + sizeof(int32_t) * batch * p.t0max);
     p.off_count = off;   off = align256(off + sizeof(int32_t) * batch);
@@ -631,7 +672,17 @@ extern "C" size_t fsem_stoi_workspace_bytes(const fsem_stoi_ctx_t* ctx, int64_t 
 extern "C" int fsem_stoi_score_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t* in, float* stoi_out,
                                    float* estoi_out, int32_t* kept_frames_out, int32_t* status_out,
                                    void* workspace, size_t workspace_bytes, void* stream_v) {
+    return fsem_stoi_score(ctx, in, FSEM_DTYPE_F32, stoi_out, estoi_out, kept_frames_out, status_out, workspace,
+                           workspace_bytes, stream_v);
+}
+
+// Any ingest dtype: the resampler (the first kernel whenever the input is not already 10 kHz) reads the rows as they
+// are; 10 kHz int16 / fp16 rows are widened into the workspace first (the frame kernels read float32).
+extern "C" int fsem_stoi_score(fsem_stoi_ctx_t* ctx, const fsem_batch_t* in, int dtype, float* stoi_out,
+                               float* estoi_out, int32_t* kept_frames_out, int32_t* status_out,
+                               void* workspace, size_t workspace_bytes, void* stream_v) {
     if (!ctx || !in || !stoi_out || !estoi_out) return fail(FSEM_E_INVALID, "fsem_stoi_score_f32: null argument");
+    if (dtype_size(dtype) == 0) return fail(FSEM_E_INVALID, "fsem_stoi_score: unknown dtype %d", dtype);
     if (in->batch < 0 || in->n < 0 || in->stride < in->n)
         return fail(FSEM_E_INVALID, "fsem_stoi_score_f32: bad shape batch=%lld n=%lld stride=%lld",
                     (long long)in->batch, (long long)in->n, (long long)in->stride);
@@ -660,29 +711,48 @@ extern "C" int fsem_stoi_score_f32(fsem_stoi_ctx_t* ctx, const fsem_batch_t* in,
     const float* d10 = in->deg;
     int64_t sstride = in->stride;
     if (p.resample) {
+        const bool vec4 = rows_vec4(in->clean, in->deg, in->stride, dtype_size(dtype));
         if (ctx->fast85) {
             const int64_t bps = ceil_div(p.lmax, (int64_t)kRs85TileOut * kRs85TilesPerCta);
             const unsigned grid = (unsigned)(bps * 2 * in->batch);       // < 2^31: batch x frames is checked above
-            const bool vec4 = aligned16(in->clean) && aligned16(in->deg) && (in->stride % 4 == 0);
             { ProfScope prof_(K_STOI_RESAMPLE, stream);
-              if (vec4)
-                  stoi_resample85_kernel<true><<<grid, kRs85Threads, 0, stream>>>(
-                      in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, ctx->taps85, ctx->d_tab, y,
-                      p.ystride, hops, p.hops_max, (int)bps);
-              else
-                  stoi_resample85_kernel<false><<<grid, kRs85Threads, 0, stream>>>(
-                      in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, ctx->taps85, ctx->d_tab, y,
-                      p.ystride, hops, p.hops_max, (int)bps); }
+              dispatch_dtype(dtype, [&](auto tag) {
+                  using T = decltype(tag);
+                  const T* c = reinterpret_cast<const T*>(in->clean);
+                  const T* d = reinterpret_cast<const T*>(in->deg);
+                  if (vec4)
+                      stoi_resample85_kernel<true, T><<<grid, kRs85Threads, 0, stream>>>(
+                          c, d, in->lengths, in->batch, in->n, in->stride, ctx->taps85, ctx->d_tab, y, p.ystride, hops,
+                          p.hops_max, (int)bps);
+                  else
+                      stoi_resample85_kernel<false, T><<<grid, kRs85Threads, 0, stream>>>(
+                          c, d, in->lengths, in->batch, in->n, in->stride, ctx->taps85, ctx->d_tab, y, p.ystride, hops,
+                          p.hops_max, (int)bps);
+                  return FSEM_OK;
+              }); }
         } else {
             const int64_t bps = ceil_div(p.lmax, 256);
             if (bps * 2 * in->batch >= (int64_t(1) << 31))
                 return fail(FSEM_E_INVALID, "fsem_stoi_score_f32: batch x samples too large for one launch; split the batch");
             { ProfScope prof_(K_STOI_RESAMPLE, stream);
-              stoi_resample_kernel<<<(unsigned)(bps * 2 * in->batch), 256, 0, stream>>>(
-                  in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, ctx->d_taps, ctx->orig, ctx->neu,
-                  ctx->width, ctx->ntaps, y, p.ystride, (int)bps); }
+              dispatch_dtype(dtype, [&](auto tag) {
+                  using T = decltype(tag);
+                  stoi_resample_kernel<T><<<(unsigned)(bps * 2 * in->batch), 256, 0, stream>>>(
+                      reinterpret_cast<const T*>(in->clean), reinterpret_cast<const T*>(in->deg), in->lengths, in->batch,
+                      in->n, in->stride, ctx->d_taps, ctx->orig, ctx->neu, ctx->width, ctx->ntaps, y, p.ystride, (int)bps);
+                  return FSEM_OK;
+              }); }
         }
         FSEM_LAUNCHED();
+        c10 = y;
+        d10 = y + in->batch * p.ystride;
+        sstride = p.ystride;
+    } else if (dtype != FSEM_DTYPE_F32) {
+        // already 10 kHz, but not float32: widen into the (otherwise unused) resample area of the workspace
+        int rc = launch_ingest(in->clean, dtype, in->batch, in->n, in->stride, y, p.ystride, stream);
+        if (rc == FSEM_OK)
+            rc = launch_ingest(in->deg, dtype, in->batch, in->n, in->stride, y + in->batch * p.ystride, p.ystride, stream);
+        if (rc != FSEM_OK) return rc;
         c10 = y;
         d10 = y + in->batch * p.ystride;
         sstride = p.ystride;
@@ -785,10 +855,6 @@ extern "C" int fsem_stoi_mask_margin(fsem_stoi_ctx_t* ctx, int64_t batch, int64_
 // ================================================================================================
 namespace {
 
-size_t dtype_size(int dtype) {
-    return dtype == FSEM_DTYPE_F32 ? sizeof(float) : (dtype == FSEM_DTYPE_I16 || dtype == FSEM_DTYPE_F16) ? 2 : 0;
-}
-
 // device rows of `dtype` -> device fp32 rows on `stream`
 int launch_ingest(const void* src, int dtype, int64_t rows, int64_t n, int64_t sstride, float* dst, int64_t dstride,
                   cudaStream_t stream) {
@@ -832,15 +898,13 @@ int score_host_any(const char* who, fsem_pesq_ctx* pctx, fsem_stoi_ctx* sctx, co
     HostPipe& P = pctx ? pctx->pipe : sctx->pipe;
     int rc = P.init();
     if (rc != FSEM_OK) return rc;
-    const bool widen = dtype != FSEM_DTYPE_F32;
-    const int64_t dstride = round_up(n, 4);                          // fp32 rows the kernels read
-    const int64_t rstride = widen ? round_up(n, 8) : dstride;        // staged rows as uploaded (16-byte aligned)
+    // staged rows as uploaded: 16-byte aligned pitch; the first kernel of either chain reads them in their own dtype
+    // (no widening pass: a 2-byte batch is read from HBM at 2 bytes per sample as well)
+    const int64_t rstride = round_up(n, 16 / (int64_t)es);
     const int64_t per = host_chunk_items(batch, n);
     const size_t raw_sig = align256(es * per * rstride);
     const size_t in_bytes = 2 * raw_sig + align256(sizeof(int32_t) * per);
-    // 2-byte dtypes are widened into ONE fp32 copy of the chunk: the compute stream is serial, only the raw
-    // staging slots are double-buffered against the copy stream
-    const size_t conv_sig = widen ? align256(sizeof(float) * per * dstride) : 0;
+    const size_t conv_sig = 0;
     const size_t ws_pesq = pctx ? align256(fsem_pesq_workspace_bytes(pctx, per, n)) : 0;
     const size_t ws_stoi = sctx ? align256(fsem_stoi_workspace_bytes(sctx, per, n)) : 0;
     const size_t col = align256(sizeof(float) * batch);
@@ -872,17 +936,10 @@ int score_host_any(const char* who, fsem_pesq_ctx* pctx, fsem_stoi_ctx* sctx, co
             FSEM_CUDA(cudaMemcpyAsync(d_len, lengths + i0, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, P.copy));
         FSEM_CUDA(cudaEventRecord(P.copied[slot], P.copy));
         FSEM_CUDA(cudaStreamWaitEvent(P.compute, P.copied[slot], 0));
-        float* d_clean = reinterpret_cast<float*>(base);
-        float* d_deg = reinterpret_cast<float*>(base + raw_sig);
-        if (widen) {
-            d_clean = reinterpret_cast<float*>(wsb);
-            d_deg = reinterpret_cast<float*>(wsb + conv_sig);
-            rc = launch_ingest(base, dtype, cnt, n, rstride, d_clean, dstride, P.compute);
-            if (rc == FSEM_OK) rc = launch_ingest(base + raw_sig, dtype, cnt, n, rstride, d_deg, dstride, P.compute);
-        }
-        fsem_batch_t dev{d_clean, d_deg, lengths ? d_len : nullptr, cnt, n, dstride};
+        fsem_batch_t dev{reinterpret_cast<const float*>(base), reinterpret_cast<const float*>(base + raw_sig),
+                         lengths ? d_len : nullptr, cnt, n, rstride};
         if (rc == FSEM_OK && pctx && sctx)
-            rc = fsem_pesq_stoi_score_f32(pctx, sctx, &dev, reinterpret_cast<float*>(ob) + i0,
+            rc = fsem_pesq_stoi_score(pctx, sctx, &dev, dtype, reinterpret_cast<float*>(ob) + i0,
                                           reinterpret_cast<int32_t*>(ob + col) + i0,
                                           reinterpret_cast<float*>(ob + 2 * col) + i0,
                                           reinterpret_cast<float*>(ob + 3 * col) + i0,
@@ -890,10 +947,10 @@ int score_host_any(const char* who, fsem_pesq_ctx* pctx, fsem_stoi_ctx* sctx, co
                                           reinterpret_cast<int32_t*>(ob + 5 * col) + i0, wsb + 2 * conv_sig, ws_pesq,
                                           wsb + 2 * conv_sig + ws_pesq, ws_stoi, P.compute);
         else if (rc == FSEM_OK && pctx)
-            rc = fsem_pesq_score_f32(pctx, &dev, reinterpret_cast<float*>(ob) + i0,
-                                     reinterpret_cast<int32_t*>(ob + col) + i0, wsb + 2 * conv_sig, ws_pesq, P.compute);
+            rc = fsem_pesq_score(pctx, &dev, dtype, reinterpret_cast<float*>(ob) + i0,
+                                 reinterpret_cast<int32_t*>(ob + col) + i0, wsb + 2 * conv_sig, ws_pesq, P.compute);
         else if (rc == FSEM_OK && sctx)
-            rc = fsem_stoi_score_f32(sctx, &dev, reinterpret_cast<float*>(ob + 2 * col) + i0,
+            rc = fsem_stoi_score(sctx, &dev, dtype, reinterpret_cast<float*>(ob + 2 * col) + i0,
                                      reinterpret_cast<float*>(ob + 3 * col) + i0,
                                      reinterpret_cast<int32_t*>(ob + 4 * col) + i0,
                                      reinterpret_cast<int32_t*>(ob + 5 * col) + i0, wsb + 2 * conv_sig + ws_pesq, ws_stoi,
@@ -1128,16 +1185,24 @@ extern "C" int fsem_lsd_score_f32(fsem_lsd_ctx_t* ctx, const fsem_batch_t* in, f
 // ------------------------------------------------------------------------------------------------
 // Device entry point for BOTH metrics: the two kernel chains back to back on `stream`, each reading the input itself
 // (SURVEY.md 8f rank 1 is delivered as "single upload": the host pipeline copies every chunk once and calls this).
+extern "C" int fsem_pesq_stoi_score(fsem_pesq_ctx_t* pctx, fsem_stoi_ctx_t* sctx, const fsem_batch_t* in, int dtype,
+                                    float* mos_out, int32_t* pesq_status_out, float* stoi_out, float* estoi_out,
+                                    int32_t* kept_frames_out, int32_t* stoi_status_out, void* ws_pesq,
+                                    size_t ws_pesq_bytes, void* ws_stoi, size_t ws_stoi_bytes, void* stream) {
+    if (!pctx || !sctx) return fail(FSEM_E_INVALID, "fsem_pesq_stoi_score: null context");
+    int rc = fsem_pesq_score(pctx, in, dtype, mos_out, pesq_status_out, ws_pesq, ws_pesq_bytes, stream);
+    if (rc == FSEM_OK)
+        rc = fsem_stoi_score(sctx, in, dtype, stoi_out, estoi_out, kept_frames_out, stoi_status_out, ws_stoi,
+                             ws_stoi_bytes, stream);
+    return rc;
+}
+
 extern "C" int fsem_pesq_stoi_score_f32(fsem_pesq_ctx_t* pctx, fsem_stoi_ctx_t* sctx, const fsem_batch_t* in,
                                         float* mos_out, int32_t* pesq_status_out, float* stoi_out, float* estoi_out,
                                         int32_t* kept_frames_out, int32_t* stoi_status_out, void* ws_pesq,
                                         size_t ws_pesq_bytes, void* ws_stoi, size_t ws_stoi_bytes, void* stream) {
-    if (!pctx || !sctx) return fail(FSEM_E_INVALID, "fsem_pesq_stoi_score_f32: null context");
-    int rc = fsem_pesq_score_f32(pctx, in, mos_out, pesq_status_out, ws_pesq, ws_pesq_bytes, stream);
-    if (rc == FSEM_OK)
-        rc = fsem_stoi_score_f32(sctx, in, stoi_out, estoi_out, kept_frames_out, stoi_status_out, ws_stoi,
-                                 ws_stoi_bytes, stream);
-    return rc;
+    return fsem_pesq_stoi_score(pctx, sctx, in, FSEM_DTYPE_F32, mos_out, pesq_status_out, stoi_out, estoi_out,
+                                kept_frames_out, stoi_status_out, ws_pesq, ws_pesq_bytes, ws_stoi, ws_stoi_bytes, stream);
 }
 
 // ================================================================================================

@@ -1,5 +1,6 @@
 // Shared helpers for the fsem sm_100a kernels.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -84,6 +85,42 @@ __device__ __forceinline__ float4 ldg_f4_l2_256(const float* p) {
     asm volatile("ld.global.nc.L2::256B.v4.f32 {%0, %1, %2, %3}, [%4];"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
+}
+
+// ---- ingest formats: the first kernel of a metric reads float32, int16 PCM or fp16 rows directly.
+// The conversion is the value-preserving cast the reference's float32 boundary implies (no 1/32768 scaling: PESQ's
+// level alignment and STOI's per-segment normalisation make both metrics scale-free), so the scores are bit-identical
+// to scoring `x.float()`.
+__device__ __forceinline__ float sample_to_f32(float v) { return v; }
+__device__ __forceinline__ float sample_to_f32(int16_t v) { return (float)v; }
+__device__ __forceinline__ float sample_to_f32(__half v) { return __half2float(v); }
+__device__ __forceinline__ float load_sample(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float load_sample(const int16_t* p) { return (float)__ldg(p); }
+__device__ __forceinline__ float load_sample(const __half* p) { return __half2float(__ldg(p)); }
+
+// four consecutive samples (address aligned to four elements) as float4; kL2Hint256 asks L2 for the 256-byte block
+template <bool kL2Hint256>
+__device__ __forceinline__ float4 load_samples4(const float* p) {
+    if (kL2Hint256) return ldg_f4_l2_256(p);
+    return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ uint2 ldg_u2_l2_256(const void* p) {
+    uint2 v;
+    asm volatile("ld.global.nc.L2::256B.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+template <bool kL2Hint256>
+__device__ __forceinline__ float4 load_samples4(const int16_t* p) {
+    const uint2 raw = kL2Hint256 ? ldg_u2_l2_256(p) : __ldg(reinterpret_cast<const uint2*>(p));
+    return make_float4((float)(int16_t)(raw.x & 0xffffu), (float)(int16_t)(raw.x >> 16),
+                       (float)(int16_t)(raw.y & 0xffffu), (float)(int16_t)(raw.y >> 16));
+}
+template <bool kL2Hint256>
+__device__ __forceinline__ float4 load_samples4(const __half* p) {
+    const uint2 raw = kL2Hint256 ? ldg_u2_l2_256(p) : __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+    return make_float4(a.x, a.y, b.x, b.y);
 }
 
 __device__ __forceinline__ int item_length(const int32_t* lengths, int64_t item, int64_t n) {

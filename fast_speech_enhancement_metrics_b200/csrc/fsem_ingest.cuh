@@ -12,9 +12,6 @@
 
 namespace fsem {
 
-__device__ __forceinline__ float sample_to_f32(int16_t v) { return (float)v; }
-__device__ __forceinline__ float sample_to_f32(__half v) { return __half2float(v); }
-
 // rows [rows, n] of T (pitch sstride elements) -> float rows (pitch dstride).  One thread = 8 consecutive
 // samples of one row: a 16-byte load and two 16-byte stores when kVec (every row start 16-byte aligned on both
 // sides), element-wise otherwise and at the ragged end of a row.

@@ -86,9 +86,9 @@ __device__ __forceinline__ float taper_weight(int t, int len) {
 // Kernel A: one thread per (signal, time chunk).  The thread starts `warm` samples before its
 // chunk with zero state (both IIRs have decayed below fp32 resolution by then), walks the chunk
 // serially, accumulates y^2 and writes z.  Signals: s < B -> clean[s], else deg[s - B].
-template <bool kVec4>
+template <bool kVec4, typename T>
 __global__ void __launch_bounds__(128)
-pesq_filter_kernel(const float* __restrict__ clean, const float* __restrict__ deg,
+pesq_filter_kernel(const T* __restrict__ clean, const T* __restrict__ deg,
                    const int32_t* __restrict__ lengths, int64_t batch, int64_t n, int64_t stride,
                    int chunk, int nchunks, int warm, const __grid_constant__ PesqFilterCoef P,
                    float* __restrict__ z_out, int64_t zstride, double* __restrict__ partial) {
@@ -97,7 +97,7 @@ pesq_filter_kernel(const float* __restrict__ clean, const float* __restrict__ de
     const int64_t sig = gid / nchunks;
     const int c = (int)(gid - sig * nchunks);
     const int64_t item = sig < batch ? sig : sig - batch;
-    const float* __restrict__ x = (sig < batch ? clean : deg) + item * stride;
+    const T* __restrict__ x = (sig < batch ? clean : deg) + item * stride;
     float* __restrict__ z = z_out + sig * zstride;
     const int len = item_length(lengths, item, n);
 
@@ -113,11 +113,11 @@ pesq_filter_kernel(const float* __restrict__ clean, const float* __restrict__ de
 
     auto load4 = [&](int tt, float (&v)[4]) {
         if (kVec4 && tt + 4 <= len) {
-            float4 q = __ldg(reinterpret_cast<const float4*>(x + tt));
+            float4 q = load_samples4<false>(x + tt);
             v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
         } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = (tt + j < len) ? __ldg(x + tt + j) : 0.f;
+            for (int j = 0; j < 4; ++j) v[j] = (tt + j < len) ? load_sample(x + tt + j) : 0.f;
         }
     };
 
@@ -199,9 +199,9 @@ constexpr int kFiltPitch = 36;   // A/B: one slot, z drained after every tile (4
 // other (pesq_order_kernel), so the 32 signals of a warp end together; a warp stops at its longest signal and a lane
 // whose signal has ended skips the arithmetic.  Results do not depend on the grouping: every lane runs the same
 // recurrence on the same chunk grid whatever its neighbours are.
-template <bool kHasLengths>
+template <bool kHasLengths, typename T>
 __global__ void __launch_bounds__(kFiltWarps * 32)
-pesq_filter_tiled_kernel(const float* __restrict__ clean, const float* __restrict__ deg,
+pesq_filter_tiled_kernel(const T* __restrict__ clean, const T* __restrict__ deg,
                          const int32_t* __restrict__ lengths, const int32_t* __restrict__ order, int64_t batch,
                          int64_t n, int64_t stride, int chunk, int nchunks, int warm,
                          const __grid_constant__ PesqFilterCoef P, float* __restrict__ z_out, int64_t zstride,
@@ -227,9 +227,9 @@ pesq_filter_tiled_kernel(const float* __restrict__ clean, const float* __restric
     // rows this lane helps to move (transfer role): slots (lane >> 3) + 4*i, float4 column lane & 7
     const int col = (lane & 7) * 4;
     const int64_t trow = row0 + (lane >> 3);
-    const float* __restrict__ sbase = (half ? deg : clean) + col;
+    const T* __restrict__ sbase = (half ? deg : clean) + col;
     float* __restrict__ dbase = z_out + (int64_t)half * batch * zstride + col;
-    const float* __restrict__ src0 = sbase + trow * stride;
+    const T* __restrict__ src0 = sbase + trow * stride;
     float* __restrict__ dst0 = dbase + trow * zstride;
     const int64_t sstep = 4 * stride, dstep = 4 * zstride;
     int row_len[kHasLengths ? 8 : 1];
@@ -245,7 +245,7 @@ pesq_filter_tiled_kernel(const float* __restrict__ clean, const float* __restric
     }
     const int rows_ok = (int)min((int64_t)8, (batch - trow + 3) / 4);      // slots trow + 4i < batch  <=>  i < rows_ok
     auto rlen = [&](int i) -> int { return kHasLengths ? row_len[kHasLengths ? i : 0] : (i < rows_ok ? (int)n : 0); };
-    auto src_row = [&](int i) -> const float* {
+    auto src_row = [&](int i) -> const T* {
         return kHasLengths ? sbase + (int64_t)row_item[kHasLengths ? i : 0] * stride : src0 + i * sstep;
     };
     auto dst_row = [&](int i) -> float* {
@@ -271,14 +271,14 @@ pesq_filter_tiled_kernel(const float* __restrict__ clean, const float* __restric
         for (int i = 0; i < 8; ++i) {
             const int a = tt + col;
             const int rl = rlen(i);
-            const float* q = src_row(i) + tt;
+            const T* q = src_row(i) + tt;
             if (a + 4 <= rl) {
-                v[i] = ldg_f4_l2_256(q);     // 4.46 -> 4.18 ms at 8192 x 10 s against a plain __ldg
+                v[i] = load_samples4<true>(q);     // L2::256B hint: 4.46 -> 4.18 ms at 8192 x 10 s against a plain __ldg
             } else {
-                v[i].x = (a < rl) ? __ldg(q) : 0.f;
-                v[i].y = (a + 1 < rl) ? __ldg(q + 1) : 0.f;
-                v[i].z = (a + 2 < rl) ? __ldg(q + 2) : 0.f;
-                v[i].w = (a + 3 < rl) ? __ldg(q + 3) : 0.f;
+                v[i].x = (a < rl) ? load_sample(q) : 0.f;
+                v[i].y = (a + 1 < rl) ? load_sample(q + 1) : 0.f;
+                v[i].z = (a + 2 < rl) ? load_sample(q + 2) : 0.f;
+                v[i].w = (a + 3 < rl) ? load_sample(q + 3) : 0.f;
             }
         }
     };

@@ -28,8 +28,9 @@ struct StoiTables {
 // General polyphase resampler: y[neu*k + p] = sum_j taps[p][j] * xpad[orig*k + j],
 // xpad = `width` zeros | x | zeros.  One thread per output sample; 1-D grid of blocks_per_sig blocks per signal
 // (no 65535 cap of grid.y on the batch).
+template <typename T>
 __global__ void __launch_bounds__(256)
-stoi_resample_kernel(const float* __restrict__ clean, const float* __restrict__ deg,
+stoi_resample_kernel(const T* __restrict__ clean, const T* __restrict__ deg,
                      const int32_t* __restrict__ lengths, int64_t batch, int64_t n, int64_t stride,
                      const float* __restrict__ taps, int orig, int neu, int width, int ntaps,
                      float* __restrict__ y, int64_t ystride, int blocks_per_sig) {
@@ -40,7 +41,7 @@ stoi_resample_kernel(const float* __restrict__ clean, const float* __restrict__ 
     const int64_t L = stoi_resampled_len(len, orig, neu);
     const int64_t m = (int64_t)bx * blockDim.x + threadIdx.x;
     if (m >= L) return;
-    const float* __restrict__ x = (sig < batch ? clean : deg) + item * stride;
+    const T* __restrict__ x = (sig < batch ? clean : deg) + item * stride;
     const int64_t k = m / neu;
     const int p = (int)(m - k * neu);
     const float* __restrict__ h = taps + (int64_t)p * ntaps;
@@ -48,7 +49,7 @@ stoi_resample_kernel(const float* __restrict__ clean, const float* __restrict__ 
     float acc = 0.f;
     for (int j = 0; j < ntaps; ++j) {
         int64_t i = i0 + j;
-        float xv = (i >= 0 && i < len) ? __ldg(x + i) : 0.f;
+        float xv = (i >= 0 && i < len) ? load_sample(x + i) : 0.f;
         acc = fmaf(__ldg(h + j), xv, acc);
     }
     y[sig * ystride + m] = acc;
@@ -100,9 +101,9 @@ static_assert(kRs85TileOut % FSEM_STOI_HOP == 0, "tiles must hold whole hops");
 //     A_h = sum_r (w[r]       * y[128h + r])^2      (hop as FIRST  half of analysis frame h)
 //     B_h = sum_r (w[r + 128] * y[128h + r])^2      (hop as SECOND half of analysis frame h-1)
 // (products rounded to fp32 like the reference, sums in fp64), so that ||w * x_t||^2 = A_t + B_{t+1} (STOI.py:92-98).
-template <bool kVec4>
+template <bool kVec4, typename T>
 __global__ void __launch_bounds__(kRs85Threads)
-stoi_resample85_kernel(const float* __restrict__ clean, const float* __restrict__ deg,
+stoi_resample85_kernel(const T* __restrict__ clean, const T* __restrict__ deg,
                        const int32_t* __restrict__ lengths, int64_t batch, int64_t n, int64_t stride,
                        const __grid_constant__ Resample85Taps taps, const StoiTables* __restrict__ tab,
                        float* __restrict__ y, int64_t ystride, double2* __restrict__ hop_energy, int hops_max,
@@ -116,10 +117,10 @@ stoi_resample85_kernel(const float* __restrict__ clean, const float* __restrict_
     const bool is_clean = sig < batch;
     const int64_t item = is_clean ? sig : sig - batch;
     const int len = item_length(lengths, item, n);
-    const int64_t L = stoi_resampled_len(len, 8, 5);
-    const int64_t tile0 = (int64_t)bx * kRs85TilesPerCta;
+    const int L = (int)stoi_resampled_len(len, 8, 5);
+    const int tile0 = bx * kRs85TilesPerCta;
     if (tile0 * kRs85TileOut >= L) return;
-    const float* __restrict__ x = (is_clean ? clean : deg) + item * stride;
+    const T* __restrict__ x = (is_clean ? clean : deg) + item * stride;
     float* __restrict__ yrow = y + sig * ystride;
     for (int i = tid; i < FSEM_STOI_WIN; i += kRs85Threads) s_win[i] = tab->window[i];
 
@@ -128,28 +129,40 @@ stoi_resample85_kernel(const float* __restrict__ clean, const float* __restrict_
     // a and a + 4 (a = group of four float4): with one pad float4 per four the padded positions p = 5a + b are then
     // distinct mod 8 and the STS.128 is conflict-free (consecutive lanes would collide on p and p + 8)
     const int fill_q = kRs85PadEvery == 4 ? (tid & ~31) + 4 * (((tid & 31) >> 3) + 4 * ((tid >> 2) & 1)) + (tid & 3) : tid;
-    auto fetch = [&](int64_t tile, float4 (&v)[kPerThread]) {
-        const int64_t in0 = tile * kRs85TileIn - 12;                              // first staged sample (multiple of 4)
+    // sample indices fit 32 bits (n < 2^30, checked on the host): 64-bit index arithmetic and compares cost this
+    // LSU / issue bound kernel ~15 % of its instructions
+    const int len32 = len;
+    auto fetch = [&](int tile, float4 (&v)[kPerThread]) {
+        const int in0 = tile * kRs85TileIn - 12;                                  // first staged sample (multiple of 4)
+        if (kVec4 && in0 >= 0 && in0 + 4 * kRs85Quads <= len32) {                 // interior tile (CTA-uniform): no checks
+#pragma unroll
+            for (int r = 0; r < kPerThread; ++r) {
+                const int q = fill_q + r * kRs85Threads;
+                if (r + 1 < kPerThread || q < kRs85Quads) v[r] = load_samples4<false>(x + in0 + 4 * q);
+                else v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            return;
+        }
 #pragma unroll
         for (int r = 0; r < kPerThread; ++r) {
             const int q = fill_q + r * kRs85Threads;
-            const int64_t i = in0 + 4 * (int64_t)q;
+            const int i = in0 + 4 * q;
             if (q >= kRs85Quads) { v[r] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
-            if (kVec4 && i >= 0 && i + 4 <= len) {
-                v[r] = __ldg(reinterpret_cast<const float4*>(x + i));
+            if (kVec4 && i >= 0 && i + 4 <= len32) {
+                v[r] = load_samples4<false>(x + i);
             } else {
-                v[r].x = (i >= 0 && i < len) ? __ldg(x + i) : 0.f;
-                v[r].y = (i + 1 >= 0 && i + 1 < len) ? __ldg(x + i + 1) : 0.f;
-                v[r].z = (i + 2 >= 0 && i + 2 < len) ? __ldg(x + i + 2) : 0.f;
-                v[r].w = (i + 3 >= 0 && i + 3 < len) ? __ldg(x + i + 3) : 0.f;
+                v[r].x = (i >= 0 && i < len32) ? load_sample(x + i) : 0.f;
+                v[r].y = (i + 1 >= 0 && i + 1 < len32) ? load_sample(x + i + 1) : 0.f;
+                v[r].z = (i + 2 >= 0 && i + 2 < len32) ? load_sample(x + i + 2) : 0.f;
+                v[r].w = (i + 3 >= 0 && i + 3 < len32) ? load_sample(x + i + 3) : 0.f;
             }
         }
     };
     float4 pre[kPerThread];
     fetch(tile0, pre);
     for (int k = 0; k < kRs85TilesPerCta; ++k) {
-        const int64_t tile = tile0 + k;
-        const int64_t out0 = tile * kRs85TileOut;
+        const int tile = tile0 + k;
+        const int out0 = tile * kRs85TileOut;
         if (out0 >= L) break;                                                      // uniform
 #pragma unroll
         for (int r = 0; r < kPerThread; ++r) {
@@ -189,16 +202,22 @@ stoi_resample85_kernel(const float* __restrict__ clean, const float* __restrict_
         }
         __syncthreads();
         // coalesced float4 stores of the tile's outputs
-        const int64_t valid = min((int64_t)kRs85TileOut, L - out0);
-        for (int q = tid; q < kRs85TileOut / 4; q += kRs85Threads) {
-            const float4 v = *reinterpret_cast<const float4*>(s_out + 4 * q);
-            float* d = yrow + out0 + 4 * q;
-            if (4 * q + 4 <= valid) {
-                *reinterpret_cast<float4*>(d) = v;
-            } else {
-                if (4 * q < valid) d[0] = v.x;
-                if (4 * q + 1 < valid) d[1] = v.y;
-                if (4 * q + 2 < valid) d[2] = v.z;
+        const int valid = min(kRs85TileOut, L - out0);
+        if (valid == kRs85TileOut) {                                               // full tile (CTA-uniform): no checks
+#pragma unroll
+            for (int q = tid; q < kRs85TileOut / 4; q += kRs85Threads)
+                *reinterpret_cast<float4*>(yrow + out0 + 4 * q) = *reinterpret_cast<const float4*>(s_out + 4 * q);
+        } else {
+            for (int q = tid; q < kRs85TileOut / 4; q += kRs85Threads) {
+                const float4 v = *reinterpret_cast<const float4*>(s_out + 4 * q);
+                float* d = yrow + out0 + 4 * q;
+                if (4 * q + 4 <= valid) {
+                    *reinterpret_cast<float4*>(d) = v;
+                } else {
+                    if (4 * q < valid) d[0] = v.x;
+                    if (4 * q + 1 < valid) d[1] = v.y;
+                    if (4 * q + 2 < valid) d[2] = v.z;
+                }
             }
         }
         if (is_clean) {
@@ -217,7 +236,7 @@ stoi_resample85_kernel(const float* __restrict__ clean, const float* __restrict_
             for (int i = 0; i < kHopsPerWarp; ++i) {
                 const int h = warp + kWarps * i;
                 double a = 0.0, b = 0.0;
-                if (h < kRs85Hops && (int64_t)(h + 1) * FSEM_STOI_HOP <= valid) {      // only complete hops matter (warp-uniform)
+                if (h < kRs85Hops && (h + 1) * FSEM_STOI_HOP <= valid) {              // only complete hops matter (warp-uniform)
                     const float4 x = *reinterpret_cast<const float4*>(s_out + h * FSEM_STOI_HOP + 4 * lane);
                     float f;
                     f = __fmul_rn(x.x, wa.x); a = fma((double)f, (double)f, a);
@@ -259,7 +278,7 @@ stoi_resample85_kernel(const float* __restrict__ clean, const float* __restrict_
             const int local = b8 ? 2 : (b4 ? 1 : 0);
             const int sum_idx = (b16 ? 3 : 0) + local;
             const int h = warp + kWarps * (sum_idx >> 1);
-            if ((lane & 3) == 0 && !(b8 && b4) && h < kRs85Hops && (int64_t)(h + 1) * FSEM_STOI_HOP <= valid) {
+            if ((lane & 3) == 0 && !(b8 && b4) && h < kRs85Hops && (h + 1) * FSEM_STOI_HOP <= valid) {
                 double* dst = reinterpret_cast<double*>(hop_energy + item * hops_max + tile * kRs85Hops + h);
                 dst[sum_idx & 1] = one;                                           // .x = A_h, .y = B_h
             }

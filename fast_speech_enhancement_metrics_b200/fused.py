@@ -20,7 +20,7 @@ from .STOI import STOI
 
 
 def score_pesq_stoi_tensors(pesq: PESQ, stoi: STOI, clean: torch.Tensor, deg: torch.Tensor, lengths=None):
-    """Device-resident scoring of both metrics: [B, n] float32 CUDA tensors -> (scores[3, B] f32 = PESQ / STOI /
+    """Device-resident scoring of both metrics: [B, n] float32 / int16 / float16 CUDA tensors -> (scores[3, B] f32 = PESQ / STOI /
     ESTOI rows, pesq_status[B], kept_frames[B], stoi_status[B]) CUDA tensors; stream-ordered, no host sync
     (C ABI fsem_pesq_stoi_score_f32: the two kernel chains back to back on the current stream)."""
     clean, deg = pesq._on_device(clean), pesq._on_device(deg)
@@ -39,8 +39,8 @@ def score_pesq_stoi_tensors(pesq: PESQ, stoi: STOI, clean: torch.Tensor, deg: to
         wsb = stoi._get_workspace(stoi._lib.fsem_stoi_workspace_bytes(stoi._ctx, b, n))
         batch = _lib.Batch(clean.data_ptr(), deg.data_ptr(), lens.data_ptr() if lens is not None else None,
                            b, n, clean.stride(0) if b > 1 else max(n, clean.stride(0)))
-        PESQ._check_score(pesq._lib.fsem_pesq_stoi_score_f32(
-            pesq._ctx, stoi._ctx, C.byref(batch), scores[0].data_ptr(), pst.data_ptr(), scores[1].data_ptr(),
+        PESQ._check_score(pesq._lib.fsem_pesq_stoi_score(
+            pesq._ctx, stoi._ctx, C.byref(batch), _lib.dtype_code(clean.dtype), scores[0].data_ptr(), pst.data_ptr(), scores[1].data_ptr(),
             scores[2].data_ptr(), kept.data_ptr(), sst.data_ptr(), wp.data_ptr(), wp.numel(), wsb.data_ptr(),
             wsb.numel(), C.c_void_p(torch.cuda.current_stream(clean.device).cuda_stream)))
     pesq._last_shape = (b, n)

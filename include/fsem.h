@@ -212,6 +212,21 @@ FSEM_API int fsem_pesq_stoi_score_f32(fsem_pesq_ctx_t* pesq, fsem_stoi_ctx_t* st
 #define FSEM_DTYPE_I16 1
 #define FSEM_DTYPE_F16 2
 
+/* Device entry points for any ingest dtype: exactly fsem_pesq_score_f32 / fsem_stoi_score_f32 /
+ * fsem_pesq_stoi_score_f32 (which forward here with FSEM_DTYPE_F32), but `in->clean` / `in->deg` point at device rows of
+ * `dtype` and `in->stride` counts ELEMENTS.  The first kernel of each chain (PESQ's IIR pass, STOI's resampler, or the
+ * general resampler of a context that resamples on ingest) reads the rows in their own type, so a device-resident int16 /
+ * fp16 batch is read from HBM once at 2 bytes per sample -- there is no widening pass.  (Only STOI on input that already
+ * is 10 kHz has no such first kernel: it widens the rows into its workspace first.) */
+FSEM_API int fsem_pesq_score(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in, int dtype, float* mos_out, int32_t* status_out,
+                    void* workspace, size_t workspace_bytes, void* stream);
+FSEM_API int fsem_stoi_score(fsem_stoi_ctx_t* ctx, const fsem_batch_t* in, int dtype, float* stoi_out, float* estoi_out,
+                    int32_t* kept_frames_out, int32_t* status_out, void* workspace, size_t workspace_bytes, void* stream);
+FSEM_API int fsem_pesq_stoi_score(fsem_pesq_ctx_t* pesq, fsem_stoi_ctx_t* stoi, const fsem_batch_t* in, int dtype,
+                         float* mos_out, int32_t* pesq_status_out, float* stoi_out, float* estoi_out,
+                         int32_t* kept_frames_out, int32_t* stoi_status_out, void* ws_pesq, size_t ws_pesq_bytes,
+                         void* ws_stoi, size_t ws_stoi_bytes, void* stream);
+
 /* Device rows [rows, n] of `dtype` (pitch src_stride ELEMENTS) -> device fp32 rows (pitch dst_stride floats);
  * stream-ordered.  FSEM_DTYPE_F32 is a strided device-to-device copy. */
 FSEM_API int fsem_ingest_f32(const void* src, int dtype, int64_t rows, int64_t n, int64_t src_stride, float* dst,
@@ -220,8 +235,8 @@ FSEM_API int fsem_ingest_f32(const void* src, int dtype, int64_t rows, int64_t n
 /* Host entry point for any ingest dtype and any subset of the two metrics: `pesq` or `stoi` may be NULL (that
  * metric is skipped and its output pointers are ignored).  clean / deg are HOST rows [batch, n] of `dtype` with
  * pitch `stride` elements (pinned memory for full PCIe speed), lengths [batch] HOST int32 or NULL.  Every chunk
- * crosses PCIe once at sizeof(dtype) bytes per sample, is widened on the device and scored by the selected kernel
- * chains while the next chunk is in flight.  With FSEM_DTYPE_F32 this is exactly fsem_pesq_score_host_f32 /
+ * crosses PCIe once at sizeof(dtype) bytes per sample and is scored in that dtype by the selected kernel chains
+ * (fsem_pesq_score / fsem_stoi_score) while the next chunk is in flight.  With FSEM_DTYPE_F32 this is exactly fsem_pesq_score_host_f32 /
  * fsem_stoi_score_host_f32 / fsem_pesq_stoi_score_host_f32 (which forward here). */
 FSEM_API int fsem_score_host(fsem_pesq_ctx_t* pesq, fsem_stoi_ctx_t* stoi, const void* clean, const void* deg, int dtype,
                     const int32_t* lengths, int64_t batch, int64_t n, int64_t stride, float* mos_out,

@@ -579,6 +579,45 @@ def test_int16_and_fp16_inputs_score_like_their_float32_values(dtype, pesq, stoi
         pesq(cf.double(), df.double())
 
 
+@pytest.mark.parametrize("dtype", [torch.int16, torch.float16])
+def test_16_bit_device_tensors_are_read_by_the_first_kernels(dtype, pesq, stoi_metrics):
+    """Device-resident int16 / float16 batches: no widening pass (`ingest_kernel` is not launched), the IIR pass and the
+    resampler read the rows in their own dtype; scores are bit-identical to the float32 tensor holding the same values.
+    Also the corners: batches below 16 items (thread-per-chunk IIR kernel), rows that are not 8-byte aligned (scalar
+    loads), STOI on 10 kHz input (the one path that still widens, inside the library) and PESQ at 8 kHz (typed general
+    resampler)."""
+    from fast_speech_enhancement_metrics_b200 import PESQ, _lib, score_pesq_stoi_tensors
+    from fast_speech_enhancement_metrics_b200.synth import synth_batch
+    clean, deg, _ = synth_batch(31, 40, 24000)
+    cn, cf = _as_dtype(clean, dtype)
+    dn, df = _as_dtype(deg, dtype)
+    cn, dn, cf, df = cn.cuda(), dn.cuda(), cf.cuda(), df.cuda()
+    st = stoi_metrics(16000)
+    _lib.profile_reset()
+    _lib.profile_enable(True)
+    got, _, kept, _ = score_pesq_stoi_tensors(pesq, st, cn, dn)
+    torch.cuda.synchronize()
+    _lib.profile_enable(False)
+    prof = _lib.profile_read()
+    assert prof["ingest_kernel"][1] == 0, prof
+    assert prof["pesq_filter_kernel"][1] == 1 and prof["stoi_resample_kernel"][1] == 1
+    want, _, kept_f, _ = score_pesq_stoi_tensors(pesq, st, cf, df)
+    assert torch.equal(got.view(torch.int32), want.view(torch.int32)) and torch.equal(kept, kept_f)
+    # small batch (thread-per-(signal, chunk) IIR kernel) and unaligned rows (odd offset inside a wider buffer)
+    for sl in (slice(0, 5), slice(0, 40)):
+        for off in (0, 1):
+            a, b = cn[sl, off:off + 20001], dn[sl, off:off + 20001]
+            af, bf = cf[sl, off:off + 20001], df[sl, off:off + 20001]
+            assert pesq(a, b) == pesq(af, bf)
+            assert st(a, b) == st(af, bf)
+    # 10 kHz input: STOI has no resampler in front, the library widens into its workspace
+    s10 = stoi_metrics(10000)
+    assert s10(cn[:6], dn[:6]) == s10(cf[:6], df[:6])
+    # PESQ at 8 kHz: the general polyphase resampler reads the 16-bit rows
+    p8 = PESQ(8000, use_gpu=True)
+    assert p8(cn[:6, :16000], dn[:6, :16000]) == p8(cf[:6, :16000], df[:6, :16000])
+
+
 def test_pesq_ragged_batch_with_empty_and_short_items(pesq):
     """Variable-length batches go through the length-sorted IIR pass and the frame-prefix work split of the
     spectrum kernel: items without a single frame (T = 0) and items below 20 frames must neither disturb their
