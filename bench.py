@@ -187,6 +187,30 @@ def run_reference(args, emit):
     return 0
 
 
+# ------------------------------------------------------------------------------------------ NUMA placement
+def bind_to_gpu_cpus(gpu_index: int):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, BEFORE any pinned host buffer is allocated: the
+    e2e leg is bound by pinned host->device copies, and a pinned buffer is placed (first touch) on the NUMA node of
+    the thread that allocates it.  Returns a short description for the bench line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, v in enumerate(words) for b in range(64) if (v >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "no local cpus reported"
+        os.sched_setaffinity(0, cpus)
+        try:
+            node = pynvml.nvmlDeviceGetNumaNodeId(h)
+        except Exception:
+            node = None
+        return "bound to %d cpus local to gpu %d (numa node %s)" % (len(cpus), gpu_index, node)
+    except Exception as exc:
+        return "not bound (%r)" % (exc,)
+
+
 # ------------------------------------------------------------------------------------------ parity at the workload
 def parity_block(pesq, stoi, clean, deg, gathered, lo, hi, world, device, items):
     """Outside the timed region: the rank's shard is scored once more (same kernels, same chunk grid as the timed
@@ -302,6 +326,10 @@ def main():
         print("bench.py: --gpus %d needs torchrun (WORLD_SIZE is 1); running 1 rank" % args.gpus, file=sys.stderr)
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    # multi-GPU: NUMA-local pinned buffers by default (FSEM_BIND_NUMA=0 disables)
+    numa = "off"
+    if os.environ.get("FSEM_BIND_NUMA", "1" if world > 1 else "0") == "1":
+        numa = bind_to_gpu_cpus(local_rank)
     n = int(args.seconds * FS)
     lo, hi = shard_range(args.batch, world, rank)
     local_b = hi - lo
@@ -500,7 +528,8 @@ def main():
         "config": {"workload": workload_string(args.batch, args.seconds, world),
                    "batch_total": args.batch, "batch_per_gpu": local_b, "samples": n, "sample_rate": FS,
                    "l2": "inputs (%.1f GB per GPU) exceed L2; no flush" % (2 * local_b * n * 4 / 1e9),
-                   "collective": "all_gather of [batch/N, 3] fp32 scores (NCCL)" if world > 1 else "none"},
+                   "collective": "all_gather of [batch/N, 3] fp32 scores (NCCL)" if world > 1 else "none",
+                   "numa": numa},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "roofline_call": roofline_call, "roofline_step": roofline_step, "kernels": kernels,
         "cpu_baseline": cpu, "parity": parity, "finite_score_fraction": finite,

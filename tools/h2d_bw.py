@@ -92,9 +92,9 @@ def main():
             numa = sorted(d for d in os.listdir("/sys/devices/system/node") if d.startswith("node"))
         except OSError:
             pass
-        print(json.dumps({"n_gpus": world, "bind": args.bind, "host_numa_nodes": numa, "host_cpus": os.cpu_count(),
+        print("H2D_JSON " + json.dumps({"n_gpus": world, "bind": args.bind, "host_numa_nodes": numa, "host_cpus": os.cpu_count(),
                           "aggregate_concurrent_gbs": round(sum(r["concurrent_gbs"] for r in recs), 1),
-                          "ranks": recs}))
+                          "ranks": recs}), flush=True)
 
 
 if __name__ == "__main__":
