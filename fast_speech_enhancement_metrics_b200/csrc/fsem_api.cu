@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -12,6 +13,7 @@
 #include "fsem_stoi.cuh"
 #include "fsem_lsd.cuh"
 #include "fsem_sdr.cuh"
+#include "fsem_sdr_tc.cuh"
 #include "fsem_ingest.cuh"
 
 using namespace fsem;
@@ -1244,12 +1246,25 @@ extern "C" int fsem_sdr_score_f32(const fsem_batch_t* in, float* sdr_out, void* 
     sdr_norm_kernel<<<(unsigned)(2 * in->batch), 256, 0, stream>>>(in->clean, in->deg, in->lengths, in->batch, in->n,
                                                                   in->stride, energy);
     FSEM_LAUNCHED();
-    { ProfScope prof_(K_SDR_CORR, stream);
-      sdr_corr_kernel<<<dim3((unsigned)p.nsuper, (unsigned)in->batch), kSdrThreads, 0, stream>>>(
-          in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, p.nsuper, partial); }
+    // correlation lags: tensor cores (tcgen05, fsem_sdr_tc.cuh) by default; FSEM_SDR_SIMT=1 selects the round-1 SIMT
+    // kernel (kept for A/B measurements)
+    static const bool simt = [] { const char* e = getenv("FSEM_SDR_SIMT"); return e && e[0] == '1'; }();
+    int nsuper = p.nsuper;
+    if (simt) {
+        ProfScope prof_(K_SDR_CORR, stream);
+        sdr_corr_kernel<<<dim3((unsigned)p.nsuper, (unsigned)in->batch), kSdrThreads, 0, stream>>>(
+            in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, p.nsuper, partial);
+    } else {
+        FSEM_CUDA(cudaFuncSetAttribute(sdr_corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcDynSmem));
+        const int vec4 = rows_vec4(in->clean, in->deg, in->stride, sizeof(float)) ? 1 : 0;
+        nsuper = 1;
+        ProfScope prof_(K_SDR_CORR, stream);
+        sdr_corr_tc_kernel<<<(unsigned)(4 * in->batch), kTcThreads, kTcDynSmem, stream>>>(
+            in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, vec4, partial);
+    }
     FSEM_LAUNCHED();
     { ProfScope prof_(K_SDR_SOLVE, stream);
-      sdr_solve_kernel<<<(unsigned)in->batch, kSdrSolveThreads, 0, stream>>>(partial, p.nsuper, energy, in->batch, sdr_out); }
+      sdr_solve_kernel<<<(unsigned)in->batch, kSdrSolveThreads, 0, stream>>>(partial, nsuper, energy, in->batch, sdr_out); }
     FSEM_LAUNCHED();
     return FSEM_OK;
 }
