@@ -1256,7 +1256,10 @@ extern "C" int fsem_sdr_score_f32(const fsem_batch_t* in, float* sdr_out, void* 
             in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, p.nsuper, partial);
     } else {
         FSEM_CUDA(cudaFuncSetAttribute(sdr_corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcDynSmem));
-        const int vec4 = rows_vec4(in->clean, in->deg, in->stride, sizeof(float)) ? 1 : 0;
+        // 2: rows 32-byte aligned (256-bit loads), 1: 16-byte aligned, 0: scalar loads
+        const bool a32 = ((reinterpret_cast<uintptr_t>(in->clean) | reinterpret_cast<uintptr_t>(in->deg)) & 31u) == 0 &&
+                         in->stride % 8 == 0;
+        const int vec4 = a32 ? 2 : (rows_vec4(in->clean, in->deg, in->stride, sizeof(float)) ? 1 : 0);
         nsuper = 1;
         ProfScope prof_(K_SDR_CORR, stream);
         sdr_corr_tc_kernel<<<(unsigned)(4 * in->batch), kTcThreads, kTcDynSmem, stream>>>(

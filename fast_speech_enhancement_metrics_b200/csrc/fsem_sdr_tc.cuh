@@ -33,13 +33,15 @@ constexpr int kTcK = 16;                  // rows m per k-step (UMMA K for bf16)
 constexpr int kTcN = 384;                 // columns j per CTA: 256 lags + 128
 constexpr int kTcLagsPerCta = 256;
 constexpr int kTcStages = 4;
-constexpr int kTcThreads = 256;
+constexpr int kTcProducers = 512;         // 16 producer warps build the operand tiles (and run the epilogue)
+constexpr int kTcUnits = 1024 / kTcProducers;   // 8-sample units per producer thread and k-step
+constexpr int kTcThreads = kTcProducers + 32;   // + one warp whose lane 0 issues the tcgen05.mma
 constexpr int kTcCore = 128;              // bytes of a core matrix: 8 k-rows x 16 bytes (8 bf16 along MN)
 constexpr int kTcABytes = 2 * (kTcM / 8) * kTcCore;          // [k1 = 2][mn1 = 16]      4096
 constexpr int kTcBBytes = 2 * (kTcN / 8) * kTcCore;          // [k1 = 2][mn1 = 48]     12288
 constexpr int kTcStageBytes = 2 * kTcABytes + 2 * kTcBBytes; // A_hi | A_lo | B_hi | B_lo   32768
 constexpr int kTcTmemCols = 512;
-constexpr size_t kTcDynSmem = (size_t)kTcStages * kTcStageBytes + 8 * kTcLagsPerCta * sizeof(float) + 1024;
+constexpr size_t kTcDynSmem = (size_t)kTcStages * kTcStageBytes + (kTcProducers / 32) * kTcLagsPerCta * sizeof(float) + 1024;
 
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     // cute::UMMA::SmemDescriptor: start address [0,14), leading byte offset [16,30), stride byte offset [32,46) (all
@@ -61,6 +63,9 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t adesc, ui
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -85,7 +90,8 @@ sdr_corr_tc_kernel(const float* __restrict__ clean, const float* __restrict__ de
                    int64_t batch, int64_t n, int64_t stride, int vec4,
                    double* __restrict__ partial /* [batch][1][2][512] */) {
     extern __shared__ __align__(1024) unsigned char s_tc[];
-    __shared__ __align__(8) unsigned long long s_empty[kTcStages];
+    __shared__ __align__(8) unsigned long long s_empty[kTcStages];   // stage free again: tcgen05.commit of the MMAs that read it
+    __shared__ __align__(8) unsigned long long s_full[kTcStages];    // stage built: one arrival per producer warp
     __shared__ __align__(8) unsigned long long s_done;
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -99,15 +105,19 @@ sdr_corr_tc_kernel(const float* __restrict__ clean, const float* __restrict__ de
     const uint32_t smem0 = smem_u32(s_tc);
 
     if (tid == 0) {
-        for (int s = 0; s < kTcStages; ++s) mbar_init(smem_u32(&s_empty[s]), 1);
+        for (int s = 0; s < kTcStages; ++s) {
+            mbar_init(smem_u32(&s_empty[s]), 1);
+            mbar_init(smem_u32(&s_full[s]), kTcProducers / 32);
+        }
         mbar_init(smem_u32(&s_done), 1);
         mbar_fence_init();
     }
-    if (warp == 0) {                                   // one warp allocates the accumulator columns
+    const bool is_mma_warp = warp == kTcProducers / 32;
+    if (is_mma_warp) {                                 // the MMA warp allocates (and later frees) the accumulator columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kTcTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    for (int i = tid; i < 8 * kTcLagsPerCta; i += kTcThreads) racc[i] = 0.f;
+    for (int i = tid; i < (kTcProducers / 32) * kTcLagsPerCta; i += kTcThreads) racc[i] = 0.f;
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -118,46 +128,89 @@ sdr_corr_tc_kernel(const float* __restrict__ clean, const float* __restrict__ de
     constexpr uint32_t kIdesc256 = umma_idesc_bf16_mn(kTcM, 256);
     constexpr uint32_t kIdesc128 = umma_idesc_bf16_mn(kTcM, 128);
 
-    for (int s = 0; s < ksteps; ++s) {
+    // Per-thread units of a k-step (fixed for the whole kernel): unit q -> (A | B, core-matrix row k0, group mn1, k1)
+    int u_off[kTcUnits];   // byte offset of the unit's 16-byte row inside its tile
+    int u_t[kTcUnits];     // sample index of the unit's first sample relative to 128 * m0
+    bool u_a[kTcUnits];
+#pragma unroll
+    for (int q = 0; q < kTcUnits; ++q) {
+        const int u = (tid & (kTcProducers - 1)) + kTcProducers * q;    // 0..1023: A units first, then B units
+        const bool is_a = u < 256;
+        const int ub = is_a ? u : u - 256;
+        const int k0 = ub & 7;
+        const int rest = ub >> 3;
+        const int groups = is_a ? kTcM / 8 : kTcN / 8;                  // core matrices along MN
+        const int k1 = rest / groups, mn1 = rest - k1 * groups;
+        // tile layout [k1][mn1] core matrices, 16-byte row k0 inside: the 8 lanes of a quarter-warp (k0 = 0..7, same
+        // mn1) write one contiguous core matrix -> conflict-free
+        u_off[q] = (k1 * groups + mn1) * kTcCore + k0 * 16;
+        u_t[q] = kTcM * (8 * k1 + k0) + 8 * mn1 + (is_a ? 0 : kTcLagsPerCta * half);
+        u_a[q] = is_a;
+    }
+    // Global loads run TWO k-steps ahead in two register sets: fence.proxy.async (needed before the tensor core may
+    // read the tiles) waits for the thread's outstanding loads, so loads issued in the same iteration as the fence
+    // would be serialised with it (measured: the fence was the top stall).  With one CTA of 8 warps per SM (the
+    // accumulator takes 384 of the 512 TMEM columns) nothing else hides their latency.
+    auto load_step = [&](int s, float (&v)[kTcUnits][8]) {
+        const int m0 = s * kTcK;
+#pragma unroll
+        for (int q = 0; q < kTcUnits; ++q) {
+            const int t0 = kTcM * m0 + u_t[q];
+            const float* __restrict__ src = (u_a[q] ? c : x) + t0;
+            if (vec4 == 2 && t0 + 8 <= len) {
+                // one 256-bit load (sm_100: LDG.E.256): the 4 lanes that share a row fetch one whole 128-byte line per
+                // instruction (two 128-bit loads per lane touch every line twice, 16 bytes per lane and 32 bytes apart:
+                // measured 32 LSU wavefronts per warp instruction)
+                asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                             : "=f"(v[q][0]), "=f"(v[q][1]), "=f"(v[q][2]), "=f"(v[q][3]), "=f"(v[q][4]), "=f"(v[q][5]),
+                               "=f"(v[q][6]), "=f"(v[q][7]) : "l"(src));
+            } else if (vec4 && t0 + 8 <= len) {
+                const float4 p0 = __ldg(reinterpret_cast<const float4*>(src));
+                const float4 p1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                v[q][0] = p0.x; v[q][1] = p0.y; v[q][2] = p0.z; v[q][3] = p0.w;
+                v[q][4] = p1.x; v[q][5] = p1.y; v[q][6] = p1.z; v[q][7] = p1.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[q][e] = (t0 + e < len) ? __ldg(src + e) : 0.f;
+            }
+        }
+    };
+    // Producers and the MMA warp are decoupled by mbarriers (no CTA-wide barrier per k-step): a producer warp that has
+    // stored its part of a stage makes it visible to the async proxy, arrives on full[stage] and moves on -- up to
+    // kTcStages k-steps ahead of the tensor core; tcgen05.commit on empty[stage] hands the stage back.
+    auto produce = [&](int s, float (&v)[kTcUnits][8]) {
         const int stage = s % kTcStages;
+        uint4 hi[kTcUnits], lo[kTcUnits];
+#pragma unroll
+        for (int q = 0; q < kTcUnits; ++q) split_bf16x8(v[q], hi[q], lo[q]);
         if (s >= kTcStages)                                             // the MMAs that read this stage have completed
             mbar_wait(smem_u32(&s_empty[stage]), (uint32_t)((s / kTcStages - 1) & 1));
         unsigned char* st = s_tc + (size_t)stage * kTcStageBytes;
-        const int m0 = s * kTcK;
-        // ---- build the four operand tiles of this k-step: unit = 8 consecutive samples of one row
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int u = tid + kTcThreads * q;                         // 0..1023: A units first, then B units
-            const bool is_a = u < 256;
-            const int ub = is_a ? u : u - 256;
-            const int k0 = ub & 7;
-            const int rest = ub >> 3;
-            const int groups = is_a ? kTcM / 8 : kTcN / 8;              // core matrices along MN
-            const int k1 = rest / groups, mn1 = rest - k1 * groups;
-            const int t0 = kTcM * (m0 + 8 * k1 + k0) + 8 * mn1 + (is_a ? 0 : kTcLagsPerCta * half);
-            const float* __restrict__ src = (is_a ? c : x) + t0;
-            float v[8];
-            if (vec4 && t0 + 8 <= len) {
-                const float4 p0 = __ldg(reinterpret_cast<const float4*>(src));
-                const float4 p1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
-                v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = (t0 + e < len) ? __ldg(src + e) : 0.f;
-            }
-            uint4 hi, lo;
-            split_bf16x8(v, hi, lo);
-            // tile layout [k1][mn1] core matrices, 16-byte row k0 inside: the 8 lanes of a quarter-warp (k0 = 0..7, same
-            // mn1) write one contiguous core matrix -> conflict-free
-            const int off = (k1 * groups + mn1) * kTcCore + k0 * 16;
-            unsigned char* base = st + (is_a ? 0 : 2 * kTcABytes);
-            const int lo_off = is_a ? kTcABytes : kTcBBytes;
-            *reinterpret_cast<uint4*>(base + off) = hi;
-            *reinterpret_cast<uint4*>(base + lo_off + off) = lo;
+        for (int q = 0; q < kTcUnits; ++q) {
+            unsigned char* base = st + (u_a[q] ? 0 : 2 * kTcABytes);
+            const int lo_off = u_a[q] ? kTcABytes : kTcBBytes;
+            *reinterpret_cast<uint4*>(base + u_off[q]) = hi[q];
+            *reinterpret_cast<uint4*>(base + lo_off + u_off[q]) = lo[q];
         }
         fence_proxy_async();                                            // generic-proxy stores -> visible to the tensor core
-        __syncthreads();
-        if (tid == 0) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s_full[stage]));
+        if (s + 2 < ksteps) load_step(s + 2, v);                        // after the fence (it would wait for them); lands
+                                                                        // while the other register set is processed
+    };
+    if (!is_mma_warp) {
+        float va[kTcUnits][8], vb[kTcUnits][8];
+        if (ksteps > 0) load_step(0, va);
+        if (ksteps > 1) load_step(1, vb);
+        for (int s = 0; s < ksteps; s += 2) {
+            produce(s, va);
+            if (s + 1 < ksteps) produce(s + 1, vb);
+        }
+    } else if (lane == 0) {
+        for (int s = 0; s < ksteps; ++s) {
+            const int stage = s % kTcStages;
+            mbar_wait(smem_u32(&s_full[stage]), (uint32_t)((s / kTcStages) & 1));
             tcgen05_fence_after();
             const uint32_t sa = smem0 + stage * kTcStageBytes;
             const uint32_t a_hi = sa, a_lo = sa + kTcABytes, b_hi = sa + 2 * kTcABytes, b_lo = b_hi + kTcBBytes;
@@ -175,16 +228,20 @@ sdr_corr_tc_kernel(const float* __restrict__ clean, const float* __restrict__ de
             if (s + 1 == ksteps) umma_commit(smem_u32(&s_done));
         }
     }
-    if (ksteps > 0) {
+    __syncwarp();
+    if (ksteps > 0 && !is_mma_warp) {
         mbar_wait(smem_u32(&s_done), 0);
         tcgen05_fence_after();
-        // ---- epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 (rows i) and the columns [192 (w / 4), +192)
+        // ---- epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 (rows i) and the columns [kCols (w / 4), + kCols)
+        constexpr int kParts = kTcProducers / 128;                      // column parts (4 with 16 producer warps)
+        constexpr int kCols = kTcN / kParts;                            // 96
+        static_assert(kCols % 32 == 0, "column parts are read in chunks of 32");
         const int quad = warp & 3;
         const int i_row = 32 * quad + lane;
         float* mine = racc + warp * kTcLagsPerCta;
 #pragma unroll 1
-        for (int cb = 0; cb < 6; ++cb) {
-            const int c0 = 192 * (warp >> 2) + 32 * cb;
+        for (int cb = 0; cb < kCols / 32; ++cb) {
+            const int c0 = kCols * (warp >> 2) + 32 * cb;
             uint32_t r[32];
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -205,13 +262,13 @@ sdr_corr_tc_kernel(const float* __restrict__ clean, const float* __restrict__ de
     }
     tcgen05_fence_before();
     __syncthreads();
-    {   // fixed-order sum of the eight per-warp arrays -> the double partials of sdr_solve_kernel (nsuper = 1)
+    if (tid < kTcLagsPerCta) {   // fixed-order sum of the eight per-warp arrays -> the double partials of sdr_solve_kernel
         float acc = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) acc += racc[w * kTcLagsPerCta + tid];
+        for (int w = 0; w < kTcProducers / 32; ++w) acc += racc[w * kTcLagsPerCta + tid];
         partial[(item * 2 + corr) * (int64_t)512 + kTcLagsPerCta * half + tid] = (double)acc;
     }
-    if (warp == 0) {
+    if (is_mma_warp) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTcTmemCols));
     }
