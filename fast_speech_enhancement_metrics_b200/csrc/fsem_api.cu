@@ -1211,6 +1211,39 @@ extern "C" int fsem_pesq_stoi_score_f32(fsem_pesq_ctx_t* pctx, fsem_stoi_ctx_t* 
 // SDR: fast_se_metrics/SDR.py:52-97
 // ================================================================================================
 namespace {
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TensorMapEncodeFn tensor_map_encoder() {
+    static TensorMapEncodeFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<TensorMapEncodeFn>(p);
+    }();
+    return fn;
+}
+// [item][row m][sample t] view of a [batch, stride] float buffer with rows of 128 samples that overlap (dim 0 is
+// kTcMapDim0 wide): address = base + 4 t + 512 m + 4 stride item.  Boxes are box0 x 16 x 1.
+bool make_sdr_tensor_map(CUtensorMap* map, const float* base, int64_t batch, int64_t n, int64_t stride, int box0) {
+    TensorMapEncodeFn enc = tensor_map_encoder();
+    if (!enc) return false;
+    const int64_t rows = (n - kTcMapDim0) / kTcM + 1;             // rows whose widest box stays inside the item's n samples
+    if (rows < kTcK) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)kTcMapDim0, (cuuint64_t)rows, (cuuint64_t)batch};
+    const cuuint64_t gstride[2] = {(cuuint64_t)kTcM * sizeof(float), (cuuint64_t)stride * sizeof(float)};
+    const cuuint32_t box[3] = {(cuuint32_t)box0, (cuuint32_t)kTcK, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstride, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+}  // namespace
+
+namespace {
 struct SdrPlan { int nsuper; size_t off_energy, off_partial, total; };
 SdrPlan sdr_plan(int64_t batch, int64_t n) {
     SdrPlan p{};
@@ -1256,14 +1289,21 @@ extern "C" int fsem_sdr_score_f32(const fsem_batch_t* in, float* sdr_out, void* 
             in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, p.nsuper, partial);
     } else {
         FSEM_CUDA(cudaFuncSetAttribute(sdr_corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcDynSmem));
-        // 2: rows 32-byte aligned (256-bit loads), 1: 16-byte aligned, 0: scalar loads
-        const bool a32 = ((reinterpret_cast<uintptr_t>(in->clean) | reinterpret_cast<uintptr_t>(in->deg)) & 31u) == 0 &&
-                         in->stride % 8 == 0;
-        const int vec4 = a32 ? 2 : (rows_vec4(in->clean, in->deg, in->stride, sizeof(float)) ? 1 : 0);
+        // TMA tensor maps over the two signal buffers as [item][row of 128 samples, overlapping][sample]; they need
+        // 16-byte aligned rows.  Otherwise (and for the last one or two k-steps of every item) the kernel reads global
+        // memory directly.
+        CUtensorMap map_a{}, map_bc{}, map_bd{};
+        static const bool no_tma = [] { const char* e = getenv("FSEM_SDR_NO_TMA"); return e && e[0] == '1'; }();
+        int use_tma = !no_tma && rows_vec4(in->clean, in->deg, in->stride, sizeof(float)) && in->n >= kTcMapDim0 ? 1 : 0;
+        if (use_tma) {
+            use_tma = make_sdr_tensor_map(&map_a, in->clean, in->batch, in->n, in->stride, kTcBoxA) &&
+                      make_sdr_tensor_map(&map_bc, in->clean, in->batch, in->n, in->stride, kTcBoxB) &&
+                      make_sdr_tensor_map(&map_bd, in->deg, in->batch, in->n, in->stride, kTcBoxB) ? 1 : 0;
+        }
         nsuper = 1;
         ProfScope prof_(K_SDR_CORR, stream);
         sdr_corr_tc_kernel<<<(unsigned)(4 * in->batch), kTcThreads, kTcDynSmem, stream>>>(
-            in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, vec4, partial);
+            in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, use_tma, map_a, map_bc, map_bd, partial);
     }
     FSEM_LAUNCHED();
     { ProfScope prof_(K_SDR_SOLVE, stream);

@@ -22,6 +22,7 @@
 // (tcgen05.ld 32x32b) and adds G[i][j] into its private lag array at l = j - i; the eight arrays are summed in a fixed
 // order (deterministic) into the double partials the Levinson kernel reads.
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 
 #include "fsem_common.cuh"
@@ -32,16 +33,15 @@ constexpr int kTcM = 128;                 // i values per row of time (UMMA M)
 constexpr int kTcK = 16;                  // rows m per k-step (UMMA K for bf16)
 constexpr int kTcN = 384;                 // columns j per CTA: 256 lags + 128
 constexpr int kTcLagsPerCta = 256;
-constexpr int kTcStages = 4;
+constexpr int kTcStages = 3;
 constexpr int kTcProducers = 512;         // 16 producer warps build the operand tiles (and run the epilogue)
 constexpr int kTcUnits = 1024 / kTcProducers;   // 8-sample units per producer thread and k-step
-constexpr int kTcThreads = kTcProducers + 32;   // + one warp whose lane 0 issues the tcgen05.mma
+constexpr int kTcThreads = kTcProducers + 64;   // + one warp whose lane 0 issues the tcgen05.mma + one warp that issues the bulk copies
 constexpr int kTcCore = 128;              // bytes of a core matrix: 8 k-rows x 16 bytes (8 bf16 along MN)
 constexpr int kTcABytes = 2 * (kTcM / 8) * kTcCore;          // [k1 = 2][mn1 = 16]      4096
 constexpr int kTcBBytes = 2 * (kTcN / 8) * kTcCore;          // [k1 = 2][mn1 = 48]     12288
 constexpr int kTcStageBytes = 2 * kTcABytes + 2 * kTcBBytes; // A_hi | A_lo | B_hi | B_lo   32768
 constexpr int kTcTmemCols = 512;
-constexpr size_t kTcDynSmem = (size_t)kTcStages * kTcStageBytes + (kTcProducers / 32) * kTcLagsPerCta * sizeof(float) + 1024;
 
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     // cute::UMMA::SmemDescriptor: start address [0,14), leading byte offset [16,30), stride byte offset [32,46) (all
@@ -85,13 +85,42 @@ __device__ __forceinline__ void split_bf16x8(const float (&x)[8], uint4& hi, uin
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// Raw float32 staging of one k-step, filled by THREE TMA tensor copies (cp.async.bulk.tensor.3d: no LSU traffic, one
+// elected thread): the 16 rows of the A segment (128 samples) and of the two halves of the B segment (2 x 192 samples).
+// The tensor map views a signal buffer as [item][row m][sample t] with OVERLAPPING rows (row pitch 128 samples); the
+// boxes are 4 samples wider than needed (132 / 196 floats) so that the row pitch in shared memory is = 4 (mod 32) words:
+// the eight lanes of a quarter-warp, which read eight different rows, then hit different banks.
+constexpr int kTcBoxA = kTcM + 4;                              // 132 floats
+constexpr int kTcBoxB = kTcN / 2 + 4;                          // 196 floats
+constexpr int kTcRawAPitch = kTcBoxA * 4;                      // 528 bytes
+constexpr int kTcRawBPitch = kTcBoxB * 4;                      // 784 bytes
+constexpr int kTcRawABytes = kTcK * kTcRawAPitch;              // 8448   (multiple of 128: TMA destination alignment)
+constexpr int kTcRawBBytes = kTcK * kTcRawBPitch;              // 12544
+constexpr int kTcRawBytes = kTcRawABytes + 2 * kTcRawBBytes;   // 33536
+static_assert(kTcRawABytes % 128 == 0 && kTcRawBBytes % 128 == 0, "TMA destinations must be 128-byte aligned");
+constexpr int kTcRawStages = 3;
+constexpr int kTcRaccBytes = (kTcProducers / 32) * kTcLagsPerCta * 4;
+constexpr size_t kTcDynSmem = (size_t)kTcStages * kTcStageBytes + (size_t)kTcRawStages * kTcRawBytes + kTcRaccBytes + 1024;
+constexpr int kTcMapDim0 = 256 + kTcN / 2 + kTcBoxB;           // 644: largest sample coordinate a box may touch + 1
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1)
 sdr_corr_tc_kernel(const float* __restrict__ clean, const float* __restrict__ deg, const int32_t* __restrict__ lengths,
-                   int64_t batch, int64_t n, int64_t stride, int vec4,
+                   int64_t batch, int64_t n, int64_t stride, int use_tma,
+                   const __grid_constant__ CUtensorMap map_a,      // clean signal, box 132 x 16
+                   const __grid_constant__ CUtensorMap map_bc,     // clean signal, box 196 x 16
+                   const __grid_constant__ CUtensorMap map_bd,     // degraded signal, box 196 x 16
                    double* __restrict__ partial /* [batch][1][2][512] */) {
     extern __shared__ __align__(1024) unsigned char s_tc[];
-    __shared__ __align__(8) unsigned long long s_empty[kTcStages];   // stage free again: tcgen05.commit of the MMAs that read it
-    __shared__ __align__(8) unsigned long long s_full[kTcStages];    // stage built: one arrival per producer warp
+    __shared__ __align__(8) unsigned long long s_empty[kTcStages];   // tile stage free again: tcgen05.commit of the MMAs that read it
+    __shared__ __align__(8) unsigned long long s_full[kTcStages];    // tile stage built: one arrival per producer warp
+    __shared__ __align__(8) unsigned long long s_raw_full[kTcRawStages];    // raw rows landed (bulk-copy transaction bytes)
+    __shared__ __align__(8) unsigned long long s_raw_empty[kTcRawStages];   // raw rows consumed: one arrival per producer warp
     __shared__ __align__(8) unsigned long long s_done;
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -101,7 +130,8 @@ sdr_corr_tc_kernel(const float* __restrict__ clean, const float* __restrict__ de
     const int len = item_length(lengths, item, n);
     const float* __restrict__ c = clean + item * stride;
     const float* __restrict__ x = (corr ? deg : clean) + item * stride;
-    float* racc = reinterpret_cast<float*>(s_tc + (size_t)kTcStages * kTcStageBytes);     // [8 warps][256 lags]
+    unsigned char* raw0 = s_tc + (size_t)kTcStages * kTcStageBytes;
+    float* racc = reinterpret_cast<float*>(raw0 + (size_t)kTcRawStages * kTcRawBytes);     // [producer warps][256 lags]
     const uint32_t smem0 = smem_u32(s_tc);
 
     if (tid == 0) {
@@ -109,10 +139,15 @@ sdr_corr_tc_kernel(const float* __restrict__ clean, const float* __restrict__ de
             mbar_init(smem_u32(&s_empty[s]), 1);
             mbar_init(smem_u32(&s_full[s]), kTcProducers / 32);
         }
+        for (int s = 0; s < kTcRawStages; ++s) {
+            mbar_init(smem_u32(&s_raw_full[s]), 1);
+            mbar_init(smem_u32(&s_raw_empty[s]), kTcProducers / 32);
+        }
         mbar_init(smem_u32(&s_done), 1);
         mbar_fence_init();
     }
     const bool is_mma_warp = warp == kTcProducers / 32;
+    const bool is_copy_warp = warp == kTcProducers / 32 + 1;
     if (is_mma_warp) {                                 // the MMA warp allocates (and later frees) the accumulator columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kTcTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -125,111 +160,130 @@ sdr_corr_tc_kernel(const float* __restrict__ clean, const float* __restrict__ de
 
     const int rows = (len + kTcM - 1) / kTcM;                          // rows m with at least one sample
     const int ksteps = (rows + kTcK - 1) / kTcK;
+    // leading k-steps whose 16 rows lie completely inside the signal (A and B segment): staged by bulk copies; the
+    // last one or two k-steps (and everything, for rows that are not 16-byte aligned) read global memory directly
+    int bulk_steps = 0;
+    if (use_tma) {
+        // largest admissible first row m0: all 16 rows inside the item's valid samples AND inside the tensor map (rows
+        // beyond its dim 1 would be zero-filled)
+        const int last_ok = min((len - kTcLagsPerCta * half - kTcN) / kTcM, (int)((n - kTcMapDim0) / kTcM)) - (kTcK - 1);
+        if (len >= kTcLagsPerCta * half + kTcN && last_ok >= 0) bulk_steps = min(ksteps, last_ok / kTcK + 1);
+    }
     constexpr uint32_t kIdesc256 = umma_idesc_bf16_mn(kTcM, 256);
     constexpr uint32_t kIdesc128 = umma_idesc_bf16_mn(kTcM, 128);
 
-    // Per-thread units of a k-step (fixed for the whole kernel): unit q -> (A | B, core-matrix row k0, group mn1, k1)
-    int u_off[kTcUnits];   // byte offset of the unit's 16-byte row inside its tile
-    int u_t[kTcUnits];     // sample index of the unit's first sample relative to 128 * m0
-    bool u_a[kTcUnits];
-#pragma unroll
-    for (int q = 0; q < kTcUnits; ++q) {
-        const int u = (tid & (kTcProducers - 1)) + kTcProducers * q;    // 0..1023: A units first, then B units
-        const bool is_a = u < 256;
-        const int ub = is_a ? u : u - 256;
-        const int k0 = ub & 7;
-        const int rest = ub >> 3;
-        const int groups = is_a ? kTcM / 8 : kTcN / 8;                  // core matrices along MN
-        const int k1 = rest / groups, mn1 = rest - k1 * groups;
-        // tile layout [k1][mn1] core matrices, 16-byte row k0 inside: the 8 lanes of a quarter-warp (k0 = 0..7, same
-        // mn1) write one contiguous core matrix -> conflict-free
-        u_off[q] = (k1 * groups + mn1) * kTcCore + k0 * 16;
-        u_t[q] = kTcM * (8 * k1 + k0) + 8 * mn1 + (is_a ? 0 : kTcLagsPerCta * half);
-        u_a[q] = is_a;
-    }
-    // Global loads run TWO k-steps ahead in two register sets: fence.proxy.async (needed before the tensor core may
-    // read the tiles) waits for the thread's outstanding loads, so loads issued in the same iteration as the fence
-    // would be serialised with it (measured: the fence was the top stall).  With one CTA of 8 warps per SM (the
-    // accumulator takes 384 of the 512 TMEM columns) nothing else hides their latency.
-    auto load_step = [&](int s, float (&v)[kTcUnits][8]) {
-        const int m0 = s * kTcK;
-#pragma unroll
-        for (int q = 0; q < kTcUnits; ++q) {
-            const int t0 = kTcM * m0 + u_t[q];
-            const float* __restrict__ src = (u_a[q] ? c : x) + t0;
-            if (vec4 == 2 && t0 + 8 <= len) {
-                // one 256-bit load (sm_100: LDG.E.256): the 4 lanes that share a row fetch one whole 128-byte line per
-                // instruction (two 128-bit loads per lane touch every line twice, 16 bytes per lane and 32 bytes apart:
-                // measured 32 LSU wavefronts per warp instruction)
-                asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                             : "=f"(v[q][0]), "=f"(v[q][1]), "=f"(v[q][2]), "=f"(v[q][3]), "=f"(v[q][4]), "=f"(v[q][5]),
-                               "=f"(v[q][6]), "=f"(v[q][7]) : "l"(src));
-            } else if (vec4 && t0 + 8 <= len) {
-                const float4 p0 = __ldg(reinterpret_cast<const float4*>(src));
-                const float4 p1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
-                v[q][0] = p0.x; v[q][1] = p0.y; v[q][2] = p0.z; v[q][3] = p0.w;
-                v[q][4] = p1.x; v[q][5] = p1.y; v[q][6] = p1.z; v[q][7] = p1.w;
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[q][e] = (t0 + e < len) ? __ldg(src + e) : 0.f;
+    if (is_copy_warp) {
+        // ---- copy warp: one lane issues the three tensor copies of every staged k-step
+        if (lane == 0) {
+            const CUtensorMap* mb = corr ? &map_bd : &map_bc;
+            for (int s = 0; s < bulk_steps; ++s) {
+                const int rs = s % kTcRawStages;
+                if (s >= kTcRawStages) mbar_wait(smem_u32(&s_raw_empty[rs]), (uint32_t)((s / kTcRawStages - 1) & 1));
+                const uint32_t bar = smem_u32(&s_raw_full[rs]);
+                mbar_arrive_expect_tx(bar, kTcRawBytes);
+                const uint32_t dst = smem_u32(raw0 + (size_t)rs * kTcRawBytes);
+                const int m0 = s * kTcK;
+                tma_load_3d(dst, &map_a, 0, m0, (int)item, bar);
+                tma_load_3d(dst + kTcRawABytes, mb, kTcLagsPerCta * half, m0, (int)item, bar);
+                tma_load_3d(dst + kTcRawABytes + kTcRawBBytes, mb, kTcLagsPerCta * half + kTcN / 2, m0, (int)item, bar);
             }
         }
-    };
-    // Producers and the MMA warp are decoupled by mbarriers (no CTA-wide barrier per k-step): a producer warp that has
-    // stored its part of a stage makes it visible to the async proxy, arrives on full[stage] and moves on -- up to
-    // kTcStages k-steps ahead of the tensor core; tcgen05.commit on empty[stage] hands the stage back.
-    auto produce = [&](int s, float (&v)[kTcUnits][8]) {
-        const int stage = s % kTcStages;
-        uint4 hi[kTcUnits], lo[kTcUnits];
+    } else if (is_mma_warp) {
+        if (lane == 0) {
+            for (int s = 0; s < ksteps; ++s) {
+                const int stage = s % kTcStages;
+                mbar_wait(smem_u32(&s_full[stage]), (uint32_t)((s / kTcStages) & 1));
+                tcgen05_fence_after();
+                const uint32_t sa = smem0 + stage * kTcStageBytes;
+                const uint32_t a_hi = sa, a_lo = sa + kTcABytes, b_hi = sa + 2 * kTcABytes, b_lo = b_hi + kTcBBytes;
+                constexpr uint32_t kALbo = (kTcM / 8) * kTcCore, kBLbo = (kTcN / 8) * kTcCore, kSbo = kTcCore;
+                const uint32_t pa[3] = {a_hi, a_hi, a_lo};
+                const uint32_t pb[3] = {b_hi, b_lo, b_hi};
 #pragma unroll
-        for (int q = 0; q < kTcUnits; ++q) split_bf16x8(v[q], hi[q], lo[q]);
-        if (s >= kTcStages)                                             // the MMAs that read this stage have completed
-            mbar_wait(smem_u32(&s_empty[stage]), (uint32_t)((s / kTcStages - 1) & 1));
-        unsigned char* st = s_tc + (size_t)stage * kTcStageBytes;
+                for (int p = 0; p < 3; ++p) {
+                    const uint32_t acc = (s > 0 || p > 0) ? 1u : 0u;
+                    const uint64_t ad = umma_smem_desc(pa[p], kALbo, kSbo);
+                    umma_bf16_ss(tmem, ad, umma_smem_desc(pb[p], kBLbo, kSbo), kIdesc256, acc);
+                    umma_bf16_ss(tmem + 256, ad, umma_smem_desc(pb[p] + 32 * kTcCore, kBLbo, kSbo), kIdesc128, acc);
+                }
+                umma_commit(smem_u32(&s_empty[stage]));                 // arrives when these MMAs have finished
+                if (s + 1 == ksteps) umma_commit(smem_u32(&s_done));
+            }
+        }
+    } else {
+        // ---- producers.  Units of a thread (fixed): unit q -> (A | B, core-matrix row k0, group mn1, k1)
+        int u_off[kTcUnits];   // byte offset of the unit's 16-byte row inside its tile
+        int u_raw[kTcUnits];   // byte offset of the unit's 8 samples inside a raw stage
+        int u_t[kTcUnits];     // sample index of the unit's first sample relative to 128 * m0
+        bool u_a[kTcUnits];
 #pragma unroll
         for (int q = 0; q < kTcUnits; ++q) {
-            unsigned char* base = st + (u_a[q] ? 0 : 2 * kTcABytes);
-            const int lo_off = u_a[q] ? kTcABytes : kTcBBytes;
-            *reinterpret_cast<uint4*>(base + u_off[q]) = hi[q];
-            *reinterpret_cast<uint4*>(base + lo_off + u_off[q]) = lo[q];
+            const int u = tid + kTcProducers * q;                       // 0..1023: A units first, then B units
+            const bool is_a = u < 256;
+            const int ub = is_a ? u : u - 256;
+            const int k0 = ub & 7;
+            const int rest = ub >> 3;
+            const int groups = is_a ? kTcM / 8 : kTcN / 8;              // core matrices along MN
+            const int k1 = rest / groups, mn1 = rest - k1 * groups;
+            // tile layout [k1][mn1] core matrices, 16-byte row k0 inside: the 8 lanes of a quarter-warp (k0 = 0..7, same
+            // mn1) write one contiguous core matrix -> conflict-free
+            u_off[q] = (k1 * groups + mn1) * kTcCore + k0 * 16;
+            u_t[q] = kTcM * (8 * k1 + k0) + 8 * mn1 + (is_a ? 0 : kTcLagsPerCta * half);
+            u_raw[q] = is_a ? (8 * k1 + k0) * kTcRawAPitch + 32 * mn1
+                            : (mn1 < kTcN / 16 ? kTcRawABytes + (8 * k1 + k0) * kTcRawBPitch + 32 * mn1
+                                               : kTcRawABytes + kTcRawBBytes + (8 * k1 + k0) * kTcRawBPitch + 32 * (mn1 - kTcN / 16));
+            u_a[q] = is_a;
         }
-        fence_proxy_async();                                            // generic-proxy stores -> visible to the tensor core
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&s_full[stage]));
-        if (s + 2 < ksteps) load_step(s + 2, v);                        // after the fence (it would wait for them); lands
-                                                                        // while the other register set is processed
-    };
-    if (!is_mma_warp) {
-        float va[kTcUnits][8], vb[kTcUnits][8];
-        if (ksteps > 0) load_step(0, va);
-        if (ksteps > 1) load_step(1, vb);
-        for (int s = 0; s < ksteps; s += 2) {
-            produce(s, va);
-            if (s + 1 < ksteps) produce(s + 1, vb);
-        }
-    } else if (lane == 0) {
         for (int s = 0; s < ksteps; ++s) {
             const int stage = s % kTcStages;
-            mbar_wait(smem_u32(&s_full[stage]), (uint32_t)((s / kTcStages) & 1));
-            tcgen05_fence_after();
-            const uint32_t sa = smem0 + stage * kTcStageBytes;
-            const uint32_t a_hi = sa, a_lo = sa + kTcABytes, b_hi = sa + 2 * kTcABytes, b_lo = b_hi + kTcBBytes;
-            constexpr uint32_t kALbo = (kTcM / 8) * kTcCore, kBLbo = (kTcN / 8) * kTcCore, kSbo = kTcCore;
-            const uint32_t pa[3] = {a_hi, a_hi, a_lo};
-            const uint32_t pb[3] = {b_hi, b_lo, b_hi};
+            float v[kTcUnits][8];
+            if (s < bulk_steps) {
+                const int rs = s % kTcRawStages;
+                mbar_wait(smem_u32(&s_raw_full[rs]), (uint32_t)((s / kTcRawStages) & 1));
+                const unsigned char* raw = raw0 + (size_t)rs * kTcRawBytes;
 #pragma unroll
-            for (int p = 0; p < 3; ++p) {
-                const uint32_t acc = (s > 0 || p > 0) ? 1u : 0u;
-                const uint64_t ad = umma_smem_desc(pa[p], kALbo, kSbo);
-                umma_bf16_ss(tmem, ad, umma_smem_desc(pb[p], kBLbo, kSbo), kIdesc256, acc);
-                umma_bf16_ss(tmem + 256, ad, umma_smem_desc(pb[p] + 32 * kTcCore, kBLbo, kSbo), kIdesc128, acc);
+                for (int q = 0; q < kTcUnits; ++q) {
+                    const float4 p0 = *reinterpret_cast<const float4*>(raw + u_raw[q]);
+                    const float4 p1 = *reinterpret_cast<const float4*>(raw + u_raw[q] + 16);
+                    v[q][0] = p0.x; v[q][1] = p0.y; v[q][2] = p0.z; v[q][3] = p0.w;
+                    v[q][4] = p1.x; v[q][5] = p1.y; v[q][6] = p1.z; v[q][7] = p1.w;
+                }
+            } else {
+                const int m0 = s * kTcK;
+#pragma unroll
+                for (int q = 0; q < kTcUnits; ++q) {
+                    const int t0 = kTcM * m0 + u_t[q];
+                    const float* __restrict__ src = (u_a[q] ? c : x) + t0;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[q][e] = (t0 + e < len) ? __ldg(src + e) : 0.f;
+                }
             }
-            umma_commit(smem_u32(&s_empty[stage]));                     // arrives when these MMAs have finished
-            if (s + 1 == ksteps) umma_commit(smem_u32(&s_done));
+            uint4 hi[kTcUnits], lo[kTcUnits];
+#pragma unroll
+            for (int q = 0; q < kTcUnits; ++q) split_bf16x8(v[q], hi[q], lo[q]);
+            if (s >= kTcStages)                                         // the MMAs that read this stage have completed
+                mbar_wait(smem_u32(&s_empty[stage]), (uint32_t)((s / kTcStages - 1) & 1));
+            unsigned char* st = s_tc + (size_t)stage * kTcStageBytes;
+#pragma unroll
+            for (int q = 0; q < kTcUnits; ++q) {
+                unsigned char* base = st + (u_a[q] ? 0 : 2 * kTcABytes);
+                const int lo_off = u_a[q] ? kTcABytes : kTcBBytes;
+                *reinterpret_cast<uint4*>(base + u_off[q]) = hi[q];
+                *reinterpret_cast<uint4*>(base + lo_off + u_off[q]) = lo[q];
+            }
+            // One proxy fence serves both hand-overs: the generic-proxy tile stores become visible to the tensor core, and
+            // the generic-proxy READS of the raw rows are ordered before the TMA writes that refill them (without it the
+            // refill raced with the reads: results changed from run to run).
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(smem_u32(&s_full[stage]));
+                if (s < bulk_steps) mbar_arrive(smem_u32(&s_raw_empty[s % kTcRawStages]));
+            }
         }
     }
     __syncwarp();
-    if (ksteps > 0 && !is_mma_warp) {
+    if (ksteps > 0 && warp < kTcProducers / 32) {
         mbar_wait(smem_u32(&s_done), 0);
         tcgen05_fence_after();
         // ---- epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 (rows i) and the columns [kCols (w / 4), + kCols)
