@@ -509,6 +509,14 @@ stoi_tob_kernel(const float* __restrict__ clean10k, const float* __restrict__ de
         {
             const int32_t* idx = kept_idx + item * t0max + u;
             const int ta = idx[0] * FSEM_STOI_HOP, tb = idx[1] * FSEM_STOI_HOP, tc = idx[2] * FSEM_STOI_HOP;
+            // Two thirds of a frame's samples were loaded by the previous frame (L1 hits); the new third is kept frame
+            // u + 2, whose latency this warp would wait for.  One prefetch instruction (16 lanes = the 16 lines of kept
+            // frame u + 3, both signals) brings the NEXT frame's new lines into L1 while this frame is transformed -- no
+            // registers, which a register prefetch does not have in this 128-register kernel (tried: 112 bytes of spills).
+            if (w + 1 < item_end && lane < 16) {
+                const float* p = ((lane & 8) ? deg10k : clean10k) + item * sstride + idx[3] * FSEM_STOI_HOP + 32 * (lane & 7);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+            }
             const float* __restrict__ xc = clean10k + item * sstride + 2 * lane;
             const float* __restrict__ xd = deg10k + item * sstride + 2 * lane;
             auto pair = [&](const float* p) -> float2 {
