@@ -43,6 +43,6 @@ class SDR(BaseMetric):
 
     def compute_metric(self, clean_speech, denoised_speech, lengths=None) -> list[dict[str, float]]:
         assert clean_speech is not None                                      # SDR.py:75
-        if not clean_speech.is_cuda:                                         # host tensors (base.py:18)
-            clean_speech, denoised_speech = self._upload(clean_speech, denoised_speech)
+        if not clean_speech.is_cuda:                                        # host tensors (base.py:18): chunked uploads
+            return [{"SDR": v} for v in self._score_host_overlapped(clean_speech, denoised_speech, lengths).tolist()]
         return [{"SDR": v} for v in self.score_tensors(clean_speech, denoised_speech, lengths).cpu().tolist()]

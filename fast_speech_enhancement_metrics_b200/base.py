@@ -147,13 +147,42 @@ class BaseMetric(ABC):
                 C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
         return out[0, :, :L], out[1, :, :L], new_lens
 
-    def _upload(self, clean: torch.Tensor, deg: torch.Tensor):
-        """Host rows -> device rows for the metrics without a chunked host pipeline in the library (LSD, SDR):
-        both copies on the current stream, non-blocking when the host tensors are pinned; 2-byte dtypes cross
-        PCIe as they are and are widened on the device."""
-        clean = clean.to(self.device, non_blocking=True)
-        deg = deg.to(self.device, non_blocking=True)
-        return self._as_f32(clean), self._as_f32(deg)
+    def _score_host_overlapped(self, clean: torch.Tensor, deg: torch.Tensor, lengths=None) -> torch.Tensor:
+        """Host rows -> per-item scores (CPU tensor) for the metrics whose library entry point is device-only (LSD,
+        SDR): the batch is cut into chunks of ~128 MB, chunk k + 1 is uploaded on a copy stream while chunk k is
+        scored on the current stream (the same double-buffered scheme as the library's fsem_score_host pipeline for
+        PESQ / STOI), and all scores come back in ONE device->host copy.  Needs pinned host tensors to overlap;
+        pageable ones still work, serialised by the driver."""
+        b, n = clean.shape
+        per = max(1, min(b, (128 << 20) // max(1, 2 * n * clean.element_size())))
+        lens = None if lengths is None else torch.as_tensor(lengths).to(torch.int32).reshape(-1)
+        cur = torch.cuda.current_stream(self.device)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        copy = self._copy_stream
+        copy.wait_stream(cur)
+        outs = []
+        staged = None
+        starts = list(range(0, b, per))
+
+        def upload(i0):
+            with torch.cuda.stream(copy):
+                c = clean[i0:i0 + per].to(self.device, non_blocking=True)
+                d = deg[i0:i0 + per].to(self.device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            return c, d, ev
+
+        staged = upload(starts[0])
+        for k, i0 in enumerate(starts):
+            c, d, ev = staged
+            if k + 1 < len(starts):
+                staged = upload(starts[k + 1])          # in flight while this chunk is scored
+            cur.wait_event(ev)
+            c.record_stream(cur)
+            d.record_stream(cur)
+            outs.append(self.score_tensors(c, d, None if lens is None else lens[i0:i0 + per]))
+        return torch.cat(outs).cpu()
 
     # ------------------------------------------------------------------ helpers
     def _get_workspace(self, nbytes: int) -> torch.Tensor:

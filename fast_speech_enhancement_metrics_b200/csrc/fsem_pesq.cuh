@@ -558,11 +558,6 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
                 T2 = pesq_num_frames(len2);
             } while (T2 == 0 && item2 + 1 < batch);
         }
-        __syncwarp();                                            // all lanes are done with the slot about to be refilled
-        if (has_next) {
-            if (same_item) issue_half(sn, item, f + 2);
-            else issue_half(sn, item2, 0);
-        }
         // wait for the two halves of the current frame
         mbar_wait(bar0 + 8 * sa, (par >> sa) & 1u);
         mbar_wait(bar0 + 8 * sb, (par >> sb) & 1u);
@@ -587,6 +582,14 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     if (fft_in_index(lane, h, j) >= room) { re[8 * h + j] = 0.f; im[8 * h + j] = 0.f; }
+        }
+        // Refill the free slot now: the frame's samples are in registers, the copy has the whole transform to land, and
+        // the proxy fence inside issue_half only has this frame's shared-memory loads to wait for (at the top of the loop
+        // it also waited for the previous frame's global stores).  The free slot was last read one frame ago.
+        __syncwarp();
+        if (has_next) {
+            if (same_item) issue_half(sn, item, f + 2);
+            else issue_half(sn, item2, 0);
         }
         float ar[8], ai[8], br[8], bi[8];
         warp_fft512<false>(re, im, buf, tw, lane, ar, ai, br, bi);
