@@ -507,6 +507,14 @@ def main():
                 "note": "dominant kernel only (one of the kernels of its metric call): see roofline_call / "
                         "roofline_step for the path; the path is FP32-issue / shared-memory bound (SURVEY 7.2), the "
                         "HBM fraction is reported because the metric asks for it"}
+    # issue / FP32-pipe / LSU utilisation of the dominant kernel from the same round's `ncu --set full` capture (north_star:
+    # "achieved HBM GB/s ... and FP32-pipe utilisation"): the path is bound by these, not by HBM
+    import glob
+    pipe_files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r[0-9][0-9]_ncu_pipes.json")))
+    if pipe_files:
+        pj = json.load(open(pipe_files[-1])).get("kernels", {})
+        if top_name in pj:
+            roofline["pipes"] = dict(pj[top_name], source=os.path.relpath(pipe_files[-1], ROOT))
     # per metric CALL: all kernels of the call against the bytes the call must read
     roofline_call = {}
     for call, prefix in (("PESQ", "pesq_"), ("STOI", "stoi_")):

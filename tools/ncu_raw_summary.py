@@ -42,6 +42,25 @@ def main():
         out.append("")
         out.append("Warp stall reasons (warps per issue-active cycle): " + ", ".join(st))
         out.append("")
+    if "--json" in sys.argv:
+        # per-kernel pipe utilisation for bench.py (roofline.pipes): keys = the library's profiler names
+        import json
+        alias = {"pesq_filter_tiled_kernel": "pesq_filter_kernel", "stoi_resample85_kernel": "stoi_resample_kernel"}
+        keys = {"fp32_fma_pipe_pct": "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+                "alu_pipe_pct": "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+                "issue_active_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active",
+                "lsu_data_pipe_pct": "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+                "dram_pct": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+                "warp_instructions": "smsp__inst_executed.sum"}
+        pipes = {}
+        for vals in rows[2:]:
+            if len(vals) < len(hdr):
+                continue
+            name = vals[ix["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0]
+            name = alias.get(name, name)
+            pipes[name] = {k: float(vals[ix[m]].replace(",", "")) for k, m in keys.items() if m in ix}
+        json.dump({"_comment": "ncu --set full of one step at 8192 x 10 s (tools/gpu_evidence.sh); % of peak", "kernels": pipes},
+                  open(sys.argv[sys.argv.index("--json") + 1], "w"), indent=1)
     txt = "\n".join(out)
     if "--md" in sys.argv:
         open(sys.argv[sys.argv.index("--md") + 1], "w").write(txt + "\n")
