@@ -12,7 +12,7 @@ from .PESQ import PESQ
 from .STOI import STOI
 from .LSD import LSD
 from .SDR import SDR
-from .fused import score_pesq_stoi, score_pesq_stoi_tensors
+from .fused import CapturedScorer, score_pesq_stoi, score_pesq_stoi_tensors
 
-__all__ = ["BaseMetric", "PESQ", "STOI", "LSD", "SDR", "score_pesq_stoi", "score_pesq_stoi_tensors"]
+__all__ = ["BaseMetric", "PESQ", "STOI", "LSD", "SDR", "score_pesq_stoi", "score_pesq_stoi_tensors", "CapturedScorer"]
 __version__ = "0.2.0"

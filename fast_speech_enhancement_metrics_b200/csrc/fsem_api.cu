@@ -234,7 +234,7 @@ struct PesqPlan {
     int64_t n_in, rstride;           // input samples per item; row pitch of the resampled signals
     bool resample;
     bool tiled;                      // lane = signal (tiled kernel) vs thread = (signal, chunk) for tiny batches
-    int tmax, chunk, nchunks;
+    int tmax, tpitch, chunk, nchunks;   // tpitch = round4(tmax): frame pitch of the Bark / disturbance rows (16-byte tiles)
     size_t off_rs, off_rslen, off_z, off_partial, off_bark, off_dist, off_power, off_order, off_fprefix, total;
 };
 
@@ -252,6 +252,7 @@ PesqPlan pesq_plan(const fsem_pesq_ctx* ctx, int64_t batch, int64_t n_in) {
     p.zstride = round_up((n > 0 ? n : 1) + FSEM_PESQ_HOP, 4);
     p.tmax = pesq_num_frames(n);
     if (p.tmax < 1) p.tmax = 1;
+    p.tpitch = (int)round_up(p.tmax, 4);
     // Chunking of the serial IIR pass.  A warp-unit = (32 signals, one chunk) and costs chunk + warm-up sample steps;
     // all units are equal, so the kernel runs in whole "waves" of resident warps.  Pick the chunk count that minimises
     // waves x (chunk + warm-up): enough units to fill the chip, no half-empty last wave, little redundant warm-up.
@@ -281,8 +282,8 @@ PesqPlan pesq_plan(const fsem_pesq_ctx* ctx, int64_t batch, int64_t n_in) {
     p.off_rs = off;      off = align256(off + (p.resample ? sizeof(float) * 2 * batch * p.rstride : 0));
     p.off_rslen = off;   off = align256(off + (p.resample ? sizeof(int32_t) * batch : 0));
     p.off_z = off;       off = align256(off + sizeof(float) * 2 * batch * p.zstride);
-    p.off_bark = off;    off = align256(off + sizeof(float) * 2 * batch * p.tmax * FSEM_PESQ_NBANDS);
-    p.off_dist = off;    off = align256(off + sizeof(float) * 2 * batch * p.tmax);
+    p.off_bark = off;    off = align256(off + sizeof(float) * 2 * batch * p.tpitch * FSEM_PESQ_NBANDS);
+    p.off_dist = off;    off = align256(off + sizeof(float) * 2 * batch * p.tpitch);
     p.off_power = off;   off = align256(off + sizeof(double) * 2 * batch);
     p.off_order = off;   off = align256(off + sizeof(int32_t) * batch);              // variable-length batches only
     p.off_fprefix = off; off = align256(off + sizeof(int64_t) * (batch + 1));
@@ -511,7 +512,7 @@ extern "C" int fsem_pesq_score(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in, int
         if (grid > cap) grid = cap;
         { ProfScope prof_(K_PESQ_SPECTRUM, stream);
           pesq_spectrum_kernel<<<(unsigned)grid, kSpecWarps * 32, kSpecDynSmem, stream>>>(
-              z, p.zstride, in->lengths, fprefix, in->batch, in->n, p.tmax, ctx->d_tab, bark); }
+              z, p.zstride, in->lengths, fprefix, in->batch, in->n, p.tmax, p.tpitch, partial, p.nchunks, ctx->d_tab, bark); }
         FSEM_LAUNCHED();
     }
     {   // kernel C
@@ -519,12 +520,12 @@ extern "C" int fsem_pesq_score(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in, int
           if (in->batch <= ctx->dev.sms)   // cannot fill the SMs anyway: one wide CTA per item, few serial tile rounds
               pesq_bark_kernel<kBarkThreadsWide, kBarkTileWide>
                   <<<(unsigned)in->batch, kBarkThreadsWide, bark_dyn_smem(kBarkTileWide), stream>>>(
-                      bark, partial, p.nchunks, in->lengths, order, in->batch, in->n, p.tmax, ctx->d_tab, dist, mos_out,
+                      bark, partial, p.nchunks, in->lengths, order, in->batch, in->n, p.tpitch, ctx->d_tab, dist, mos_out,
                       status_out, power);
           else
               pesq_bark_kernel<kBarkThreads, kBarkTile>
                   <<<(unsigned)in->batch, kBarkThreads, bark_dyn_smem(kBarkTile), stream>>>(
-                      bark, partial, p.nchunks, in->lengths, order, in->batch, in->n, p.tmax, ctx->d_tab, dist, mos_out,
+                      bark, partial, p.nchunks, in->lengths, order, in->batch, in->n, p.tpitch, ctx->d_tab, dist, mos_out,
                       status_out, power); }
         FSEM_LAUNCHED();
     }
@@ -539,8 +540,9 @@ extern "C" int fsem_pesq_debug_taps(fsem_pesq_ctx_t* ctx, int64_t batch, int64_t
     const char* ws = static_cast<const char*>(workspace);
     if (frames_out) *frames_out = p.tmax;
     if (bark_out)
-        FSEM_CUDA(cudaMemcpyAsync(bark_out, ws + p.off_bark, sizeof(float) * 2 * batch * p.tmax * FSEM_PESQ_NBANDS,
-                                  cudaMemcpyDeviceToDevice, stream));
+        FSEM_CUDA(cudaMemcpy2DAsync(bark_out, sizeof(float) * p.tmax * FSEM_PESQ_NBANDS, ws + p.off_bark,
+                                    sizeof(float) * p.tpitch * FSEM_PESQ_NBANDS, sizeof(float) * p.tmax * FSEM_PESQ_NBANDS,
+                                    (size_t)(2 * batch), cudaMemcpyDeviceToDevice, stream));
     if (power_out)
         FSEM_CUDA(cudaMemcpyAsync(power_out, ws + p.off_power, sizeof(double) * 2 * batch, cudaMemcpyDeviceToDevice,
                                   stream));
@@ -1205,6 +1207,103 @@ extern "C" int fsem_pesq_stoi_score_f32(fsem_pesq_ctx_t* pctx, fsem_stoi_ctx_t* 
                                         size_t ws_pesq_bytes, void* ws_stoi, size_t ws_stoi_bytes, void* stream) {
     return fsem_pesq_stoi_score(pctx, sctx, in, FSEM_DTYPE_F32, mos_out, pesq_status_out, stoi_out, estoi_out,
                                 kept_frames_out, stoi_status_out, ws_pesq, ws_pesq_bytes, ws_stoi, ws_stoi_bytes, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Captured scoring: one CUDA graph, the PESQ chain and the STOI chain as two parallel branches (include/fsem.h).
+struct fsem_graph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int kernel_nodes = 0;
+    int device = -1;
+};
+
+namespace {
+void graph_free(fsem_graph* g) {
+    if (!g) return;
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+}
+}  // namespace
+
+extern "C" int fsem_graph_create(fsem_graph_t** out, fsem_pesq_ctx_t* pctx, fsem_stoi_ctx_t* sctx, const fsem_batch_t* in,
+                                 int dtype, float* mos_out, int32_t* pesq_status_out, float* stoi_out, float* estoi_out,
+                                 int32_t* kept_frames_out, int32_t* stoi_status_out, void* ws_pesq, size_t ws_pesq_bytes,
+                                 void* ws_stoi, size_t ws_stoi_bytes) {
+    if (!out) return fail(FSEM_E_INVALID, "fsem_graph_create: null output");
+    *out = nullptr;
+    if (!pctx && !sctx) return fail(FSEM_E_INVALID, "fsem_graph_create: no metric selected");
+    if (!in || in->batch <= 0) return fail(FSEM_E_INVALID, "fsem_graph_create: empty batch");
+    fsem_graph* g = new (std::nothrow) fsem_graph();
+    if (!g) return fail(FSEM_E_INVALID, "fsem_graph_create: out of host memory");
+    cudaStream_t main_s = nullptr, side_s = nullptr;
+    cudaEvent_t fork_e = nullptr, join_e = nullptr;
+    int rc = FSEM_OK;
+    cudaError_t e = cudaGetDevice(&g->device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&main_s, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&side_s, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fork_e, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&join_e, cudaEventDisableTiming);
+    const bool profile_was = g_profile;
+    g_profile = false;                                     // event pairs of the per-kernel profiler do not belong in a graph
+    const int64_t launches_before = g_launches.load(std::memory_order_relaxed);
+    bool capturing = false;
+    if (e == cudaSuccess) {
+        e = cudaStreamBeginCapture(main_s, cudaStreamCaptureModeThreadLocal);
+        capturing = (e == cudaSuccess);
+    }
+    if (capturing) {
+        const bool both = pctx && sctx;
+        if (both) {                                        // fork: the STOI chain runs on the side stream
+            e = cudaEventRecord(fork_e, main_s);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(side_s, fork_e, 0);
+        }
+        if (e == cudaSuccess && pctx)
+            rc = fsem_pesq_score(pctx, in, dtype, mos_out, pesq_status_out, ws_pesq, ws_pesq_bytes, main_s);
+        if (e == cudaSuccess && rc == FSEM_OK && sctx)
+            rc = fsem_stoi_score(sctx, in, dtype, stoi_out, estoi_out, kept_frames_out, stoi_status_out, ws_stoi,
+                                 ws_stoi_bytes, both ? side_s : main_s);
+        if (both && e == cudaSuccess) {                    // join (also on the error path: the capture must be closed)
+            cudaError_t j = cudaEventRecord(join_e, side_s);
+            if (j == cudaSuccess) j = cudaStreamWaitEvent(main_s, join_e, 0);
+            if (rc == FSEM_OK) e = j;
+        }
+        cudaError_t end = cudaStreamEndCapture(main_s, &g->graph);
+        if (e == cudaSuccess) e = end;
+    }
+    g_profile = profile_was;
+    if (e == cudaSuccess && rc == FSEM_OK) {
+        g->kernel_nodes = (int)(g_launches.load(std::memory_order_relaxed) - launches_before);
+        e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+    }
+    g_launches.store(launches_before, std::memory_order_relaxed);   // captured, not launched
+    if (main_s) cudaStreamDestroy(main_s);
+    if (side_s) cudaStreamDestroy(side_s);
+    if (fork_e) cudaEventDestroy(fork_e);
+    if (join_e) cudaEventDestroy(join_e);
+    if (rc != FSEM_OK) { graph_free(g); cudaGetLastError(); return rc; }   // message already set by the score call
+    if (e != cudaSuccess) {
+        graph_free(g);
+        cudaGetLastError();
+        return fail(FSEM_E_CUDA, "fsem_graph_create: %s", cudaGetErrorString(e));
+    }
+    *out = g;
+    return FSEM_OK;
+}
+
+extern "C" int fsem_graph_launch(fsem_graph_t* g, void* stream) {
+    if (!g || !g->exec) return fail(FSEM_E_INVALID, "fsem_graph_launch: null graph");
+    FSEM_CUDA(cudaGraphLaunch(g->exec, static_cast<cudaStream_t>(stream)));
+    g_launches.fetch_add(g->kernel_nodes, std::memory_order_relaxed);
+    return FSEM_OK;
+}
+
+extern "C" int fsem_graph_nodes(const fsem_graph_t* g) { return g ? g->kernel_nodes : 0; }
+
+extern "C" int fsem_graph_destroy(fsem_graph_t* g) {
+    graph_free(g);
+    return FSEM_OK;
 }
 
 // ================================================================================================

@@ -437,12 +437,26 @@ constexpr int kSpecWarps = FSEM_FFT_WARPS;
 // 3-slot ring of half-frames (256 samples of the clean and of the degraded signal per slot) filled by TMA bulk
 // copies: frame f needs halves f and f+1, half f+2 is in flight while frame f is transformed, so the global-load
 // latency is off the critical path and every sample is fetched from L2/HBM once (frames overlap by 50 %).
+// Level alignment (PESQ.py:97-100): band-pass energy of one signal = fixed-order sum of the IIR pass's chunk partials,
+// g^2 = 1e7 / (sum(y^2) / (len + 5120) / 1.04684).  One definition for the spectrum kernel (which applies g^2 to the
+// Bark powers it stores) and the Bark kernel (which decides NaN / all-zero items on it).
+__device__ __forceinline__ double pesq_band_power(const double* __restrict__ partial, int nchunks, int64_t batch, int sig,
+                                                  int64_t item) {
+    const double* p = partial + ((int64_t)sig * batch + item) * nchunks;
+    double acc = 0.0;
+    for (int c = 0; c < nchunks; ++c) acc += p[c];
+    return acc;
+}
+__device__ __forceinline__ float pesq_level_gain(double power, int len) {
+    return (float)(1.0e7 * ((double)len + 5120.0) * 1.04684 / power);
+}
+
 struct SpecWarpSmem {
     float2 fft[kFftBufElems];          // 6016 B: FFT exchanges, then the band stage's P and S rows
     float half_c[3][FSEM_PESQ_HOP];    // 3072 B
     float half_d[3][FSEM_PESQ_HOP];    // 3072 B
     unsigned long long bar[3];         //   24 B (+8 pad)
-    unsigned long long pad_;
+    float gain[2];                     //    8 B: level-alignment gains g^2 of the current item (clean, degraded)
 };
 static_assert(kBandBufFloats <= 2 * kFftBufElems, "band rows alias the FFT exchange buffer");
 // extra lanes a Bark band may reach back into: bands 0..31 (<= 4 bins at 16 kHz) at most one, bands 32..48 at most four
@@ -454,8 +468,10 @@ static_assert(sizeof(SpecWarpSmem) % 16 == 0, "per-warp shared block must keep 1
 
 __global__ void __launch_bounds__(kSpecWarps * 32, FSEM_FFT_MINBLOCKS)
 pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t* __restrict__ lengths,
-                     const int64_t* __restrict__ frame_prefix, int64_t batch, int64_t n, int tmax,
-                     const PesqTables* __restrict__ tab, float* __restrict__ bark /* [2][batch][tmax][49], unscaled */) {
+                     const int64_t* __restrict__ frame_prefix, int64_t batch, int64_t n, int tmax, int tpitch,
+                     const double* __restrict__ partial /* [2][batch][nchunks] band-pass energies of the IIR pass */,
+                     int nchunks, const PesqTables* __restrict__ tab,
+                     float* __restrict__ bark /* [2][batch][tpitch][49], level-aligned */) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -543,6 +559,13 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
     int sa = 0, sb = 1;                                          // slots of the current frame's two halves
     issue_half(0, item, f);
     issue_half(1, item, f + 1);
+    // level alignment is linear up to the power spectrum: g^2 of the item multiplies the Bark powers as they are stored
+    // (an all-zero item has g^2 = inf and stores NaN rows; the Bark kernel never reads them)
+    auto set_gain = [&](int64_t it, int ln) {
+        if (lane < 2) sm.gain[lane] = pesq_level_gain(pesq_band_power(partial, nchunks, batch, lane, it), ln);
+        __syncwarp();
+    };
+    set_gain(item, len);
 
     while (true) {
         const int sn = 3 - sa - sb;                              // the free slot
@@ -597,15 +620,16 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
         packed_power_regs(ar, ai, br, bi, lane, pc, pd);
         if (lane == 0) { pc[0] = 0.f; pd[0] = 0.f; }             // bin 0: "we won't use energy feature" (PESQ.py:136)
         scan.scan_store(pc, pd, wbuf, lane);
-        float* __restrict__ out_c = bark + (item * tmax + f) * FSEM_PESQ_NBANDS;
-        float* __restrict__ out_d = bark + ((batch + item) * tmax + f) * FSEM_PESQ_NBANDS;
+        float* __restrict__ out_c = bark + (item * tpitch + f) * FSEM_PESQ_NBANDS;
+        float* __restrict__ out_d = bark + ((batch + item) * tpitch + f) * FSEM_PESQ_NBANDS;
         const float lo_c = g_lo.sum(S), lo_d = g_lo.sum(S + kBandSStride);
         const float hi_c = g_hi.sum(S), hi_d = g_hi.sum(S + kBandSStride);     // all lanes: no divergence around the loads
-        out_c[lane] = lo_c * scale0;
-        out_d[lane] = lo_d * scale0;
+        const float2 g2 = *reinterpret_cast<const float2*>(sm.gain);
+        out_c[lane] = (lo_c * scale0) * g2.x;
+        out_d[lane] = (lo_d * scale0) * g2.y;
         if (lane + 32 < FSEM_PESQ_NBANDS) {
-            out_c[lane + 32] = hi_c * scale1;
-            out_d[lane + 32] = hi_d * scale1;
+            out_c[lane + 32] = (hi_c * scale1) * g2.x;
+            out_d[lane + 32] = (hi_d * scale1) * g2.y;
         }
         if (!has_next) break;
         --remaining;
@@ -618,6 +642,7 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
             sa = sn; sb = freed;
             __syncwarp();
             issue_half(sb, item, f + 1);
+            set_gain(item, len);                                 // every lane has read the old pair (syncwarp above)
         }
     }
 }
@@ -634,9 +659,13 @@ constexpr int kBarkThreadsWide = 640;
 constexpr int kBarkTileWide = 320;
 __host__ __device__ constexpr size_t bark_dyn_smem(int tile) { return tile <= 64 ? 0 : sizeof(float) * (size_t)tile * (2 * FSEM_PESQ_NBANDS + 2); }
 
-// x^y for x > 0 through the SFU (lg2.approx / ex2.approx): relative error ~1e-6 for the exponents used here
-// (|y * log2 x| < 10), three orders of magnitude inside the PESQ budget and ~20x cheaper than powf.
-__device__ __forceinline__ float fast_pow(float x, float y) { return exp2f(y * __log2f(x)); }
+// x^y for x > 0 through the SFU (lg2.approx / ex2.approx, one MUFU each: the .ftz forms skip the denormal range fix-ups,
+// and every argument here is a normal number): relative error ~1e-6 for the exponents used (|y * log2 x| < 10), three
+// orders of magnitude inside the PESQ budget and ~20x cheaper than powf.  NaN propagates.
+__device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_pow(float x, float y) { return mufu_ex2(y * mufu_lg2(x)); }
 
 __device__ __forceinline__ float zwicker_loudness(float p, float thr, float inv_thr, float e, float scale) {
     // loudness.py:62-67: Sl*(2 thr)^e * ((0.5 + 0.5 p/thr)^e - 1), 0 where p <= thr
@@ -644,77 +673,90 @@ __device__ __forceinline__ float zwicker_loudness(float p, float thr, float inv_
     return (p <= thr) ? 0.f : l;   // NaN p: comparison false -> l (NaN) propagates like the reference
 }
 
+// The Bark rows arrive LEVEL-ALIGNED (the spectrum kernel applies g^2) in rows of `tpitch` = round4(tmax) frames per
+// (signal, item), so every frame tile is one contiguous, 16-byte aligned run: tiles are fetched with two bulk copies
+// (cp.async.bulk + mbarrier, no register pass), 1.40 -> see DESIGN.md.
 template <int kThreads, int kTile>
 __global__ void __launch_bounds__(kThreads)
 pesq_bark_kernel(const float* __restrict__ bark, const double* __restrict__ partial, int nchunks,
-                 const int32_t* __restrict__ lengths, const int32_t* __restrict__ order, int64_t batch, int64_t n, int tmax,
-                 const PesqTables* __restrict__ tab, float* __restrict__ dist_ws /* [2][batch][tmax] */,
+                 const int32_t* __restrict__ lengths, const int32_t* __restrict__ order, int64_t batch, int64_t n, int tpitch,
+                 const PesqTables* __restrict__ tab, float* __restrict__ dist_ws /* [2][batch][tpitch] */,
                  float* __restrict__ mos_out, int32_t* __restrict__ status_out,
                  double* __restrict__ power_out /* [2][batch] */) {
     static_assert(kThreads == 2 * kTile && kThreads % 32 == 0 && kThreads >= 2 * FSEM_PESQ_NBANDS, "two threads per frame of a tile");
+    static_assert(kTile % 4 == 0, "tile rows are fetched in 16-byte units");
     // the throughput shape keeps its tiles in static arrays (the compiler schedules the unrolled band loops better
-    // around provably distinct arrays: 1.40 vs 1.85 ms at 8192 items); only the wide shape needs dynamic memory
+    // around provably distinct arrays); only the wide shape needs dynamic memory
     constexpr bool kDyn = bark_dyn_smem(kTile) > 0;
     extern __shared__ __align__(16) float s_bark_dyn[];
-    __shared__ float s_tile_st[kDyn ? 1 : 2][kDyn ? 1 : kTile][FSEM_PESQ_NBANDS];
-    __shared__ float s_silent_st[kDyn ? 1 : kTile];
+    __shared__ __align__(16) float s_tile_st[kDyn ? 1 : 2][kDyn ? 1 : kTile][FSEM_PESQ_NBANDS];
+    __shared__ float s_live_st[kDyn ? 1 : kTile];
     __shared__ float s_fr_st[kDyn ? 1 : kTile];
     float (*s_tile)[kTile][FSEM_PESQ_NBANDS] =
         kDyn ? reinterpret_cast<float (*)[kTile][FSEM_PESQ_NBANDS]>(s_bark_dyn)
              : reinterpret_cast<float (*)[kTile][FSEM_PESQ_NBANDS]>(&s_tile_st[0][0][0]);
-    float* s_silent = kDyn ? s_bark_dyn + 2 * kTile * FSEM_PESQ_NBANDS : s_silent_st;
+    float* s_live = kDyn ? s_bark_dyn + 2 * kTile * FSEM_PESQ_NBANDS : s_live_st;     // 1 - silent flag of a frame
     float* s_fr = kDyn ? s_bark_dyn + 2 * kTile * FSEM_PESQ_NBANDS + kTile : s_fr_st;
-    __shared__ float s_thr[FSEM_PESQ_NBANDS], s_ithr[FSEM_PESQ_NBANDS], s_exp[FSEM_PESQ_NBANDS],
+    __shared__ float s_thr[FSEM_PESQ_NBANDS], s_thr100[FSEM_PESQ_NBANDS], s_ithr[FSEM_PESQ_NBANDS], s_exp[FSEM_PESQ_NBANDS],
         s_lsc[FSEM_PESQ_NBANDS], s_w[FSEM_PESQ_NBANDS], s_ratio[FSEM_PESQ_NBANDS];
     __shared__ float s_g2[2];
-    __shared__ float s_carry;
-    __shared__ double s_mean[2][FSEM_PESQ_NBANDS];
+    __shared__ float s_carry[2];                          // last frame ratio of the previous tile, by tile parity
     __shared__ float s_red[2][kThreads / 32];
+    __shared__ __align__(8) unsigned long long s_bar;
 
     const int tid = threadIdx.x;
     // ragged batches: CTAs are scheduled in launch order, so the longest items go first (no long item left for the tail)
     const int64_t item = order ? (int64_t)order[batch - 1 - blockIdx.x] : (int64_t)blockIdx.x;
     const int len = item_length(lengths, item, n);
     const int T = pesq_num_frames(len);
+    const uint32_t bar = smem_u32(&s_bar);
 
     if (tid < FSEM_PESQ_NBANDS) {
         float thr = tab->thresh[tid];
         s_thr[tid] = thr;
+        s_thr100[tid] = thr * 100.f;
         s_ithr[tid] = 1.f / thr;
         s_exp[tid] = tab->zw_exp[tid];
         s_lsc[tid] = tab->loud_scale[tid];
         s_w[tid] = tab->width[tid];
     }
     if (tid < 2) {
-        // level alignment (PESQ.py:97-100): g^2 = 1e7 / (sum(y^2) / (len + 5120) / 1.04684)
-        const double* p = partial + ((int64_t)tid * batch + item) * nchunks;
-        double acc = 0.0;
-        for (int c = 0; c < nchunks; ++c) acc += p[c];
+        // level alignment (PESQ.py:97-100): g^2 = 1e7 / (sum(y^2) / (len + 5120) / 1.04684); applied by the spectrum
+        // kernel (pesq_level_gain, the same expression), recomputed here for the NaN / all-zero decision
+        const double acc = pesq_band_power(partial, nchunks, batch, tid, item);
         power_out[(int64_t)tid * batch + item] = acc;
-        s_g2[tid] = (float)(1.0e7 * ((double)len + 5120.0) * 1.04684 / acc);
+        s_g2[tid] = pesq_level_gain(acc, len);
+    }
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
     }
     __syncthreads();
-    const float g2c = s_g2[0], g2d = s_g2[1];
-    if (T < 20 || !(isfinite(g2c) && isfinite(g2d))) {
+    if (T < 20 || !(isfinite(s_g2[0]) && isfinite(s_g2[1]))) {
         if (tid == 0) {
             mos_out[item] = nanf("");
             if (status_out) status_out[item] = (T < 20) ? FSEM_ITEM_TOO_SHORT : FSEM_ITEM_NAN;
         }
         return;
     }
-    const float* __restrict__ bc = bark + item * (int64_t)tmax * FSEM_PESQ_NBANDS;
-    const float* __restrict__ bd = bark + (batch + item) * (int64_t)tmax * FSEM_PESQ_NBANDS;
+    const float* __restrict__ bc = bark + item * (int64_t)tpitch * FSEM_PESQ_NBANDS;
+    const float* __restrict__ bd = bark + (batch + item) * (int64_t)tpitch * FSEM_PESQ_NBANDS;
+    const uint32_t tile_c = smem_u32(&s_tile[0][0][0]), tile_d = smem_u32(&s_tile[1][0][0]);
+    unsigned parity = 0;
 
+    // all threads have finished with the previous tile (barrier), then one thread starts the two copies; rows beyond
+    // nf (up to three, inside the item's own pitch) ride along and are never read
     auto load_tile = [&](int f0, int nf) {
-        const int cnt = nf * FSEM_PESQ_NBANDS;
-        const float* srcc = bc + (int64_t)f0 * FSEM_PESQ_NBANDS;
-        const float* srcd = bd + (int64_t)f0 * FSEM_PESQ_NBANDS;
-        float* dc = &s_tile[0][0][0];
-        float* dd = &s_tile[1][0][0];
-        for (int i = tid; i < cnt; i += kThreads) {
-            dc[i] = __ldg(srcc + i) * g2c;
-            dd[i] = __ldg(srcd + i) * g2d;
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)((nf + 3) & ~3) * (FSEM_PESQ_NBANDS * sizeof(float));
+            fence_proxy_async();
+            mbar_arrive_expect_tx(bar, 2 * bytes);
+            bulk_copy_g2s(tile_c, bc + (int64_t)f0 * FSEM_PESQ_NBANDS, bytes, bar);
+            bulk_copy_g2s(tile_d, bd + (int64_t)f0 * FSEM_PESQ_NBANDS, bytes, bar);
         }
+        mbar_wait(bar, parity);
+        parity ^= 1u;
     };
 
     // ---- phase 1: silent-frame flags and mean audible band power (PESQ.py:144-147)
@@ -723,9 +765,7 @@ pesq_bark_kernel(const float* __restrict__ bark, const double* __restrict__ part
     const int my_band = tid - my_sig * FSEM_PESQ_NBANDS;
     for (int f0 = 0; f0 < T; f0 += kTile) {
         const int nf = min(kTile, T - f0);
-        __syncthreads();
         load_tile(f0, nf);
-        __syncthreads();
         {   // two threads per frame (even / odd bands), combined with one shuffle
             const int fs = tid >> 1, half = tid & 1;
             float a = 0.f;
@@ -733,41 +773,43 @@ pesq_bark_kernel(const float* __restrict__ bark, const double* __restrict__ part
 #pragma unroll 5
                 for (int b = half; b < FSEM_PESQ_NBANDS; b += 2) {
                     float p = s_tile[0][fs][b];
-                    a += p * ((p > s_thr[b] * 100.f) ? 1.f : 0.f);
+                    a += p * ((p > s_thr100[b]) ? 1.f : 0.f);
                 }
             }
             a += __shfl_xor_sync(kFull, a, 1);
-            if (fs < nf && half == 0) s_silent[fs] = (a < 1.0e7f) ? 1.f : 0.f;
+            if (fs < nf && half == 0) s_live[fs] = (a < 1.0e7f) ? 0.f : 1.f;
         }
         __syncthreads();
         if (tid < 2 * FSEM_PESQ_NBANDS) {
-            const float thr100 = s_thr[my_band] * 100.f;
+            const float thr100 = s_thr100[my_band];
+            const float* col = &s_tile[my_sig][0][my_band];
+            float acc = 0.f;                                   // one tile in float32, tiles in float64
+#pragma unroll 4
             for (int f = 0; f < nf; ++f) {
-                float p = s_tile[my_sig][f][my_band];
-                float m = ((p > thr100) ? 1.f : 0.f) * (1.f - s_silent[f]);
-                band_acc += (double)(p * m);
+                const float p = col[f * FSEM_PESQ_NBANDS];
+                acc += (p > thr100) ? p * s_live[f] : 0.f;
             }
+            band_acc += (double)acc;
         }
     }
-    if (tid < 2 * FSEM_PESQ_NBANDS) s_mean[my_sig][my_band] = band_acc / (double)T;
+    __syncthreads();                                         // the last tile is dead: its memory carries the 98 band means
+    double* s_mean = reinterpret_cast<double*>(&s_tile[0][0][0]);
+    if (tid < 2 * FSEM_PESQ_NBANDS) s_mean[tid] = band_acc / (double)T;
     __syncthreads();
     if (tid < FSEM_PESQ_NBANDS) {
-        float r = (float)((s_mean[1][tid] + 1000.0) / (s_mean[0][tid] + 1000.0));
+        float r = (float)((s_mean[FSEM_PESQ_NBANDS + tid] + 1000.0) / (s_mean[tid] + 1000.0));
         s_ratio[tid] = fminf(fmaxf(r, 0.01f), 100.f);
     }
-    if (tid == 0) s_carry = 0.f;
-    __syncthreads();
+    if (tid == 0) s_carry[0] = 0.f;
 
     const float wtot = tab->width_total;
-    float* __restrict__ dsym = dist_ws + item * (int64_t)tmax;
-    float* __restrict__ dasym = dist_ws + (batch + item) * (int64_t)tmax;
+    float* __restrict__ dsym = dist_ws + item * (int64_t)tpitch;
+    float* __restrict__ dasym = dist_ws + (batch + item) * (int64_t)tpitch;
 
     // ---- phase 2: frame equalisation, loudness, disturbances (PESQ.py:149-224)
     for (int f0 = 0; f0 < T; f0 += kTile) {
         const int nf = min(kTile, T - f0);
-        __syncthreads();
-        load_tile(f0, nf);
-        __syncthreads();
+        load_tile(f0, nf);                                  // its leading barrier also publishes s_ratio / s_carry
         // two threads per frame: thread 2*fs handles the even bands, 2*fs+1 the odd ones
         const int fs = tid >> 1, half = tid & 1;
         const bool live = fs < nf;
@@ -790,7 +832,7 @@ pesq_bark_kernel(const float* __restrict__ bark, const double* __restrict__ part
             const int f = f0 + fs;
             float fr = s_fr[fs];
             if (f > 0) {
-                float prev = (fs == 0) ? s_carry : s_fr[fs - 1];
+                float prev = (fs == 0) ? s_carry[(f0 / kTile) & 1] : s_fr[fs - 1];
                 fr = 0.8f * fr + 0.2f * prev;               // non-recursive smoothing (PESQ.py:159)
             }
             fr = fminf(fmaxf(fr, 3.0e-4f), 5.f);
@@ -805,15 +847,14 @@ pesq_bark_kernel(const float* __restrict__ bark, const double* __restrict__ part
                 float mag = fmaxf(fabsf(diff) - dead, 0.f);
                 float dist = copysignf(mag, diff);
                 if (diff != diff) dist = diff;             // keep NaN
-                if (b >= 1) {                               // band 0 excluded (bark.py:184)
-                    const float wd = s_w[b] * dist;
-                    sym_acc = fmaf(wd, wd, sym_acc);
-                    const float ratio = __fdividef(d + 50.f, c + 50.f);
-                    float scale = 0.f;
-                    // ratio^1.2 < 3  <=>  ratio < 3^(1/1.2): decide on the ratio itself (no pow error in the decision)
-                    if (!(ratio < 2.49804953f)) scale = fminf(fast_pow(ratio, 1.2f), 12.f);
-                    asym_acc += fabsf(wd * scale);
-                }
+                // band 0 excluded (bark.py:184): its width weight is dropped here
+                const float wd = (b >= 1) ? s_w[b] * dist : 0.f;
+                sym_acc = fmaf(wd, wd, sym_acc);
+                const float ratio = (d + 50.f) * mufu_rcp(c + 50.f);   // c + 50 >= 50: a normal number
+                // ratio^1.2 < 3  <=>  ratio < 3^(1/1.2): decide on the ratio itself (no pow error in the decision);
+                // branch-free: the pow is two MUFU operations
+                const float scale = (ratio < 2.49804953f) ? 0.f : fminf(fast_pow(ratio, 1.2f), 12.f);
+                asym_acc += fabsf(wd * scale);
             }
         }
         sym_acc += __shfl_xor_sync(kFull, sym_acc, 1);
@@ -826,8 +867,8 @@ pesq_bark_kernel(const float* __restrict__ bark, const double* __restrict__ part
             dsym[f] = fminf(sym / weight, 45.f);
             dasym[f] = fminf(asym / weight, 45.f);
         }
-        __syncthreads();
-        if (tid == 0) s_carry = s_fr[nf - 1];
+        if (tid == 2 * (nf - 1)) s_carry[(f0 / kTile + 1) & 1] = s_fr[nf - 1];   // for the next tile (other slot: thread 0
+                                                                                 // may still be reading this tile's)
     }
     __syncthreads();   // dsym/dasym written by this CTA are visible to it after the barrier
 

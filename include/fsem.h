@@ -151,8 +151,8 @@ FSEM_API int fsem_pesq_score_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in, f
 FSEM_API int fsem_pesq_score_host_f32(fsem_pesq_ctx_t* ctx, const fsem_batch_t* in, float* mos_out,
                              int32_t* status_out);
 /* Stage taps for parity tests (device pointers, after a score call on the same workspace):
- * copies the Bark-band power densities [2, batch, frames, 49] (clean then degraded, BEFORE level
- * alignment: multiply by g^2 = 1e7 * (n + 5120) * 1.04684 / power) into `bark_out` and the
+ * copies the Bark-band power densities [2, batch, frames, 49] (clean then degraded, level-aligned:
+ * the spectrum kernel applies g^2 = 1e7 * (n + 5120) * 1.04684 / power as it stores them) into `bark_out` and the
  * band-pass energies sum(y^2) [2, batch] (double) into `power_out`. */
 FSEM_API int fsem_pesq_debug_taps(fsem_pesq_ctx_t* ctx, int64_t batch, int64_t n, const void* workspace,
                          float* bark_out, double* power_out, int64_t* frames_out, void* stream);
@@ -242,6 +242,26 @@ FSEM_API int fsem_score_host(fsem_pesq_ctx_t* pesq, fsem_stoi_ctx_t* stoi, const
                     const int32_t* lengths, int64_t batch, int64_t n, int64_t stride, float* mos_out,
                     int32_t* pesq_status_out, float* stoi_out, float* estoi_out, int32_t* kept_frames_out,
                     int32_t* stoi_status_out);
+
+/* ------------------------------------------------------------------ captured scoring (CUDA graph)
+ * The reference scores a pair of tensors with ~100 eager torch ops per metric (PESQ.compute_metric, PESQ.py:232-245;
+ * STOI.compute_metric, STOI.py:200-205); here a call is 3 + 7 kernel launches, and for the small batches of the
+ * reference's README example (4 x 10 s) those launches run back to back at their latency floor.  fsem_graph_create
+ * captures ONE scoring of fixed device buffers into a CUDA graph whose PESQ chain and STOI chain are two PARALLEL
+ * branches (they share nothing but the read-only inputs), so a replay costs one graph launch and the longer of the
+ * two chains.  Arguments are exactly those of fsem_pesq_stoi_score; `pesq` or `stoi` may be NULL (that chain and its
+ * outputs are skipped).  The graph bakes in every pointer: inputs, outputs and workspaces must stay allocated, the
+ * caller rewrites the INPUT buffers in place between replays (the static-buffer contract of CUDA graphs).
+ * fsem_graph_launch is stream-ordered and does not synchronise; replays of one graph must not overlap (they share the
+ * workspaces): launch them on one stream.  fsem_graph_nodes: kernel nodes per replay. */
+typedef struct fsem_graph fsem_graph_t;
+FSEM_API int fsem_graph_create(fsem_graph_t** out, fsem_pesq_ctx_t* pesq, fsem_stoi_ctx_t* stoi, const fsem_batch_t* in,
+                      int dtype, float* mos_out, int32_t* pesq_status_out, float* stoi_out, float* estoi_out,
+                      int32_t* kept_frames_out, int32_t* stoi_status_out, void* ws_pesq, size_t ws_pesq_bytes,
+                      void* ws_stoi, size_t ws_stoi_bytes);
+FSEM_API int fsem_graph_launch(fsem_graph_t* g, void* stream);
+FSEM_API int fsem_graph_nodes(const fsem_graph_t* g);
+FSEM_API int fsem_graph_destroy(fsem_graph_t* g);
 
 /* ------------------------------------------------------------------ resample-on-ingest (building block)
  * Replaces the torchaudio Resample of BaseMetric.prepare_audio (fast_se_metrics/base.py:13,19-20) for the metrics

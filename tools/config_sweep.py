@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from fast_speech_enhancement_metrics_b200 import LSD, PESQ, SDR, STOI, _lib  # noqa: E402
+from fast_speech_enhancement_metrics_b200 import LSD, PESQ, SDR, STOI, CapturedScorer, _lib  # noqa: E402
 from fast_speech_enhancement_metrics_b200.synth import synth_batch  # noqa: E402
 
 
@@ -54,6 +54,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="gpurun_out/config_sweep.json")
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--max-batch", type=int, default=0, help="only shapes up to this batch size (0 = all); skips LSD / SDR")
     args = ap.parse_args()
     pesq, stoi = PESQ(16000, use_gpu=True), STOI(16000, use_gpu=True)
     shapes = [("configs[0] README 4 x 10 s", 4, 160000, None),
@@ -65,6 +66,8 @@ def main():
     shapes += [("ladder %d x 10 s" % b, b, 160000, None) for b in (1, 2, 8, 16, 32, 64, 128, 512, 1024, 2048)]
     rows = []
     for i, (name, b, n, mode) in enumerate(shapes):
+        if args.max_batch and b > args.max_batch:
+            continue
         c, d = make(b, n, 2000 + i)
         lengths = None
         if mode == "var":
@@ -76,9 +79,26 @@ def main():
             row[label] = {"ms": round(ms, 4), "audio_s_per_s": round(audio_s / (ms * 1e-3), 1), "kernels_ms": prof}
         both = row["PESQ"]["ms"] + row["STOI"]["ms"]
         row["PESQ+STOI"] = {"ms": round(both, 4), "audio_s_per_s": round(audio_s / (both * 1e-3), 1)}
+        # the same scoring as ONE CUDA graph (two parallel branches): CUDA events around `steps` replays
+        scorer = CapturedScorer(pesq, stoi, c, d, lengths)
+        for _ in range(3):
+            scorer.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = args.steps * (20 if b <= 64 else 1)
+        e0.record()
+        for _ in range(reps):
+            scorer.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        gms = e0.elapsed_time(e1) / reps
+        row["PESQ+STOI graph"] = {"ms": round(gms, 4), "audio_s_per_s": round(audio_s / (gms * 1e-3), 1),
+                                  "kernel_nodes": scorer.kernel_nodes, "speedup_vs_calls": round(both / gms, 3)}
+        scorer.close()
+        del scorer
         rows.append(row)
-        print("%-42s PESQ %9.3f ms  STOI %9.3f ms  both %12.0f audio-s/s" % (name, row["PESQ"]["ms"], row["STOI"]["ms"],
-                                                                            row["PESQ+STOI"]["audio_s_per_s"]), flush=True)
+        print("%-42s PESQ %9.3f ms  STOI %9.3f ms  both %12.0f audio-s/s   graph %9.3f ms (x%.2f)" % (
+            name, row["PESQ"]["ms"], row["STOI"]["ms"], row["PESQ+STOI"]["audio_s_per_s"], gms, both / gms), flush=True)
         del c, d
         torch.cuda.empty_cache()
     # adjacent metrics at the headline shape, with their HBM roofline line: one call must read both
@@ -91,6 +111,8 @@ def main():
         pass
     lsd, sdr = LSD(16000, use_gpu=True), SDR(16000, use_gpu=True)
     for name, b, n in (("LSD/SDR 8192 x 10 s", 8192, 160000), ("LSD/SDR 256 x 10 s", 256, 160000)):
+        if args.max_batch:
+            break
         c, d = make(b, n, 3000 + b)
         audio_s = b * n / 16000.0
         row = {"shape": name, "batch": b, "samples": n, "audio_s": audio_s}
