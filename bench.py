@@ -303,6 +303,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the direct entry points instead of the CUDA-graph path")
     ap.add_argument("--parity-items", type=int, default=32, help="items per rank scored by the oracle (outside the timed region)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -324,7 +325,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from fast_speech_enhancement_metrics_b200 import PESQ, STOI, _lib
+    from fast_speech_enhancement_metrics_b200 import PESQ, STOI, CapturedScorer, _lib
     from fast_speech_enhancement_metrics_b200.dist import gather_scores, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -360,10 +361,22 @@ def main():
 
     gathered = torch.empty(args.batch, 3, dtype=torch.float32, device=device)
 
-    def step_device():
+    # The timed step is the library's captured-scoring path (public API CapturedScorer = C ABI fsem_graph_*): ONE CUDA
+    # graph per step whose PESQ chain and STOI chain are parallel branches (the tails of one chain's kernels fill
+    # with the other's: x1.01 at 8192 items per GPU, x1.08 at 1024), then the all-gather of the score rows.
+    # --no-graph times the direct entry points (fsem_pesq_score + fsem_stoi_score back to back on one stream).
+    scorer = None if args.no_graph else CapturedScorer(pesq, stoi, clean, deg)
+
+    def step_direct():
         mos, _ = pesq.score_tensors(clean, deg)
         sc, _, _ = stoi.score_tensors(clean, deg)
-        local = torch.stack([mos, sc[0], sc[1]], dim=1)
+        return torch.stack([mos, sc[0], sc[1]], dim=1)
+
+    def step_device():
+        if scorer is not None:
+            local = scorer.replay()[0].t().contiguous()
+        else:
+            local = step_direct()
         return gather_scores(local, args.batch, world, out=gathered)
 
     # ---- value: device-resident inputs
@@ -373,8 +386,6 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    _lib.profile_reset()
-    _lib.profile_enable(True)
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -385,6 +396,18 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = _lib.launch_count() - launches0
+    # ---- per-kernel times: the same kernels launched directly (one stream, one CUDA-event pair around every launch,
+    # fsem_profile_*), right after the timed region and under the same clocks; events cannot bracket the nodes of a
+    # graph whose branches run concurrently.  Rank-local, no collective.
+    _lib.profile_reset()
+    _lib.profile_enable(True)
+    pv0, pv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pv0.record()
+    for _ in range(args.steps):
+        step_direct()
+    pv1.record()
+    torch.cuda.synchronize()
+    direct_ms_per_step = pv0.elapsed_time(pv1) / args.steps
     _lib.profile_enable(False)
     prof = _lib.profile_read()
     if rank == 0 and len(sampler.lines) < 4:
@@ -392,8 +415,7 @@ def main():
         # until there are enough samples to report the clocks under load
         t_end = time.perf_counter() + 1.0
         while time.perf_counter() < t_end and len(sampler.lines) < 6:
-            pesq.score_tensors(clean, deg)          # rank-local work only: no collective outside the timed steps
-            stoi.score_tensors(clean, deg)
+            step_direct()                           # rank-local work only: no collective outside the timed steps
             torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -550,9 +572,14 @@ def main():
                    "batch_total": args.batch, "batch_per_gpu": local_b, "samples": n, "sample_rate": FS,
                    "l2": "inputs (%.1f GB per GPU) exceed L2; no flush" % (2 * local_b * n * 4 / 1e9),
                    "collective": "all_gather of [batch/N, 3] fp32 scores (NCCL)" if world > 1 else "none",
+                   "step": "direct calls" if args.no_graph else "one CUDA graph (fsem_graph_launch) + score gather",
                    "numa": numa},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "roofline_call": roofline_call, "roofline_step": roofline_step, "kernels": kernels,
+        "kernels_from": {"pass": "direct entry points on one stream, one CUDA-event pair per launch, run right after the timed "
+                                 "region (the timed steps replay the CUDA graph, whose concurrent branches events cannot bracket)",
+                         "direct_ms_per_step": direct_ms_per_step,
+                         "timed_path": "direct calls" if args.no_graph else "CapturedScorer.replay (fsem_graph_launch): PESQ and STOI chains as parallel graph branches"},
         "cpu_baseline": cpu, "parity": parity, "finite_score_fraction": finite,
     }
     emit(line)

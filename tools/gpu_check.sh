@@ -14,7 +14,7 @@ timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/$
 echo "bench ref rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
     -k regex:"pesq_|stoi_" -s 30 -c 10 --csv --log-file gpurun_out/${TAG}_launches.csv \
-    python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-parity > gpurun_out/${TAG}_ncu.log 2>&1
+    python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-parity --no-graph > gpurun_out/${TAG}_ncu.log 2>&1
 echo "ncu rc=$?"
 python - <<PY
 import json

@@ -19,7 +19,7 @@ except Exception as e:
 PY
 if [ -n "$2" ]; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$2" -s 3 -c 1 -o gpurun_out/${TAG}_full -f \
-      python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-parity > gpurun_out/${TAG}_ncufull.log 2>&1
+      python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-parity --no-graph > gpurun_out/${TAG}_ncufull.log 2>&1
   echo "ncu full rc=$?"
   ncu -i gpurun_out/${TAG}_full.ncu-rep --page raw --csv > gpurun_out/${TAG}_full_raw.csv 2>/dev/null
 fi
