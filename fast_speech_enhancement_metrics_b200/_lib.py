@@ -33,7 +33,7 @@ EXPORTS = [
     "fsem_sdr_workspace_bytes", "fsem_sdr_score_f32", "fsem_ingest_f32", "fsem_score_host",
     "fsem_stoi_mask_margin", "fsem_resampler_create", "fsem_resampler_destroy", "fsem_resampled_len",
     "fsem_resample_f32", "fsem_pesq_score", "fsem_stoi_score", "fsem_pesq_stoi_score",
-    "fsem_graph_create", "fsem_graph_launch", "fsem_graph_nodes", "fsem_graph_destroy",
+    "fsem_graph_create", "fsem_graph_launch", "fsem_graph_nodes", "fsem_graph_slices", "fsem_graph_destroy",
 ]
 
 # ingest formats (include/fsem.h FSEM_DTYPE_*)
@@ -102,10 +102,10 @@ def load() -> C.CDLL:
     lib.fsem_stoi_score.argtypes = [vp, C.POINTER(Batch), C.c_int, fp, fp, i32p, i32p, vp, C.c_size_t, vp]
     lib.fsem_pesq_stoi_score.argtypes = [vp, vp, C.POINTER(Batch), C.c_int, fp, i32p, fp, fp, i32p, i32p, vp, C.c_size_t,
                                          vp, C.c_size_t, vp]
-    lib.fsem_graph_create.argtypes = [C.POINTER(vp), vp, vp, C.POINTER(Batch), C.c_int, fp, i32p, fp, fp, i32p, i32p, vp,
-                                      C.c_size_t, vp, C.c_size_t]
+    lib.fsem_graph_create.argtypes = [C.POINTER(vp), vp, vp, C.POINTER(Batch), C.c_int, fp, i32p, fp, fp, i32p, i32p, C.c_int]
     lib.fsem_graph_launch.argtypes = [vp, vp]
     lib.fsem_graph_nodes.argtypes = [vp]
+    lib.fsem_graph_slices.argtypes = [vp]
     lib.fsem_graph_destroy.argtypes = [vp]
     lib.fsem_stoi_mask_margin.argtypes = [vp, i64, i64, i32p, vp, fp, vp]
     lib.fsem_resampler_create.argtypes = [C.POINTER(vp), C.c_int32, C.c_int32, C.c_int32, C.c_int32,

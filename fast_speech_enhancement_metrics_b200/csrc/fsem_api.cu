@@ -224,6 +224,10 @@ struct fsem_pesq_ctx {
     float* d_rs_taps = nullptr;
     int spec_ctas_per_sm = 2;
     int filt_ctas_per_sm = 4;
+    // > 0: plan the IIR time-chunk grid as for a batch of this size (fsem_graph_create scores a batch in slices and
+    // keeps the chunk grid -- the only batch-dependent arithmetic of either chain -- of the whole batch, so that sliced
+    // and unsliced scoring agree bit for bit)
+    int64_t plan_batch_hint = 0;
     HostPipe pipe;
 };
 
@@ -257,14 +261,15 @@ PesqPlan pesq_plan(const fsem_pesq_ctx* ctx, int64_t batch, int64_t n_in) {
     // all units are equal, so the kernel runs in whole "waves" of resident warps.  Pick the chunk count that minimises
     // waves x (chunk + warm-up): enough units to fill the chip, no half-empty last wave, little redundant warm-up.
     const int64_t nn = n > 0 ? n : 1;
-    const int64_t groups = 2 * ceil_div(batch > 0 ? batch : 1, 32);
+    const int64_t plan_batch = ctx->plan_batch_hint > 0 ? ctx->plan_batch_hint : batch;
+    const int64_t groups = 2 * ceil_div(plan_batch > 0 ? plan_batch : 1, 32);
     const int64_t slots = (int64_t)ctx->dev.sms * ctx->filt_ctas_per_sm * kFiltWarps;   // resident warps of the IIR pass
     const int64_t max_ch = ceil_div(nn, 256) < 1024 ? ceil_div(nn, 256) : 1024;     // chunks of at least 256 samples
     int64_t nch = 1, chunk = round_up(nn, quantum);
     double best = 1e300;
     // tiny batches cannot fill the 32 signal lanes of a warp: there a thread takes one (signal, chunk) and the time
     // axis is cut as finely as the warm-up allows
-    p.tiled = batch >= 16;
+    p.tiled = plan_batch >= 16;
     if (!p.tiled) {
         chunk = round_up(ceil_div(nn, max_ch), 64);
         nch = ceil_div(nn, chunk);
@@ -1210,11 +1215,14 @@ extern "C" int fsem_pesq_stoi_score_f32(fsem_pesq_ctx_t* pctx, fsem_stoi_ctx_t* 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Captured scoring: one CUDA graph, the PESQ chain and the STOI chain as two parallel branches (include/fsem.h).
+// Captured scoring: one CUDA graph; the batch is cut into slices and every slice's PESQ chain and STOI chain is a
+// parallel branch (include/fsem.h).
 struct fsem_graph {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
+    void* ws = nullptr;                 // workspaces of all branches (owned)
     int kernel_nodes = 0;
+    int slices = 0;
     int device = -1;
 };
 
@@ -1223,28 +1231,56 @@ void graph_free(fsem_graph* g) {
     if (!g) return;
     if (g->exec) cudaGraphExecDestroy(g->exec);
     if (g->graph) cudaGraphDestroy(g->graph);
+    if (g->ws) cudaFree(g->ws);
     delete g;
 }
+constexpr int kGraphMaxSlices = 16;
 }  // namespace
 
 extern "C" int fsem_graph_create(fsem_graph_t** out, fsem_pesq_ctx_t* pctx, fsem_stoi_ctx_t* sctx, const fsem_batch_t* in,
                                  int dtype, float* mos_out, int32_t* pesq_status_out, float* stoi_out, float* estoi_out,
-                                 int32_t* kept_frames_out, int32_t* stoi_status_out, void* ws_pesq, size_t ws_pesq_bytes,
-                                 void* ws_stoi, size_t ws_stoi_bytes) {
+                                 int32_t* kept_frames_out, int32_t* stoi_status_out, int slices) {
     if (!out) return fail(FSEM_E_INVALID, "fsem_graph_create: null output");
     *out = nullptr;
     if (!pctx && !sctx) return fail(FSEM_E_INVALID, "fsem_graph_create: no metric selected");
     if (!in || in->batch <= 0) return fail(FSEM_E_INVALID, "fsem_graph_create: empty batch");
+    if ((pctx && !mos_out) || (sctx && (!stoi_out || !estoi_out)))
+        return fail(FSEM_E_INVALID, "fsem_graph_create: null output column");
+    const size_t es = dtype_size(dtype);
+    if (es == 0) return fail(FSEM_E_INVALID, "fsem_graph_create: unknown dtype %d", dtype);
+    // measured on B200 (profiles/r02_config_sweep.json, by_slices): two branches already fill the chip, cutting the batch
+    // further gains <= 1 % at 8192 x 10 s and loses below that -- the library's own choice is one slice
+    if (slices <= 0) slices = 1;
+    if (slices > kGraphMaxSlices) slices = kGraphMaxSlices;
+    if (slices > in->batch) slices = (int)in->batch;
     fsem_graph* g = new (std::nothrow) fsem_graph();
     if (!g) return fail(FSEM_E_INVALID, "fsem_graph_create: out of host memory");
-    cudaStream_t main_s = nullptr, side_s = nullptr;
-    cudaEvent_t fork_e = nullptr, join_e = nullptr;
+    g->slices = slices;
+    // slice s = items [b0[s], b0[s + 1]): contiguous, sizes differ by at most one
+    int64_t b0[kGraphMaxSlices + 1];
+    for (int s = 0; s <= slices; ++s) b0[s] = in->batch * s / slices;
+    if (pctx) pctx->plan_batch_hint = in->batch;                      // one IIR chunk grid for every slice
+    size_t ws_off[2 * kGraphMaxSlices + 1];
+    ws_off[0] = 0;
+    for (int s = 0; s < slices; ++s) {
+        const int64_t nb = b0[s + 1] - b0[s];
+        ws_off[2 * s + 1] = ws_off[2 * s] + (pctx ? align256(fsem_pesq_workspace_bytes(pctx, nb, in->n)) : 0);
+        ws_off[2 * s + 2] = ws_off[2 * s + 1] + (sctx ? align256(fsem_stoi_workspace_bytes(sctx, nb, in->n)) : 0);
+    }
+    const int nbranch = (pctx ? slices : 0) + (sctx ? slices : 0);
+    cudaStream_t main_s = nullptr;
+    std::vector<cudaStream_t> side(nbranch > 1 ? nbranch - 1 : 0, nullptr);
+    std::vector<cudaEvent_t> join(side.size(), nullptr);
+    cudaEvent_t fork_e = nullptr;
     int rc = FSEM_OK;
     cudaError_t e = cudaGetDevice(&g->device);
+    if (e == cudaSuccess) e = cudaMalloc(&g->ws, ws_off[2 * slices] > 0 ? ws_off[2 * slices] : 256);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&main_s, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&side_s, cudaStreamNonBlocking);
+    for (size_t i = 0; i < side.size() && e == cudaSuccess; ++i) {
+        e = cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fork_e, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&join_e, cudaEventDisableTiming);
     const bool profile_was = g_profile;
     g_profile = false;                                     // event pairs of the per-kernel profiler do not belong in a graph
     const int64_t launches_before = g_launches.load(std::memory_order_relaxed);
@@ -1254,24 +1290,41 @@ extern "C" int fsem_graph_create(fsem_graph_t** out, fsem_pesq_ctx_t* pctx, fsem
         capturing = (e == cudaSuccess);
     }
     if (capturing) {
-        const bool both = pctx && sctx;
-        if (both) {                                        // fork: the STOI chain runs on the side stream
-            e = cudaEventRecord(fork_e, main_s);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(side_s, fork_e, 0);
+        if (!side.empty()) e = cudaEventRecord(fork_e, main_s);
+        for (size_t i = 0; i < side.size() && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(side[i], fork_e, 0);
+        // branch k runs on the main stream (k = 0) or on side[k - 1]; PESQ branches first: they are the longer chains
+        int k = 0;
+        auto stream_of = [&](int idx) { return idx == 0 ? main_s : side[idx - 1]; };
+        const char* cb = reinterpret_cast<const char*>(in->clean);
+        const char* db = reinterpret_cast<const char*>(in->deg);
+        char* wsb = static_cast<char*>(g->ws);
+        for (int pass = 0; pass < 2 && e == cudaSuccess && rc == FSEM_OK; ++pass) {
+            if ((pass == 0 && !pctx) || (pass == 1 && !sctx)) continue;
+            for (int s = 0; s < slices && rc == FSEM_OK; ++s, ++k) {
+                const int64_t i0 = b0[s], nb = b0[s + 1] - b0[s];
+                const fsem_batch_t sub{reinterpret_cast<const float*>(cb + (size_t)i0 * in->stride * es),
+                                       reinterpret_cast<const float*>(db + (size_t)i0 * in->stride * es),
+                                       in->lengths ? in->lengths + i0 : nullptr, nb, in->n, in->stride};
+                if (pass == 0)
+                    rc = fsem_pesq_score(pctx, &sub, dtype, mos_out + i0, pesq_status_out ? pesq_status_out + i0 : nullptr,
+                                         wsb + ws_off[2 * s], ws_off[2 * s + 1] - ws_off[2 * s], stream_of(k));
+                else
+                    rc = fsem_stoi_score(sctx, &sub, dtype, stoi_out + i0, estoi_out + i0,
+                                         kept_frames_out ? kept_frames_out + i0 : nullptr,
+                                         stoi_status_out ? stoi_status_out + i0 : nullptr, wsb + ws_off[2 * s + 1],
+                                         ws_off[2 * s + 2] - ws_off[2 * s + 1], stream_of(k));
+            }
         }
-        if (e == cudaSuccess && pctx)
-            rc = fsem_pesq_score(pctx, in, dtype, mos_out, pesq_status_out, ws_pesq, ws_pesq_bytes, main_s);
-        if (e == cudaSuccess && rc == FSEM_OK && sctx)
-            rc = fsem_stoi_score(sctx, in, dtype, stoi_out, estoi_out, kept_frames_out, stoi_status_out, ws_stoi,
-                                 ws_stoi_bytes, both ? side_s : main_s);
-        if (both && e == cudaSuccess) {                    // join (also on the error path: the capture must be closed)
-            cudaError_t j = cudaEventRecord(join_e, side_s);
-            if (j == cudaSuccess) j = cudaStreamWaitEvent(main_s, join_e, 0);
-            if (rc == FSEM_OK) e = j;
+        // join every side stream (also on the error path: the capture must be closed with all streams rejoined)
+        for (size_t i = 0; i < side.size(); ++i) {
+            cudaError_t j = cudaEventRecord(join[i], side[i]);
+            if (j == cudaSuccess) j = cudaStreamWaitEvent(main_s, join[i], 0);
+            if (e == cudaSuccess && rc == FSEM_OK) e = j;
         }
         cudaError_t end = cudaStreamEndCapture(main_s, &g->graph);
         if (e == cudaSuccess) e = end;
     }
+    if (pctx) pctx->plan_batch_hint = 0;
     g_profile = profile_was;
     if (e == cudaSuccess && rc == FSEM_OK) {
         g->kernel_nodes = (int)(g_launches.load(std::memory_order_relaxed) - launches_before);
@@ -1279,9 +1332,11 @@ extern "C" int fsem_graph_create(fsem_graph_t** out, fsem_pesq_ctx_t* pctx, fsem
     }
     g_launches.store(launches_before, std::memory_order_relaxed);   // captured, not launched
     if (main_s) cudaStreamDestroy(main_s);
-    if (side_s) cudaStreamDestroy(side_s);
+    for (size_t i = 0; i < side.size(); ++i) {
+        if (side[i]) cudaStreamDestroy(side[i]);
+        if (join[i]) cudaEventDestroy(join[i]);
+    }
     if (fork_e) cudaEventDestroy(fork_e);
-    if (join_e) cudaEventDestroy(join_e);
     if (rc != FSEM_OK) { graph_free(g); cudaGetLastError(); return rc; }   // message already set by the score call
     if (e != cudaSuccess) {
         graph_free(g);
@@ -1300,6 +1355,7 @@ extern "C" int fsem_graph_launch(fsem_graph_t* g, void* stream) {
 }
 
 extern "C" int fsem_graph_nodes(const fsem_graph_t* g) { return g ? g->kernel_nodes : 0; }
+extern "C" int fsem_graph_slices(const fsem_graph_t* g) { return g ? g->slices : 0; }
 
 extern "C" int fsem_graph_destroy(fsem_graph_t* g) {
     graph_free(g);

@@ -89,11 +89,13 @@ def score_pesq_stoi(pesq: PESQ, stoi: STOI, clean_speech: torch.Tensor, denoised
 class CapturedScorer:
     """PESQ and/or STOI/ESTOI of FIXED device buffers as ONE CUDA graph (C ABI fsem_graph_*).
 
-    The two kernel chains share nothing but their read-only inputs, so the graph runs them as two parallel
-    branches: a replay costs one graph launch and the longer chain instead of 3 + 7 launches back to back.  This is
-    the path for the small batches of the reference's README example (4 x 10 s, README.md:21-30), where every
-    kernel sits on its latency floor, and for scoring inside a loop that refills the same buffers (validation
-    steps).  Static-buffer contract of CUDA graphs: `clean` / `deg` (and `lengths`) are captured BY ADDRESS -- write
+    The two kernel chains share nothing but their read-only inputs, so the graph runs them as parallel branches
+    (and, for large batches, one pair of branches per slice of the batch: the tail of every kernel overlaps with
+    another branch's work): a replay costs one graph launch and the longer chain instead of 3 + 7 launches back to
+    back.  This is the path for the small batches of the reference's README example (4 x 10 s, README.md:21-30),
+    where every kernel sits on its latency floor, and for scoring inside a loop that refills the same buffers
+    (validation steps).  `slices` = parts the batch is cut into (0: the library's choice); the scores do not depend
+    on it.  Static-buffer contract of CUDA graphs: `clean` / `deg` (and `lengths`) are captured BY ADDRESS -- write
     the next batch into them in place (`clean.copy_(...)`) and call the scorer again.  Results are bit-identical to
     `score_pesq_stoi_tensors` on the same buffers (same kernels, same launch shapes).
 
@@ -102,7 +104,8 @@ class CapturedScorer:
         clean_cuda.copy_(next_clean); deg_cuda.copy_(next_deg); rows = scorer()
     """
 
-    def __init__(self, pesq: PESQ | None, stoi: STOI | None, clean: torch.Tensor, deg: torch.Tensor, lengths=None):
+    def __init__(self, pesq: PESQ | None, stoi: STOI | None, clean: torch.Tensor, deg: torch.Tensor, lengths=None,
+                 slices: int = 0):
         if pesq is None and stoi is None:
             raise Exception("CapturedScorer needs at least one metric")
         owner = pesq if pesq is not None else stoi
@@ -128,11 +131,7 @@ class CapturedScorer:
         self.pesq_status = torch.zeros(b, dtype=torch.int32, device=clean.device)
         self.kept_frames = torch.zeros(b, dtype=torch.int32, device=clean.device)
         self.stoi_status = torch.zeros(b, dtype=torch.int32, device=clean.device)
-        # the graph owns its workspaces: the metric objects' cached ones may be reallocated by later calls
-        wp = int(self._lib.fsem_pesq_workspace_bytes(pesq._ctx, b, n)) if pesq is not None else 0
-        wsb = int(self._lib.fsem_stoi_workspace_bytes(stoi._ctx, b, n)) if stoi is not None else 0
-        self._ws_pesq = torch.empty(max(wp, 256), dtype=torch.uint8, device=clean.device)
-        self._ws_stoi = torch.empty(max(wsb, 256), dtype=torch.uint8, device=clean.device)
+        # the library cuts the batch into `slices` parts (0: its own choice) and owns the graph's workspaces
         self._handle = C.c_void_p()
         batch = _lib.Batch(clean.data_ptr(), deg.data_ptr(), self.lengths.data_ptr() if self.lengths is not None else None,
                            b, n, clean.stride(0) if b > 1 else max(n, clean.stride(0)))
@@ -141,8 +140,8 @@ class CapturedScorer:
                 C.byref(self._handle), pesq._ctx if pesq is not None else None, stoi._ctx if stoi is not None else None,
                 C.byref(batch), _lib.dtype_code(clean.dtype), self.scores[0].data_ptr(), self.pesq_status.data_ptr(),
                 self.scores[1].data_ptr(), self.scores[2].data_ptr(), self.kept_frames.data_ptr(),
-                self.stoi_status.data_ptr(), self._ws_pesq.data_ptr(), self._ws_pesq.numel(), self._ws_stoi.data_ptr(),
-                self._ws_stoi.numel()))
+                self.stoi_status.data_ptr(), int(slices)))
+        self.slices = int(self._lib.fsem_graph_slices(self._handle))
         self.kernel_nodes = int(self._lib.fsem_graph_nodes(self._handle))
 
     def replay(self):

@@ -247,20 +247,24 @@ FSEM_API int fsem_score_host(fsem_pesq_ctx_t* pesq, fsem_stoi_ctx_t* stoi, const
  * The reference scores a pair of tensors with ~100 eager torch ops per metric (PESQ.compute_metric, PESQ.py:232-245;
  * STOI.compute_metric, STOI.py:200-205); here a call is 3 + 7 kernel launches, and for the small batches of the
  * reference's README example (4 x 10 s) those launches run back to back at their latency floor.  fsem_graph_create
- * captures ONE scoring of fixed device buffers into a CUDA graph whose PESQ chain and STOI chain are two PARALLEL
- * branches (they share nothing but the read-only inputs), so a replay costs one graph launch and the longer of the
- * two chains.  Arguments are exactly those of fsem_pesq_stoi_score; `pesq` or `stoi` may be NULL (that chain and its
- * outputs are skipped).  The graph bakes in every pointer: inputs, outputs and workspaces must stay allocated, the
- * caller rewrites the INPUT buffers in place between replays (the static-buffer contract of CUDA graphs).
- * fsem_graph_launch is stream-ordered and does not synchronise; replays of one graph must not overlap (they share the
- * workspaces): launch them on one stream.  fsem_graph_nodes: kernel nodes per replay. */
+ * captures ONE scoring of fixed device buffers into a CUDA graph.  The batch is cut into `slices` contiguous parts
+ * (<= 0: the library's choice, currently 1; at most 16) and every part's PESQ chain and STOI chain is a PARALLEL branch (they share
+ * nothing but the read-only inputs): a replay costs one graph launch, small batches pay the longer of the two chains
+ * instead of their sum, and for large batches the tail of every kernel overlaps with another branch's work.  Scores do
+ * not depend on the slicing: they are bit-identical to fsem_pesq_stoi_score on the whole batch (the IIR time-chunk grid,
+ * the only batch-dependent arithmetic, is planned for the whole batch).  Arguments as for fsem_pesq_stoi_score; `pesq`
+ * or `stoi` may be NULL (that chain and its outputs are skipped).  The graph owns its workspaces and bakes in every
+ * pointer: inputs and outputs must stay allocated, the caller rewrites the INPUT buffers in place between replays (the
+ * static-buffer contract of CUDA graphs).  fsem_graph_launch is stream-ordered and does not synchronise; replays of one
+ * graph must not overlap (they share the workspaces): launch them on one stream.  fsem_graph_nodes: kernel nodes per
+ * replay; fsem_graph_slices: the slice count in use. */
 typedef struct fsem_graph fsem_graph_t;
 FSEM_API int fsem_graph_create(fsem_graph_t** out, fsem_pesq_ctx_t* pesq, fsem_stoi_ctx_t* stoi, const fsem_batch_t* in,
                       int dtype, float* mos_out, int32_t* pesq_status_out, float* stoi_out, float* estoi_out,
-                      int32_t* kept_frames_out, int32_t* stoi_status_out, void* ws_pesq, size_t ws_pesq_bytes,
-                      void* ws_stoi, size_t ws_stoi_bytes);
+                      int32_t* kept_frames_out, int32_t* stoi_status_out, int slices);
 FSEM_API int fsem_graph_launch(fsem_graph_t* g, void* stream);
 FSEM_API int fsem_graph_nodes(const fsem_graph_t* g);
+FSEM_API int fsem_graph_slices(const fsem_graph_t* g);
 FSEM_API int fsem_graph_destroy(fsem_graph_t* g);
 
 /* ------------------------------------------------------------------ resample-on-ingest (building block)

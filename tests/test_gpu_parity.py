@@ -645,14 +645,14 @@ def test_pesq_ragged_batch_with_empty_and_short_items(pesq):
         assert abs(want - mos[i]) <= 2e-4, (i, lens[i], want, mos[i])
 
 
-@pytest.mark.parametrize("shape", [(4, 160000, False), (6, 48000, True), (40, 40004, False)])
+@pytest.mark.parametrize("shape", [(4, 160000, False, 0), (6, 48000, True, 2), (40, 40004, False, 3), (70, 33000, True, 16)])
 def test_captured_scorer_against_oracle_and_direct_calls(shape, pesq, stoi_metrics):
     """CUDA-graph path (fsem_graph_*: the PESQ and STOI chains as parallel branches of one graph): scores against the
     float64 ORACLE, bit-identical to the direct entry point, and replays follow in-place updates of the captured
     buffers (the README shape 4 x 10 s is the case the graph exists for)."""
     from fast_speech_enhancement_metrics_b200 import CapturedScorer, score_pesq_stoi_tensors
     from fast_speech_enhancement_metrics_b200.synth import synth_batch
-    b, n, ragged = shape
+    b, n, ragged, slices = shape
     st = stoi_metrics(16000)
     clean, deg, _ = synth_batch(777 + b, b, n)
     clean2, deg2, _ = synth_batch(888 + b, b, n)
@@ -661,8 +661,8 @@ def test_captured_scorer_against_oracle_and_direct_calls(shape, pesq, stoi_metri
         lens = np.random.default_rng(b).integers(20000, n + 1, size=b).tolist()
         lens[0] = n
     c, d = torch.from_numpy(clean).cuda(), torch.from_numpy(deg).cuda()
-    scorer = CapturedScorer(pesq, st, c, d, lens)
-    assert scorer.kernel_nodes >= 10
+    scorer = CapturedScorer(pesq, st, c, d, lens, slices=slices)       # scores must not depend on the slicing
+    assert scorer.slices == (slices or 1) and scorer.kernel_nodes >= 10 * scorer.slices
     for cc, dd in ((clean, deg), (clean2, deg2), (clean, deg)):
         c.copy_(torch.from_numpy(cc)); d.copy_(torch.from_numpy(dd))
         rows = scorer()

@@ -79,23 +79,29 @@ def main():
             row[label] = {"ms": round(ms, 4), "audio_s_per_s": round(audio_s / (ms * 1e-3), 1), "kernels_ms": prof}
         both = row["PESQ"]["ms"] + row["STOI"]["ms"]
         row["PESQ+STOI"] = {"ms": round(both, 4), "audio_s_per_s": round(audio_s / (both * 1e-3), 1)}
-        # the same scoring as ONE CUDA graph (two parallel branches): CUDA events around `steps` replays
-        scorer = CapturedScorer(pesq, stoi, c, d, lengths)
-        for _ in range(3):
-            scorer.replay()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = args.steps * (20 if b <= 64 else 1)
-        e0.record()
-        for _ in range(reps):
-            scorer.replay()
-        e1.record()
-        torch.cuda.synchronize()
-        gms = e0.elapsed_time(e1) / reps
-        row["PESQ+STOI graph"] = {"ms": round(gms, 4), "audio_s_per_s": round(audio_s / (gms * 1e-3), 1),
-                                  "kernel_nodes": scorer.kernel_nodes, "speedup_vs_calls": round(both / gms, 3)}
-        scorer.close()
-        del scorer
+        # the same scoring as ONE CUDA graph (parallel branches; large batches also cut into slices): CUDA events
+        # around `steps` replays
+        def graph_ms(slices):
+            scorer = CapturedScorer(pesq, stoi, c, d, lengths, slices=slices)
+            for _ in range(3):
+                scorer.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = args.steps * (20 if b <= 64 else 1)
+            e0.record()
+            for _ in range(reps):
+                scorer.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            out = (e0.elapsed_time(e1) / reps, scorer.kernel_nodes, scorer.slices)
+            scorer.close()
+            return out
+        gms, nodes, used = graph_ms(0)
+        row["PESQ+STOI graph"] = {"ms": round(gms, 4), "audio_s_per_s": round(audio_s / (gms * 1e-3), 1), "slices": used,
+                                  "kernel_nodes": nodes, "speedup_vs_calls": round(both / gms, 3)}
+        if b >= 512:
+            row["PESQ+STOI graph"]["by_slices"] = {str(k): round(graph_ms(k)[0], 4) for k in (1, 2, 3, 4, 8)}
+            print("   by slices:", row["PESQ+STOI graph"]["by_slices"], flush=True)
         rows.append(row)
         print("%-42s PESQ %9.3f ms  STOI %9.3f ms  both %12.0f audio-s/s   graph %9.3f ms (x%.2f)" % (
             name, row["PESQ"]["ms"], row["STOI"]["ms"], row["PESQ+STOI"]["audio_s_per_s"], gms, both / gms), flush=True)
