@@ -159,9 +159,9 @@ struct HostPipe {
     }
 };
 
-// items per chunk of the host pipeline: ~128 MB of input per chunk, at least 1 item
-int64_t host_chunk_items(int64_t batch, int64_t n) {
-    const int64_t bytes_per_item = 2 * n * (int64_t)sizeof(float);
+// items per chunk of the host pipeline: ~128 MB of input per chunk (in the dtype that crosses PCIe), at least 1 item
+int64_t host_chunk_items(int64_t batch, int64_t n, size_t es) {
+    const int64_t bytes_per_item = 2 * n * (int64_t)es;
     int64_t items = (int64_t(128) << 20) / (bytes_per_item > 0 ? bytes_per_item : 1);
     if (items < 1) items = 1;
     if (items > batch) items = batch;
@@ -375,6 +375,9 @@ extern "C" int fsem_pesq_create(fsem_pesq_ctx_t** out, const fsem_pesq_design_t*
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(pesq_bark_kernel<kBarkThreadsWide, kBarkTileWide>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bark_dyn_smem(kBarkTileWide));
+    if (e == cudaSuccess && bark_dyn_smem(kBarkTile) > 0)
+        e = cudaFuncSetAttribute(pesq_bark_kernel<kBarkThreads, kBarkTile>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bark_dyn_smem(kBarkTile));
     if (e != cudaSuccess) {
         cudaFree(ctx->d_tab);
         if (ctx->d_rs_taps) cudaFree(ctx->d_rs_taps);
@@ -910,7 +913,7 @@ int score_host_any(const char* who, fsem_pesq_ctx* pctx, fsem_stoi_ctx* sctx, co
     // staged rows as uploaded: 16-byte aligned pitch; the first kernel of either chain reads them in their own dtype
     // (no widening pass: a 2-byte batch is read from HBM at 2 bytes per sample as well)
     const int64_t rstride = round_up(n, 16 / (int64_t)es);
-    const int64_t per = host_chunk_items(batch, n);
+    const int64_t per = host_chunk_items(batch, n, es);
     const size_t raw_sig = align256(es * per * rstride);
     const size_t in_bytes = 2 * raw_sig + align256(sizeof(int32_t) * per);
     const size_t conv_sig = 0;

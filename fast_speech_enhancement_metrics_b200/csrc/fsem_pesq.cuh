@@ -653,8 +653,11 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
 // barriers (128-frame tiles were slower) -- and (640 threads, 320-frame tiles) for batches that cannot fill the SMs
 // anyway, where the kernel's latency is the number of serial tile rounds (2 instead of 10 for a 10 s utterance).
 // Frame tiles live in dynamic shared memory: 2 x kTile x 49 Bark powers + the per-frame flags.
-constexpr int kBarkThreads = 128;
-constexpr int kBarkTile = 64;
+#ifndef FSEM_BARK_THREADS
+#define FSEM_BARK_THREADS 128
+#endif
+constexpr int kBarkThreads = FSEM_BARK_THREADS;
+constexpr int kBarkTile = FSEM_BARK_THREADS / 2;
 constexpr int kBarkThreadsWide = 640;
 constexpr int kBarkTileWide = 320;
 __host__ __device__ constexpr size_t bark_dyn_smem(int tile) { return tile <= 64 ? 0 : sizeof(float) * (size_t)tile * (2 * FSEM_PESQ_NBANDS + 2); }
