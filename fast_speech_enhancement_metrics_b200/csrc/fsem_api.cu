@@ -287,7 +287,7 @@ PesqPlan pesq_plan(const fsem_pesq_ctx* ctx, int64_t batch, int64_t n_in) {
     p.off_rs = off;      off = align256(off + (p.resample ? sizeof(float) * 2 * batch * p.rstride : 0));
     p.off_rslen = off;   off = align256(off + (p.resample ? sizeof(int32_t) * batch : 0));
     p.off_z = off;       off = align256(off + sizeof(float) * 2 * batch * p.zstride);
-    p.off_bark = off;    off = align256(off + sizeof(float) * 2 * batch * p.tpitch * FSEM_PESQ_NBANDS);
+    p.off_bark = off;    off = align256(off + sizeof(float) * 2 * batch * p.tpitch * kBarkRow);
     p.off_dist = off;    off = align256(off + sizeof(float) * 2 * batch * p.tpitch);
     p.off_power = off;   off = align256(off + sizeof(double) * 2 * batch);
     p.off_order = off;   off = align256(off + sizeof(int32_t) * batch);              // variable-length batches only
@@ -548,9 +548,10 @@ extern "C" int fsem_pesq_debug_taps(fsem_pesq_ctx_t* ctx, int64_t batch, int64_t
     const char* ws = static_cast<const char*>(workspace);
     if (frames_out) *frames_out = p.tmax;
     if (bark_out)
-        FSEM_CUDA(cudaMemcpy2DAsync(bark_out, sizeof(float) * p.tmax * FSEM_PESQ_NBANDS, ws + p.off_bark,
-                                    sizeof(float) * p.tpitch * FSEM_PESQ_NBANDS, sizeof(float) * p.tmax * FSEM_PESQ_NBANDS,
-                                    (size_t)(2 * batch), cudaMemcpyDeviceToDevice, stream));
+        for (int64_t r = 0; r < 2 * batch; ++r)                  // rows of 49 valid floats at pitch kBarkRow, tpitch frames per item
+            FSEM_CUDA(cudaMemcpy2DAsync(bark_out + r * p.tmax * FSEM_PESQ_NBANDS, sizeof(float) * FSEM_PESQ_NBANDS,
+                                        ws + p.off_bark + sizeof(float) * r * p.tpitch * kBarkRow, sizeof(float) * kBarkRow,
+                                        sizeof(float) * FSEM_PESQ_NBANDS, (size_t)p.tmax, cudaMemcpyDeviceToDevice, stream));
     if (power_out)
         FSEM_CUDA(cudaMemcpyAsync(power_out, ws + p.off_power, sizeof(double) * 2 * batch, cudaMemcpyDeviceToDevice,
                                   stream));

@@ -437,6 +437,11 @@ constexpr int kSpecWarps = FSEM_FFT_WARPS;
 // 3-slot ring of half-frames (256 samples of the clean and of the degraded signal per slot) filled by TMA bulk
 // copies: frame f needs halves f and f+1, half f+2 is in flight while frame f is transformed, so the global-load
 // latency is off the critical path and every sample is fetched from L2/HBM once (frames overlap by 50 %).
+// Row pitch of the Bark buffer: 49 bands + 1 pad float.  The Bark kernel reads a tile as (frame = lane / 2, band = lane % 2
+// + 2k): with 50 floats per frame the 32 lanes of a warp hit 32 different banks (18 * frame mod 32 runs through the even
+// banks); with 49 two of them collide on every access (20 % of that kernel's shared-memory wavefronts).
+constexpr int kBarkRow = FSEM_PESQ_NBANDS + 1;
+
 // Level alignment (PESQ.py:97-100): band-pass energy of one signal = fixed-order sum of the IIR pass's chunk partials,
 // g^2 = 1e7 / (sum(y^2) / (len + 5120) / 1.04684).  One definition for the spectrum kernel (which applies g^2 to the
 // Bark powers it stores) and the Bark kernel (which decides NaN / all-zero items on it).
@@ -471,7 +476,7 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
                      const int64_t* __restrict__ frame_prefix, int64_t batch, int64_t n, int tmax, int tpitch,
                      const double* __restrict__ partial /* [2][batch][nchunks] band-pass energies of the IIR pass */,
                      int nchunks, const PesqTables* __restrict__ tab,
-                     float* __restrict__ bark /* [2][batch][tpitch][49], level-aligned */) {
+                     float* __restrict__ bark /* [2][batch][tpitch][kBarkRow], level-aligned */) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -620,8 +625,8 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
         packed_power_regs(ar, ai, br, bi, lane, pc, pd);
         if (lane == 0) { pc[0] = 0.f; pd[0] = 0.f; }             // bin 0: "we won't use energy feature" (PESQ.py:136)
         scan.scan_store(pc, pd, wbuf, lane);
-        float* __restrict__ out_c = bark + (item * tpitch + f) * FSEM_PESQ_NBANDS;
-        float* __restrict__ out_d = bark + ((batch + item) * tpitch + f) * FSEM_PESQ_NBANDS;
+        float* __restrict__ out_c = bark + (item * tpitch + f) * kBarkRow;
+        float* __restrict__ out_d = bark + ((batch + item) * tpitch + f) * kBarkRow;
         const float lo_c = g_lo.sum(S), lo_d = g_lo.sum(S + kBandSStride);
         const float hi_c = g_hi.sum(S), hi_d = g_hi.sum(S + kBandSStride);     // all lanes: no divergence around the loads
         const float2 g2 = *reinterpret_cast<const float2*>(sm.gain);
@@ -660,7 +665,7 @@ constexpr int kBarkThreads = FSEM_BARK_THREADS;
 constexpr int kBarkTile = FSEM_BARK_THREADS / 2;
 constexpr int kBarkThreadsWide = 640;
 constexpr int kBarkTileWide = 320;
-__host__ __device__ constexpr size_t bark_dyn_smem(int tile) { return tile <= 64 ? 0 : sizeof(float) * (size_t)tile * (2 * FSEM_PESQ_NBANDS + 2); }
+__host__ __device__ constexpr size_t bark_dyn_smem(int tile) { return tile <= 64 ? 0 : sizeof(float) * (size_t)tile * (2 * kBarkRow + 2); }
 
 // x^y for x > 0 through the SFU (lg2.approx / ex2.approx, one MUFU each: the .ftz forms skip the denormal range fix-ups,
 // and every argument here is a normal number): relative error ~1e-6 for the exponents used (|y * log2 x| < 10), three
@@ -692,14 +697,14 @@ pesq_bark_kernel(const float* __restrict__ bark, const double* __restrict__ part
     // around provably distinct arrays); only the wide shape needs dynamic memory
     constexpr bool kDyn = bark_dyn_smem(kTile) > 0;
     extern __shared__ __align__(16) float s_bark_dyn[];
-    __shared__ __align__(16) float s_tile_st[kDyn ? 1 : 2][kDyn ? 1 : kTile][FSEM_PESQ_NBANDS];
+    __shared__ __align__(16) float s_tile_st[kDyn ? 1 : 2][kDyn ? 1 : kTile][kBarkRow];
     __shared__ float s_live_st[kDyn ? 1 : kTile];
     __shared__ float s_fr_st[kDyn ? 1 : kTile];
-    float (*s_tile)[kTile][FSEM_PESQ_NBANDS] =
-        kDyn ? reinterpret_cast<float (*)[kTile][FSEM_PESQ_NBANDS]>(s_bark_dyn)
-             : reinterpret_cast<float (*)[kTile][FSEM_PESQ_NBANDS]>(&s_tile_st[0][0][0]);
-    float* s_live = kDyn ? s_bark_dyn + 2 * kTile * FSEM_PESQ_NBANDS : s_live_st;     // 1 - silent flag of a frame
-    float* s_fr = kDyn ? s_bark_dyn + 2 * kTile * FSEM_PESQ_NBANDS + kTile : s_fr_st;
+    float (*s_tile)[kTile][kBarkRow] =
+        kDyn ? reinterpret_cast<float (*)[kTile][kBarkRow]>(s_bark_dyn)
+             : reinterpret_cast<float (*)[kTile][kBarkRow]>(&s_tile_st[0][0][0]);
+    float* s_live = kDyn ? s_bark_dyn + 2 * kTile * kBarkRow : s_live_st;     // 1 - silent flag of a frame
+    float* s_fr = kDyn ? s_bark_dyn + 2 * kTile * kBarkRow + kTile : s_fr_st;
     __shared__ float s_thr[FSEM_PESQ_NBANDS], s_thr100[FSEM_PESQ_NBANDS], s_ithr[FSEM_PESQ_NBANDS], s_exp[FSEM_PESQ_NBANDS],
         s_lsc[FSEM_PESQ_NBANDS], s_w[FSEM_PESQ_NBANDS], s_ratio[FSEM_PESQ_NBANDS];
     __shared__ float s_g2[2];
@@ -742,8 +747,8 @@ pesq_bark_kernel(const float* __restrict__ bark, const double* __restrict__ part
         }
         return;
     }
-    const float* __restrict__ bc = bark + item * (int64_t)tpitch * FSEM_PESQ_NBANDS;
-    const float* __restrict__ bd = bark + (batch + item) * (int64_t)tpitch * FSEM_PESQ_NBANDS;
+    const float* __restrict__ bc = bark + item * (int64_t)tpitch * kBarkRow;
+    const float* __restrict__ bd = bark + (batch + item) * (int64_t)tpitch * kBarkRow;
     const uint32_t tile_c = smem_u32(&s_tile[0][0][0]), tile_d = smem_u32(&s_tile[1][0][0]);
     unsigned parity = 0;
 
@@ -752,11 +757,11 @@ pesq_bark_kernel(const float* __restrict__ bark, const double* __restrict__ part
     auto load_tile = [&](int f0, int nf) {
         __syncthreads();
         if (tid == 0) {
-            const uint32_t bytes = (uint32_t)((nf + 3) & ~3) * (FSEM_PESQ_NBANDS * sizeof(float));
+            const uint32_t bytes = (uint32_t)((nf + 3) & ~3) * (kBarkRow * sizeof(float));
             fence_proxy_async();
             mbar_arrive_expect_tx(bar, 2 * bytes);
-            bulk_copy_g2s(tile_c, bc + (int64_t)f0 * FSEM_PESQ_NBANDS, bytes, bar);
-            bulk_copy_g2s(tile_d, bd + (int64_t)f0 * FSEM_PESQ_NBANDS, bytes, bar);
+            bulk_copy_g2s(tile_c, bc + (int64_t)f0 * kBarkRow, bytes, bar);
+            bulk_copy_g2s(tile_d, bd + (int64_t)f0 * kBarkRow, bytes, bar);
         }
         mbar_wait(bar, parity);
         parity ^= 1u;
@@ -789,7 +794,7 @@ pesq_bark_kernel(const float* __restrict__ bark, const double* __restrict__ part
             float acc = 0.f;                                   // one tile in float32, tiles in float64
 #pragma unroll 4
             for (int f = 0; f < nf; ++f) {
-                const float p = col[f * FSEM_PESQ_NBANDS];
+                const float p = col[f * kBarkRow];
                 acc += (p > thr100) ? p * s_live[f] : 0.f;
             }
             band_acc += (double)acc;
