@@ -1146,7 +1146,7 @@ extern "C" int fsem_lsd_create(fsem_lsd_ctx_t** out, const float* hann512) {
         return fail(FSEM_E_CUDA, "fsem_lsd_create: %s", cudaGetErrorString(e));
     }
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lsd_frames_kernel, kLsdWarps * 32, 0) == cudaSuccess && occ > 0)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lsd_frames_kernel<true>, kLsdWarps * 32, 0) == cudaSuccess && occ > 0)
         ctx->ctas_per_sm = occ;
     *out = ctx;
     return FSEM_OK;
@@ -1185,9 +1185,15 @@ extern "C" int fsem_lsd_score_f32(fsem_lsd_ctx_t* ctx, const fsem_batch_t* in, f
     int64_t grid = ceil_div(units, kLsdWarps);
     const int64_t cap = (int64_t)ctx->dev.sms * ctx->ctas_per_sm;
     if (grid > cap) grid = cap;
+    const bool vec2 = (reinterpret_cast<uintptr_t>(in->clean) & 7u) == 0 && (reinterpret_cast<uintptr_t>(in->deg) & 7u) == 0 &&
+                      in->stride % 2 == 0;
     { ProfScope prof_(K_LSD_FRAMES, stream);
-      lsd_frames_kernel<<<(unsigned)grid, kLsdWarps * 32, 0, stream>>>(in->clean, in->deg, in->lengths, in->batch, in->n,
-                                                                     in->stride, p.tmax, ctx->d_hann, alpha, frames); }
+      if (vec2)
+          lsd_frames_kernel<true><<<(unsigned)grid, kLsdWarps * 32, 0, stream>>>(
+              in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, p.tmax, ctx->d_hann, alpha, frames);
+      else
+          lsd_frames_kernel<false><<<(unsigned)grid, kLsdWarps * 32, 0, stream>>>(
+              in->clean, in->deg, in->lengths, in->batch, in->n, in->stride, p.tmax, ctx->d_hann, alpha, frames); }
     FSEM_LAUNCHED();
     lsd_finalize_kernel<<<(unsigned)ceil_div(in->batch, 128), 128, 0, stream>>>(frames, in->lengths, in->batch, in->n,
                                                                                p.tmax, lsd_out);

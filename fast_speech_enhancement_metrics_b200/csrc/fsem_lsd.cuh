@@ -44,6 +44,15 @@ lsd_scale_kernel(const float* __restrict__ clean, const float* __restrict__ deg,
 
 constexpr int kLsdWarps = 8;
 
+__device__ __forceinline__ float lsd_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lsd_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lsd_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// kVec2: rows are 8-byte aligned with an even pitch, so a lane fetches its sample pairs (2L, 2L + 1) of an interior frame
+// with one 64-bit load and no bounds checks.  The per-bin log ratio goes through the SFU (sqrt / rcp / lg2 .approx, ~1e-6
+// relative: two orders of magnitude inside the 5e-4 the float32 FFT round-off of near-eps bins already costs, tests/
+// test_lsd.py): 10.2 -> see DESIGN.md at 8192 x 10 s.
+template <bool kVec2>
 __global__ void __launch_bounds__(kLsdWarps * 32, 2)
 lsd_frames_kernel(const float* __restrict__ clean, const float* __restrict__ deg, const int32_t* __restrict__ lengths,
                   int64_t batch, int64_t n, int64_t stride, int tmax, const float* __restrict__ hann,
@@ -76,34 +85,46 @@ lsd_frames_kernel(const float* __restrict__ clean, const float* __restrict__ deg
             const float* __restrict__ d = deg + item * stride;
             const int first = f * 256 - 256;                     // centred frames, zero ("constant") padding
             float re[16], im[16];
+            if (kVec2 && first >= 0 && first + 512 <= len) {     // interior frame (warp-uniform)
+                const float2* __restrict__ pc2 = reinterpret_cast<const float2*>(c + first) + lane;
+                const float2* __restrict__ pd2 = reinterpret_cast<const float2*>(d + first) + lane;
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int i = first + fft_in_index(lane, h, j);
-                    const bool ok = i >= 0 && i < len;
-                    re[8 * h + j] = ok ? __ldg(c + i) * win[8 * h + j] : 0.f;
-                    im[8 * h + j] = ok ? __ldg(d + i) * win[8 * h + j] : 0.f;
+                for (int j = 0; j < 8; ++j) {                    // samples 2*lane + 64 j and + 1 = fft_in_index(lane, 0 | 1, j)
+                    const float2 cv = __ldg(pc2 + 32 * j), dv = __ldg(pd2 + 32 * j);
+                    re[j] = cv.x * win[j];  re[8 + j] = cv.y * win[8 + j];
+                    im[j] = dv.x * win[j];  im[8 + j] = dv.y * win[8 + j];
                 }
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int i = first + fft_in_index(lane, h, j);
+                        const bool ok = i >= 0 && i < len;
+                        re[8 * h + j] = ok ? __ldg(c + i) * win[8 * h + j] : 0.f;
+                        im[8 * h + j] = ok ? __ldg(d + i) * win[8 * h + j] : 0.f;
+                    }
+            }
             float ar[8], ai[8], br[8], bi[8];
             warp_fft512<false>(re, im, buf, tw, lane, ar, ai, br, bi);
             float pc[8], pd[8];
             packed_power_regs(ar, ai, br, bi, lane, pc, pd);     // 4x the power of this lane's 8 bins below 256
             const float a = fabsf(alpha[item]);
-            float acc = 0.f;
+            float acc = 0.f;                                     // sum of log2(...)^2; ln(2)^2 is applied once per frame
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float den = fmaf(a, sqrtf(pd[j] * kPackedPowerScale), kLsdEps);
-                const float l = logf(pc[j] * kPackedPowerScale / (den * den) + kLsdEps);
+                const float den = fmaf(a, lsd_sqrt(pd[j] * kPackedPowerScale), kLsdEps);
+                const float l = lsd_lg2(fmaf(pc[j] * kPackedPowerScale, lsd_rcp(den * den), kLsdEps));
                 acc = fmaf(l, l, acc);
             }
             if (lane == 0) {                                     // Nyquist bin 256 = A[4] of lane 0: C = Re Z, D = Im Z
                 const float den = fmaf(a, fabsf(ai[4]), kLsdEps);
-                const float l = logf(ar[4] * ar[4] / (den * den) + kLsdEps);
+                const float l = lsd_lg2(fmaf(ar[4] * ar[4], lsd_rcp(den * den), kLsdEps));
                 acc = fmaf(l, l, acc);
             }
             acc = warp_sum(acc);
-            if (lane == 0) frame_lsd[item * tmax + f] = sqrtf(acc * (1.f / 257.f));
+            constexpr float kLn2Sq = 0.69314718056f * 0.69314718056f;
+            if (lane == 0) frame_lsd[item * tmax + f] = sqrtf(acc * (kLn2Sq / 257.f));
             __syncwarp();
         }
         if (++f == tmax) {
