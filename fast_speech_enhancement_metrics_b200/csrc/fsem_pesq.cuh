@@ -445,12 +445,14 @@ constexpr int kBarkRow = FSEM_PESQ_NBANDS + 1;
 // Level alignment (PESQ.py:97-100): band-pass energy of one signal = fixed-order sum of the IIR pass's chunk partials,
 // g^2 = 1e7 / (sum(y^2) / (len + 5120) / 1.04684).  One definition for the spectrum kernel (which applies g^2 to the
 // Bark powers it stores) and the Bark kernel (which decides NaN / all-zero items on it).
+// called by all 32 lanes of a warp; every lane returns the same value (strided partial sums, xor-butterfly: a fixed order).
+// Tiny batches cut the signal into hundreds of chunks, so a serial sum per frame-warp would dominate their spectrum kernel.
 __device__ __forceinline__ double pesq_band_power(const double* __restrict__ partial, int nchunks, int64_t batch, int sig,
-                                                  int64_t item) {
+                                                  int64_t item, int lane) {
     const double* p = partial + ((int64_t)sig * batch + item) * nchunks;
     double acc = 0.0;
-    for (int c = 0; c < nchunks; ++c) acc += p[c];
-    return acc;
+    for (int c = lane; c < nchunks; c += 32) acc += p[c];
+    return warp_sum(acc);
 }
 __device__ __forceinline__ float pesq_level_gain(double power, int len) {
     return (float)(1.0e7 * ((double)len + 5120.0) * 1.04684 / power);
@@ -567,7 +569,9 @@ pesq_spectrum_kernel(const float* __restrict__ z, int64_t zstride, const int32_t
     // level alignment is linear up to the power spectrum: g^2 of the item multiplies the Bark powers as they are stored
     // (an all-zero item has g^2 = inf and stores NaN rows; the Bark kernel never reads them)
     auto set_gain = [&](int64_t it, int ln) {
-        if (lane < 2) sm.gain[lane] = pesq_level_gain(pesq_band_power(partial, nchunks, batch, lane, it), ln);
+        const float gc = pesq_level_gain(pesq_band_power(partial, nchunks, batch, 0, it, lane), ln);
+        const float gd = pesq_level_gain(pesq_band_power(partial, nchunks, batch, 1, it, lane), ln);
+        if (lane == 0) { sm.gain[0] = gc; sm.gain[1] = gd; }
         __syncwarp();
     };
     set_gain(item, len);
@@ -728,12 +732,15 @@ pesq_bark_kernel(const float* __restrict__ bark, const double* __restrict__ part
         s_lsc[tid] = tab->loud_scale[tid];
         s_w[tid] = tab->width[tid];
     }
-    if (tid < 2) {
+    if (tid < 64) {
         // level alignment (PESQ.py:97-100): g^2 = 1e7 / (sum(y^2) / (len + 5120) / 1.04684); applied by the spectrum
-        // kernel (pesq_level_gain, the same expression), recomputed here for the NaN / all-zero decision
-        const double acc = pesq_band_power(partial, nchunks, batch, tid, item);
-        power_out[(int64_t)tid * batch + item] = acc;
-        s_g2[tid] = pesq_level_gain(acc, len);
+        // kernel (pesq_level_gain, the same expression), recomputed here for the NaN / all-zero decision (warp = signal)
+        const int sig = tid >> 5;
+        const double acc = pesq_band_power(partial, nchunks, batch, sig, item, tid & 31);
+        if ((tid & 31) == 0) {
+            power_out[(int64_t)sig * batch + item] = acc;
+            s_g2[sig] = pesq_level_gain(acc, len);
+        }
     }
     if (tid == 0) {
         mbar_init(bar, 1);
