@@ -248,6 +248,7 @@ def parity_block(pesq, stoi, clean, deg, gathered, lo, hi, world, device, items)
     k_equal = bool(np.array_equal(k_got, o_k))
     ref_stats = [-1.0, -1.0, -1.0]
     ref_extra = [0.0, 0.0]          # items whose |dPESQ| vs the reference exceeds the bar; max |reference - oracle| over those
+    ref_unexplained = 0.0           # ... of which the reference itself is within the bar of the oracle (a real discrepancy)
     if make_ref.available():
         RP, RS = make_ref.load()
         rp = np.array([r["PESQ"] for r in RP(FS, use_gpu=False)(c, d)])
@@ -258,12 +259,13 @@ def parity_block(pesq, stoi, clean, deg, gathered, lo, hi, world, device, items)
         over = np.abs(got[:, 0] - rp) > 1e-3
         if over.any():
             ref_extra = [float(over.sum()), float(np.max(np.abs(rp[over] - o_p[over])))]
+            ref_unexplained = float((over & (np.abs(rp - o_p) <= 1e-3)).sum())
     finite_margin = margin[torch.isfinite(margin)]
     mmin = float(finite_margin.min()) if finite_margin.numel() else float("inf")
     near = int((margin < 1e-4).sum())
     red_max = torch.tensor(stats + ref_stats + [0.0 if k_equal else 1.0, 0.0 if gather_equal else 1.0, -mmin],
                            dtype=torch.float64, device=device)
-    red_sum = torch.tensor([float(len(idx)), float(near), ref_extra[0]], dtype=torch.float64, device=device)
+    red_sum = torch.tensor([float(len(idx)), float(near), ref_extra[0], ref_unexplained], dtype=torch.float64, device=device)
     red_max = torch.cat([red_max, torch.tensor([ref_extra[1]], dtype=torch.float64, device=device)])
     if world > 1:
         dist.all_reduce(red_max, op=dist.ReduceOp.MAX)
@@ -285,6 +287,8 @@ def parity_block(pesq, stoi, clean, deg, gathered, lo, hi, world, device, items)
             # how far the REFERENCE is from the float64 evaluation of its own algorithm (the CUDA path is within
             # `pesq_max_abs` of that evaluation on every item)
             out["vs_reference"]["reference_vs_oracle_max_abs_on_those_items"] = m[9]
+            # 0 = on every item above the bar the reference is itself more than the bar away from the float64 evaluation
+            out["vs_reference"]["items_above_1e-3_not_explained_by_reference_noise"] = int(red_sum[3].item())
     # the pinned checker is the float64 oracle (tests/test_oracle_vs_golden.py pins it on the reference's outputs)
     out["ok"] = bool(m[0] <= 1e-3 and m[1] <= 1e-4 and m[2] <= 1e-4 and out["k_equal"]
                      and out["gathered_rows_equal_rank_local_bitwise"])
