@@ -147,7 +147,7 @@ class CapturedScorer:
     def replay(self):
         """One graph launch on the current stream; returns the captured output tensors (scores[3, B] = PESQ / STOI /
         ESTOI rows, pesq_status, kept_frames, stoi_status), valid in stream order, overwritten by the next replay."""
-        if not self._handle:
+        if not getattr(self, "_handle", None):
             raise Exception("CapturedScorer is closed")
         with torch.cuda.device(self.device):
             _lib.check(self._lib.fsem_graph_launch(
@@ -169,7 +169,7 @@ class CapturedScorer:
         return [{k: cols[k][j] for k, _ in names} for j in range(packed.shape[1])]
 
     def close(self):
-        h, self._handle = self._handle, C.c_void_p()
+        h, self._handle = getattr(self, "_handle", None), C.c_void_p()   # a constructor that raised never set it
         if h:
             try:
                 torch.cuda.synchronize(self.device)

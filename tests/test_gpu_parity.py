@@ -701,3 +701,52 @@ def test_captured_scorer_single_metric_and_errors(pesq, stoi_metrics):
         CapturedScorer(pesq, None, c[:, :4000], d[:, :4000])       # < 20 PESQ frames, like the direct call
     after = pesq(c, d)                                             # a failed capture leaves the library usable
     assert after == only_p()
+
+
+@pytest.mark.parametrize("shape", [(5, 24000, False), (33, 20004, False), (37, 17003, True)])
+def test_kernels_stay_inside_their_buffers(shape, pesq, stoi_metrics):
+    """compute-sanitizer is not available on the GPU pool, so bounds are checked by hand: the inputs are views into a
+    NaN-filled buffer (NaN rows before and after, NaN in the pitch padding of every row) and the workspaces are views
+    into canary-filled buffers.  Any read outside the rows that reaches a score turns it into NaN or moves it away from
+    the oracle; any write outside the planned workspace breaks a canary."""
+    from fast_speech_enhancement_metrics_b200.synth import synth_batch
+    b, n, ragged = shape
+    st = stoi_metrics(16000)
+    clean, deg, _ = synth_batch(99 + b, b, n)
+    lens = None
+    if ragged:
+        lens = np.random.default_rng(b).integers(6000, n + 1, size=b).tolist()
+        lens[0], lens[-1] = n, 6000
+    pitch = n + 52                                              # multiple of 4 (vector paths) for these n, not of 32
+    pad_rows = 2
+
+    def guarded(x):
+        big = torch.full((b + 2 * pad_rows, pitch), float("nan"), dtype=torch.float32, device="cuda")
+        view = big[pad_rows:pad_rows + b, :n]
+        view.copy_(torch.from_numpy(x))
+        return big, view
+
+    bc, c = guarded(clean)
+    bd, d = guarded(deg)
+    G = 4096
+    for metric, nbytes in ((pesq, pesq._lib.fsem_pesq_workspace_bytes(pesq._ctx, b, n)),
+                           (st, st._lib.fsem_stoi_workspace_bytes(st._ctx, b, n))):
+        big = torch.full((int(nbytes) + 2 * G,), 0xA5, dtype=torch.uint8, device="cuda")
+        saved = metric._workspace
+        try:
+            metric._workspace = big[G:G + int(nbytes)]
+            res = metric(c, d, lengths=lens)
+            torch.cuda.synchronize()
+        finally:
+            metric._workspace = saved
+        assert bool((big[:G] == 0xA5).all()) and bool((big[G + int(nbytes):] == 0xA5).all()), type(metric).__name__
+        if metric is pesq:
+            got = np.array([r["PESQ"] for r in res])
+            assert _maxdiff(got, po.pesq_batch(clean, deg, lens)) <= 2e-4
+        else:
+            ws, we, wk = so.stoi_batch(clean, deg, 16000, lens)
+            assert _maxdiff(np.array([r["STOI"] for r in res]), ws) <= 1e-4
+            assert _maxdiff(np.array([r["ESTOI"] for r in res]), we) <= 1e-4
+    # the inputs (and their NaN surroundings) are untouched
+    assert bool(torch.isnan(bc[:pad_rows]).all()) and bool(torch.isnan(bc[pad_rows + b:]).all()) and bool(torch.isnan(bc[:, n:]).all())
+    assert np.array_equal(c.cpu().numpy(), clean) and np.array_equal(d.cpu().numpy(), deg)

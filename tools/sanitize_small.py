@@ -15,3 +15,14 @@ p8 = PESQ(8000, True)
 print(p8(c[:, :12000].contiguous(), d[:, :12000].contiguous()))
 torch.cuda.synchronize()
 print("done")
+# round 2: the graph path (bulk-copied Bark tiles, sliced branches), a 33-item batch (tiled IIR kernel), LSD / SDR
+from fast_speech_enhancement_metrics_b200 import LSD, SDR, CapturedScorer
+c33, d33, _ = synth_batch(6, 33, 20004)
+c33, d33 = torch.from_numpy(c33).cuda(), torch.from_numpy(d33).cuda()
+sc = CapturedScorer(p, s, c33, d33, slices=3)
+print(sc()[:2]); sc.close()
+sc = CapturedScorer(p, s, c, d, lengths=[24000, 5400, 17001])
+print(sc()); sc.close()
+print(LSD(16000, True)(c, d)); print(SDR(16000, True)(c, d))
+torch.cuda.synchronize()
+print("done round 2")
