@@ -111,3 +111,19 @@ def test_ingest_dtype_codes_follow_the_header():
     for bad in (torch.float64, torch.int32, torch.bfloat16):
         with pytest.raises(RuntimeError, match="expected scalar type Float"):
             _lib.dtype_code(bad)
+
+
+def test_graph_entry_points_validate_their_arguments_without_a_gpu():
+    """fsem_graph_*: argument validation comes before any CUDA call, so it can be checked here (no compute)."""
+    lib = _lib.load()
+    handle = ctypes.c_void_p()
+    batch = _lib.Batch(None, None, None, 4, 16000, 16000)
+    assert lib.fsem_graph_create(ctypes.byref(handle), None, None, ctypes.byref(batch), _lib.DTYPE_F32,
+                                 None, None, None, None, None, None, 1) == _lib.FSEM_E_INVALID
+    assert b"no metric" in lib.fsem_last_error()
+    assert not handle.value
+    assert lib.fsem_graph_create(None, None, None, ctypes.byref(batch), _lib.DTYPE_F32,
+                                 None, None, None, None, None, None, 1) == _lib.FSEM_E_INVALID
+    assert lib.fsem_graph_launch(None, None) == _lib.FSEM_E_INVALID
+    assert lib.fsem_graph_nodes(None) == 0 and lib.fsem_graph_slices(None) == 0
+    assert lib.fsem_graph_destroy(None) == _lib.FSEM_OK
