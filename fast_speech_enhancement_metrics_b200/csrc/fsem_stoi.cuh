@@ -66,15 +66,16 @@ resampled_lengths_kernel(const int32_t* __restrict__ lengths, int64_t batch, int
 // ------------------------------------------------------------------------------------------------
 // Specialised 16 kHz -> 10 kHz (8:5, half-width 10, 28 taps) resampler.
 //
-// Thread = two consecutive polyphase blocks (16 new inputs -> 10 outputs) so that every staged input
-// sample is read from shared memory ~2x instead of 3.5x; the 36 inputs a thread needs are ten LDS.128
-// from a tile padded by one float4 per four (lane pitch 5 float4 = conflict-free).  The taps arrive as a
-// kernel argument (constant bank: FFMA reads them for free) and only the statically known non-zero range
+// Thread = FOUR consecutive polyphase blocks (32 new inputs -> 20 outputs) walked with a sliding window of eight float4s
+// (two new ones per block), so every staged input sample is read from shared memory 1.9x instead of 3.5x (one block
+// per thread) or 2.75x (two blocks, round 1) -- the kernel is bound by the LSU data pipe (91 %), and its registers do not
+// grow with the blocks per thread.  The tile is padded by one float4 per eight (lane pitch 9 float4 = conflict-free).  The
+// taps arrive as a kernel argument (constant bank: FFMA reads them for free) and only the statically known non-zero range
 // of each phase is evaluated (97 of 140 FMAs per block); the host checks that the taps outside those
 // ranges are exactly zero before selecting this kernel.
 struct Resample85Taps { float h[5][28]; };
 #ifndef FSEM_RS85_BLOCKS
-#define FSEM_RS85_BLOCKS 2
+#define FSEM_RS85_BLOCKS 4
 #endif
 constexpr int kRs85Threads = 128;
 constexpr int kRs85Nb = FSEM_RS85_BLOCKS;                       // polyphase blocks (8 in -> 5 out) per thread
@@ -101,8 +102,12 @@ static_assert(kRs85TileOut % FSEM_STOI_HOP == 0, "tiles must hold whole hops");
 //     A_h = sum_r (w[r]       * y[128h + r])^2      (hop as FIRST  half of analysis frame h)
 //     B_h = sum_r (w[r + 128] * y[128h + r])^2      (hop as SECOND half of analysis frame h-1)
 // (products rounded to fp32 like the reference, sums in fp64), so that ||w * x_t||^2 = A_t + B_{t+1} (STOI.py:92-98).
+// five CTAs per SM (<= 102 registers): measured 2.99 ms against 3.30 (no cap, 110 registers), 3.13 (four) and 3.62 (six: spills)
+#ifndef FSEM_RS85_MINBLOCKS
+#define FSEM_RS85_MINBLOCKS 5
+#endif
 template <bool kVec4, typename T>
-__global__ void __launch_bounds__(kRs85Threads)
+__global__ void __launch_bounds__(kRs85Threads, FSEM_RS85_MINBLOCKS)
 stoi_resample85_kernel(const T* __restrict__ clean, const T* __restrict__ deg,
                        const int32_t* __restrict__ lengths, int64_t batch, int64_t n, int64_t stride,
                        const __grid_constant__ Resample85Taps taps, const StoiTables* __restrict__ tab,
@@ -172,16 +177,21 @@ stoi_resample85_kernel(const T* __restrict__ clean, const T* __restrict__ deg,
         __syncthreads();
         if (k + 1 < kRs85TilesPerCta && (out0 + kRs85TileOut) < L) fetch(tile + 1, pre);
         // thread t: blocks NB*t .. NB*t+NB-1 of this tile need staged floats [8*NB*t + 2, 8*NB*t + 8*NB + 22)
+        // block b reads staged floats 8b + 3 .. 8b + 28 = float4s 2b .. 2b + 7: a sliding window of eight float4s, two new
+        // ones per block, so the registers do not grow with the blocks per thread (every staged sample is then read
+        // (8 NB + 28) / (8 NB) times from shared memory: 2.75x for NB = 2, 1.9x for NB = 4)
         float xin[4 * kRs85ThreadQuads];
         const float4* src = s_in + (kRs85PadEvery + 1) * tid;
-#pragma unroll
-        for (int i = 0; i < kRs85ThreadQuads; ++i) {
+        auto load_quad = [&](int i) {
             float4 v = src[i + i / kRs85PadEvery];
             xin[4 * i] = v.x; xin[4 * i + 1] = v.y; xin[4 * i + 2] = v.z; xin[4 * i + 3] = v.w;
-        }
+        };
+#pragma unroll
+        for (int i = 0; i < 8; ++i) load_quad(i);
         float out[5 * kRs85Nb];
 #pragma unroll
         for (int b = 0; b < kRs85Nb; ++b) {
+            if (b + 1 < kRs85Nb) { load_quad(2 * b + 8); load_quad(2 * b + 9); }   // the next block's two new float4s
 #pragma unroll
             for (int p = 0; p < 5; ++p) {
                 float acc = 0.f;
@@ -229,12 +239,14 @@ stoi_resample85_kernel(const T* __restrict__ clean, const T* __restrict__ deg,
             const float4 wa = *reinterpret_cast<const float4*>(s_win + 4 * lane);
             const float4 wb = *reinterpret_cast<const float4*>(s_win + 128 + 4 * lane);
             constexpr int kWarps = kRs85Threads / 32;
-            constexpr int kHopsPerWarp = (kRs85Hops + kWarps - 1) / kWarps;        // 3
-            static_assert(kHopsPerWarp == 3, "the reduce-scatter below is written for three hops (six sums) per warp");
+            constexpr int kHopsPerWarp = (kRs85Hops + kWarps - 1) / kWarps;        // 3 (two blocks per thread), 5 (four)
+            constexpr int kHopGroups = (kHopsPerWarp + 2) / 3;                     // the reduce-scatter takes three hops (six sums)
+#pragma unroll 1
+            for (int grp = 0; grp < kHopGroups; ++grp) {
             double v[6];
 #pragma unroll
-            for (int i = 0; i < kHopsPerWarp; ++i) {
-                const int h = warp + kWarps * i;
+            for (int i = 0; i < 3; ++i) {
+                const int h = warp + kWarps * (3 * grp + i);
                 double a = 0.0, b = 0.0;
                 if (h < kRs85Hops && (h + 1) * FSEM_STOI_HOP <= valid) {              // only complete hops matter (warp-uniform)
                     const float4 x = *reinterpret_cast<const float4*>(s_out + h * FSEM_STOI_HOP + 4 * lane);
@@ -277,10 +289,11 @@ stoi_resample85_kernel(const T* __restrict__ clean, const T* __restrict__ deg,
             // lane (b16, b8, b4) now holds the total of sum index (b16 ? 3 : 0) + (b8 ? 2 : (b4 ? 1 : 0)); b8 && b4 is the zero
             const int local = b8 ? 2 : (b4 ? 1 : 0);
             const int sum_idx = (b16 ? 3 : 0) + local;
-            const int h = warp + kWarps * (sum_idx >> 1);
+            const int h = warp + kWarps * (3 * grp + (sum_idx >> 1));
             if ((lane & 3) == 0 && !(b8 && b4) && h < kRs85Hops && (h + 1) * FSEM_STOI_HOP <= valid) {
                 double* dst = reinterpret_cast<double*>(hop_energy + item * hops_max + tile * kRs85Hops + h);
                 dst[sum_idx & 1] = one;                                           // .x = A_h, .y = B_h
+            }
             }
         }
         __syncthreads();
