@@ -575,7 +575,12 @@ constexpr int kSegTile = 64;
 constexpr int kSegThreads = 256;
 constexpr int kSegCols = kSegTile + FSEM_STOI_SEG - 1;  // 93 frames feed 64 segments
 constexpr int kSegPitch = 97;                            // odd pitch: conflict-free rows
-constexpr int kSegTilesPerCta = 4;                       // consecutive tiles per CTA, next tile prefetched into registers
+constexpr int kSegTilesPerCta = 4;
+#ifndef FSEM_SEG_RUN
+#define FSEM_SEG_RUN 4
+#endif
+constexpr int kSegRun = FSEM_SEG_RUN;                   // consecutive segments of one band per thread in part A
+static_assert(kSegTile % kSegRun == 0, "runs tile the segment tile");                       // consecutive tiles per CTA, next tile prefetched into registers
 
 __device__ __forceinline__ float rsqrt_or_zero(float v) { return v > 0.f ? rsqrtf(v) : 0.f; }
 // 1 / sqrt(v) for a centred second moment v = s2 - (sum)^2 / N computed from raw sums; 0 when v is not resolved against
@@ -642,44 +647,68 @@ stoi_segment_kernel(const float* __restrict__ tob, int64_t batch, int ustride, i
     __syncthreads();
     if (tk + 1 < kSegTilesPerCta && tile + 1 < ntiles && (m0 + kSegTile) < M) fetch(tile + 1, pre);
 
-    // ---- part A: per (segment, band) rows: STOI term + row statistics for ESTOI
+    // ---- part A: per (segment, band) rows: STOI term + row statistics for ESTOI.
+    // A thread takes kSegRun CONSECUTIVE segments of one band: their 30-frame rows overlap in all but kSegRun - 1 frames, so
+    // the 30 + kSegRun - 1 values are loaded from shared memory once (8 instead of 60 loads per segment) and the raw sums of
+    // the frames common to all of them are formed once; every segment adds its own kSegRun - 1 edge frames.  Additions
+    // only (no sliding subtraction): an all-zero or constant row still gives exactly zero moments.  The clipped pass
+    // depends on the segment's own alpha and is done in full.
     float stoi_acc = 0.f;
-    for (int id = tid; id < FSEM_STOI_NBANDS * kSegTile; id += kSegThreads) {
-        const int j = id / kSegTile, m = id - j * kSegTile;
-        if (m >= nseg) continue;
-        float x[FSEM_STOI_SEG], y[FSEM_STOI_SEG];
-        float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f;
+    constexpr int kRunsPerBand = kSegTile / kSegRun;
+    for (int id = tid; id < FSEM_STOI_NBANDS * kRunsPerBand; id += kSegThreads) {
+        const int j = id / kRunsPerBand, mb = (id - j * kRunsPerBand) * kSegRun;
+        if (mb >= nseg) continue;
+        float x[FSEM_STOI_SEG + kSegRun - 1], y[FSEM_STOI_SEG + kSegRun - 1];
 #pragma unroll
-        for (int q = 0; q < FSEM_STOI_SEG; ++q) {
-            x[q] = s_x[j][m + q];
-            y[q] = s_y[j][m + q];
-            sx += x[q]; sy += y[q];
-            sxx = fmaf(x[q], x[q], sxx);
-            syy = fmaf(y[q], y[q], syy);
+        for (int q = 0; q < FSEM_STOI_SEG + kSegRun - 1; ++q) {      // columns beyond the tile's last segment hold zeros
+            x[q] = s_x[j][mb + q];
+            y[q] = s_y[j][mb + q];
         }
-        // equalize_clip (STOI.py:129-139)
-        const float alpha = sqrtf(sxx) / (sqrtf(syy) + 1e-9f);
-        const float mx = sx * (1.f / FSEM_STOI_SEG), my = sy * (1.f / FSEM_STOI_SEG);
-        // Centred second moments from raw sums (sum (x - mx)^2 = sum x^2 - mx * sum x, ...): one pass over the clipped
-        // row instead of two, 10 instead of 18 operations per element -- this kernel is issue-bound.  In float32 the
-        // formula is less exact than subtracting the mean first, by ~eps * (1 + mean^2 / variance) per row: measured
-        // on speech-like and white-noise third-octave rows <= 2e-5 per (segment, band) term and <= 3e-7 in STOI
-        // (the bar is 1e-4; the two-pass form gave 7e-8).  Rows whose relative variance is below what the formula can
-        // resolve count as constant rows (contribution 0, like exactly constant rows before).
-        float syc = 0.f, sycc = 0.f, sxyc = 0.f;
+        float cx = 0.f, cy = 0.f, cxx = 0.f, cyy = 0.f;              // frames kSegRun - 1 .. 29: in every segment of the run
 #pragma unroll
-        for (int q = 0; q < FSEM_STOI_SEG; ++q) {
-            const float yc = fminf(y[q] * alpha, x[q] * clip);
-            syc += yc;
-            sycc = fmaf(yc, yc, sycc);
-            sxyc = fmaf(x[q], yc, sxyc);
+        for (int q = kSegRun - 1; q < FSEM_STOI_SEG; ++q) {
+            cx += x[q]; cy += y[q];
+            cxx = fmaf(x[q], x[q], cxx);
+            cyy = fmaf(y[q], y[q], cyy);
         }
-        const float myc = syc * (1.f / FSEM_STOI_SEG);
-        const float vxx = fmaf(-sx, mx, sxx), vyo = fmaf(-sy, my, syy);
-        const float vyy = fmaf(-syc, myc, sycc), vxy = fmaf(-sx, myc, sxyc);
-        const float rx = rsqrt_resolved(vxx, sxx), ry = rsqrt_resolved(vyy, sycc);
-        stoi_acc += vxy * rx * ry;                     // correlation of the normalised rows (STOI.py:174-175, 190)
-        s_row[m][j] = make_float4(mx, rx, my, rsqrt_resolved(vyo, syy));
+#pragma unroll
+        for (int r = 0; r < kSegRun; ++r) {
+            const int m = mb + r;
+            if (m < nseg) {
+                float sx = cx, sy = cy, sxx = cxx, syy = cyy;
+#pragma unroll
+                for (int e = 0; e < kSegRun - 1; ++e) {              // edge frames r .. kSegRun - 2 and 30 .. 29 + r
+                    const int q = (e < kSegRun - 1 - r) ? r + e : FSEM_STOI_SEG + e - (kSegRun - 1 - r);
+                    sx += x[q]; sy += y[q];
+                    sxx = fmaf(x[q], x[q], sxx);
+                    syy = fmaf(y[q], y[q], syy);
+                }
+                // equalize_clip (STOI.py:129-139)
+                const float alpha = sqrtf(sxx) / (sqrtf(syy) + 1e-9f);
+                const float mx = sx * (1.f / FSEM_STOI_SEG), my = sy * (1.f / FSEM_STOI_SEG);
+                // Centred second moments from raw sums (sum (x - mx)^2 = sum x^2 - mx * sum x, ...): one pass over the
+                // clipped row instead of two, 10 instead of 18 operations per element -- this kernel is issue-bound.  In
+                // float32 the formula is less exact than subtracting the mean first, by ~eps * (1 + mean^2 / variance)
+                // per row: measured on speech-like and white-noise third-octave rows <= 2e-5 per (segment, band) term
+                // and <= 3e-7 in STOI (the bar is 1e-4; the two-pass form gave 7e-8).  Rows whose relative variance is
+                // below what the formula can resolve count as constant rows (contribution 0, like exactly constant rows
+                // before).
+                float syc = 0.f, sycc = 0.f, sxyc = 0.f;
+#pragma unroll
+                for (int q = 0; q < FSEM_STOI_SEG; ++q) {
+                    const float yc = fminf(y[r + q] * alpha, x[r + q] * clip);
+                    syc += yc;
+                    sycc = fmaf(yc, yc, sycc);
+                    sxyc = fmaf(x[r + q], yc, sxyc);
+                }
+                const float myc = syc * (1.f / FSEM_STOI_SEG);
+                const float vxx = fmaf(-sx, mx, sxx), vyo = fmaf(-sy, my, syy);
+                const float vyy = fmaf(-syc, myc, sycc), vxy = fmaf(-sx, myc, sxyc);
+                const float rx = rsqrt_resolved(vxx, sxx), ry = rsqrt_resolved(vyy, sycc);
+                stoi_acc += vxy * rx * ry;             // correlation of the normalised rows (STOI.py:174-175, 190)
+                s_row[m][j] = make_float4(mx, rx, my, rsqrt_resolved(vyo, syy));
+            }
+        }
     }
     __syncthreads();
 
