@@ -266,23 +266,22 @@ pesq_filter_tiled_kernel(const T* __restrict__ clean, const T* __restrict__ deg,
     st.s1 = 0.f; st.s2 = 0.f;
     double acc_d = 0.0;
 
-    auto fetch = [&](int tt, float4 (&v)[8]) {
+    // the prefetch registers hold the samples as loaded (RawQuad): they are widened to float when the tile is filled
+    auto fetch = [&](int tt, RawQuad<T> (&v)[8]) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int a = tt + col;
             const int rl = rlen(i);
             const T* q = src_row(i) + tt;
             if (a + 4 <= rl) {
-                v[i] = load_samples4<true>(q);     // L2::256B hint: 4.46 -> 4.18 ms at 8192 x 10 s against a plain __ldg
+                v[i] = load_raw4<true>(q);         // L2::256B hint: 4.46 -> 4.18 ms at 8192 x 10 s against a plain __ldg
             } else {
-                v[i].x = (a < rl) ? load_sample(q) : 0.f;
-                v[i].y = (a + 1 < rl) ? load_sample(q + 1) : 0.f;
-                v[i].z = (a + 2 < rl) ? load_sample(q + 2) : 0.f;
-                v[i].w = (a + 3 < rl) ? load_sample(q + 3) : 0.f;
+                v[i] = raw_pack(load_raw1(q, a < rl), load_raw1(q + 1, a + 1 < rl), load_raw1(q + 2, a + 2 < rl),
+                                load_raw1(q + 3, a + 3 < rl), q);
             }
         }
     };
-    float4 pre[8];
+    RawQuad<T> pre[8];
     if (t < t_stop) fetch(t, pre);
     for (; t < t_stop; t += 32) {
         // fill the tile with the prefetched segment, then prefetch the next one
@@ -293,7 +292,7 @@ pesq_filter_tiled_kernel(const T* __restrict__ clean, const T* __restrict__ deg,
 #endif
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<float4*>(tile + ((lane >> 3) + 4 * i) * kFiltPitch + cs + col) = pre[i];
+            *reinterpret_cast<float4*>(tile + ((lane >> 3) + 4 * i) * kFiltPitch + cs + col) = raw_to_f4(pre[i]);
         __syncwarp();
         if (t + 32 < t_stop) fetch(t + 32, pre);
         // compute: lane owns row `lane`

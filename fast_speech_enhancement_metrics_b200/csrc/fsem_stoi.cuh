@@ -137,14 +137,15 @@ stoi_resample85_kernel(const T* __restrict__ clean, const T* __restrict__ deg,
     // sample indices fit 32 bits (n < 2^30, checked on the host): 64-bit index arithmetic and compares cost this
     // LSU / issue bound kernel ~15 % of its instructions
     const int len32 = len;
-    auto fetch = [&](int tile, float4 (&v)[kPerThread]) {
+    // the prefetch registers hold the samples as loaded (RawQuad): they are widened to float when the tile is filled
+    auto fetch = [&](int tile, RawQuad<T> (&v)[kPerThread]) {
         const int in0 = tile * kRs85TileIn - 12;                                  // first staged sample (multiple of 4)
         if (kVec4 && in0 >= 0 && in0 + 4 * kRs85Quads <= len32) {                 // interior tile (CTA-uniform): no checks
 #pragma unroll
             for (int r = 0; r < kPerThread; ++r) {
                 const int q = fill_q + r * kRs85Threads;
-                if (r + 1 < kPerThread || q < kRs85Quads) v[r] = load_samples4<false>(x + in0 + 4 * q);
-                else v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r + 1 < kPerThread || q < kRs85Quads) v[r] = load_raw4<false>(x + in0 + 4 * q);
+                else v[r] = raw_zero<T>();
             }
             return;
         }
@@ -152,18 +153,17 @@ stoi_resample85_kernel(const T* __restrict__ clean, const T* __restrict__ deg,
         for (int r = 0; r < kPerThread; ++r) {
             const int q = fill_q + r * kRs85Threads;
             const int i = in0 + 4 * q;
-            if (q >= kRs85Quads) { v[r] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+            if (q >= kRs85Quads) { v[r] = raw_zero<T>(); continue; }
             if (kVec4 && i >= 0 && i + 4 <= len32) {
-                v[r] = load_samples4<false>(x + i);
+                v[r] = load_raw4<false>(x + i);
             } else {
-                v[r].x = (i >= 0 && i < len32) ? load_sample(x + i) : 0.f;
-                v[r].y = (i + 1 >= 0 && i + 1 < len32) ? load_sample(x + i + 1) : 0.f;
-                v[r].z = (i + 2 >= 0 && i + 2 < len32) ? load_sample(x + i + 2) : 0.f;
-                v[r].w = (i + 3 >= 0 && i + 3 < len32) ? load_sample(x + i + 3) : 0.f;
+                v[r] = raw_pack(load_raw1(x + i, i >= 0 && i < len32), load_raw1(x + i + 1, i + 1 >= 0 && i + 1 < len32),
+                                load_raw1(x + i + 2, i + 2 >= 0 && i + 2 < len32),
+                                load_raw1(x + i + 3, i + 3 >= 0 && i + 3 < len32), x);
             }
         }
     };
-    float4 pre[kPerThread];
+    RawQuad<T> pre[kPerThread];
     fetch(tile0, pre);
     for (int k = 0; k < kRs85TilesPerCta; ++k) {
         const int tile = tile0 + k;
@@ -172,7 +172,7 @@ stoi_resample85_kernel(const T* __restrict__ clean, const T* __restrict__ deg,
 #pragma unroll
         for (int r = 0; r < kPerThread; ++r) {
             const int q = fill_q + r * kRs85Threads;
-            if (q < kRs85Quads) s_in[q + q / kRs85PadEvery] = pre[r];
+            if (q < kRs85Quads) s_in[q + q / kRs85PadEvery] = raw_to_f4(pre[r]);
         }
         __syncthreads();
         if (k + 1 < kRs85TilesPerCta && (out0 + kRs85TileOut) < L) fetch(tile + 1, pre);
