@@ -565,10 +565,25 @@ def main():
             roofline_call[call] = {"ms": call_ms, "achieved": alg_bytes / (call_ms * 1e-3) / 1e9, "peak": peak,
                                    "unit": "GB/s", "frac": alg_bytes / (call_ms * 1e-3) / 1e9 / peak,
                                    "algorithmic_bytes": alg_bytes, "traffic": tr}
+    # what binds the step: device time each resource is busy, summed over the kernels (utilisation from the round's
+    # `ncu --set full` capture x this run's kernel times; DRAM = the launch list's bytes at the measured copy bandwidth)
+    pipe_time = None
+    if pipe_files:
+        lsu = issue = 0.0
+        for k, v in kernels.items():
+            pk = pj.get(k)
+            if pk and v["ms_per_step"] > 0:
+                lsu += pk.get("lsu_data_pipe_pct", 0.0) / 100.0 * v["ms_per_step"]
+                issue += pk.get("issue_active_pct", 0.0) / 100.0 * v["ms_per_step"]
+        pipe_time = {"lsu_data_pipe_ms": lsu, "issue_slots_ms": issue, "source": os.path.relpath(pipe_files[-1], ROOT)}
+        if tj is not None:
+            tot = sum(tj.get("bytes_per_launch", {}).values()) * (local_b * args.seconds) / (tj.get("items", 8192) * 10.0)
+            pipe_time["dram_ms_at_measured_peak"] = tot / (peak * 1e9) * 1e3
+            pipe_time["dram_bytes_per_step"] = tot
     step_bytes = 2 * BYTES_PER_AUDIO_SECOND_PER_METRIC * local_audio_s
     roofline_step = {"achieved": step_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
-                     "algorithmic_bytes_per_step_per_gpu": step_bytes}
+                     "algorithmic_bytes_per_step_per_gpu": step_bytes, "resource_busy_ms": pipe_time}
 
     cpu = None
     if not args.no_cpu and world == 1:
