@@ -50,7 +50,8 @@ def main():
         f.writelines(lines)
     md = ["# ncu launch list of one step (8192 x 10 s, one B200): `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,"
           "dram__bytes_write.sum --clock-control none -k regex:\"pesq_|stoi_\" -s 30 -c 10 python bench.py --steps 1 "
-          "--warmup 3 --no-e2e --no-cpu`", "",
+          "--warmup 3 --no-e2e --no-cpu --no-parity --no-graph` (`--no-graph`: the same ten kernels launched directly on one "
+          "stream, so that the launch order under ncu is the chain order; the timed bench replays them as one CUDA graph)", "",
           "Cold-cache, serialised launches: compare SHARES with the live CUDA-event times in the same round's bench JSON "
           "(`kernels`).", "", "| kernel | time (us) | share | DRAM read (GB) | DRAM write (GB) |", "|---|---|---|---|---|"]
     traffic = {}
