@@ -387,9 +387,6 @@ extern "C" int fsem_pesq_create(fsem_pesq_ctx_t** out, const fsem_pesq_design_t*
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pesq_spectrum_kernel, kSpecWarps * 32, kSpecDynSmem) == cudaSuccess && occ > 0)
         ctx->spec_ctas_per_sm = occ;
-#ifdef FSEM_AB_SPEC_CTAS
-    ctx->spec_ctas_per_sm = FSEM_AB_SPEC_CTAS;
-#endif
     occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pesq_filter_tiled_kernel<false, float>, kFiltWarps * 32, 0) == cudaSuccess && occ > 0)
         ctx->filt_ctas_per_sm = occ;
@@ -667,9 +664,6 @@ extern "C" int fsem_stoi_create(fsem_stoi_ctx_t** out, const fsem_stoi_design_t*
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stoi_tob_kernel<true>, kTobWarps * 32, 0) == cudaSuccess && occ > 0)
         ctx->tob_ctas_per_sm = occ;
-#ifdef FSEM_AB_TOB_CTAS
-    ctx->tob_ctas_per_sm = FSEM_AB_TOB_CTAS;
-#endif
     *out = ctx;
     return FSEM_OK;
 }
