@@ -127,3 +127,56 @@ def test_graph_entry_points_validate_their_arguments_without_a_gpu():
     assert lib.fsem_graph_launch(None, None) == _lib.FSEM_E_INVALID
     assert lib.fsem_graph_nodes(None) == 0 and lib.fsem_graph_slices(None) == 0
     assert lib.fsem_graph_destroy(None) == _lib.FSEM_OK
+
+
+_C_CONSUMER = r"""
+#include <stddef.h>
+#include <stdio.h>
+#include <string.h>
+#include "fsem.h"
+int main(void) {
+    fsem_batch_t b;
+    memset(&b, 0, sizeof b);
+    printf("batch %zu %zu %zu %zu %zu %zu %zu\n", sizeof(fsem_batch_t), offsetof(fsem_batch_t, clean), offsetof(fsem_batch_t, deg),
+           offsetof(fsem_batch_t, lengths), offsetof(fsem_batch_t, batch), offsetof(fsem_batch_t, n), offsetof(fsem_batch_t, stride));
+    printf("pesq %zu %zu %zu %zu %zu\n", sizeof(fsem_pesq_design_t), offsetof(fsem_pesq_design_t, hann),
+           offsetof(fsem_pesq_design_t, band_first_bin), offsetof(fsem_pesq_design_t, sl), offsetof(fsem_pesq_design_t, rs_taps));
+    printf("stoi %zu %zu %zu %zu %zu\n", sizeof(fsem_stoi_design_t), offsetof(fsem_stoi_design_t, taps),
+           offsetof(fsem_stoi_design_t, window), offsetof(fsem_stoi_design_t, band_lo), offsetof(fsem_stoi_design_t, dyn_range));
+    printf("version %d %d\n", fsem_version(), FSEM_VERSION);
+    /* argument validation happens before any CUDA call: a C caller gets the error code and the message */
+    printf("null %d %s\n", fsem_pesq_score(NULL, &b, FSEM_DTYPE_F32, NULL, NULL, NULL, 0, NULL), fsem_last_error());
+    printf("ws %zu\n", fsem_sdr_workspace_bytes(0, 0));
+    return 0;
+}
+"""
+
+
+def test_header_is_plain_c_and_a_c_program_can_call_the_library(tmp_path):
+    """The drop-in boundary is a C ABI: include/fsem.h must compile as C99 (gcc -std=c99 -pedantic-errors), a C program
+    must link against the built library, and the struct layouts the C compiler sees must be the ones the Python mirror
+    (ctypes) uses.  No compute call (no GPU here): version, argument validation, a workspace query."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    lib_dir = os.path.dirname(_lib.LIB_PATH)
+    src = tmp_path / "consumer.c"
+    src.write_text(_C_CONSUMER)
+    exe = tmp_path / "consumer"
+    subprocess.run([gcc, "-std=c99", "-pedantic-errors", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-o", str(exe), "-L", lib_dir, "-l:" + os.path.basename(_lib.LIB_PATH), "-Wl,-rpath," + lib_dir],
+                   check=True, capture_output=True, text=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines()
+    rows = {ln.split()[0]: ln.split()[1:] for ln in out}
+    B, P, S = _lib.Batch, design.PesqDesign, design.StoiDesign
+    assert [int(v) for v in rows["batch"]] == [ctypes.sizeof(B), B.clean.offset, B.deg.offset, B.lengths.offset,
+                                               B.batch.offset, B.n.offset, B.stride.offset]
+    assert [int(v) for v in rows["pesq"]] == [ctypes.sizeof(P), P.hann.offset, P.band_first_bin.offset, P.sl.offset,
+                                              P.rs_taps.offset]
+    assert [int(v) for v in rows["stoi"]] == [ctypes.sizeof(S), S.taps.offset, S.window.offset, S.band_lo.offset,
+                                              S.dyn_range.offset]
+    assert rows["version"] == ["200", "200"]
+    assert int(rows["null"][0]) == -1 and len(rows["null"]) > 1          # FSEM_E_INVALID + a message
+    assert rows["ws"] == ["0"]
